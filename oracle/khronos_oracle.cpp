@@ -1,0 +1,1229 @@
+// ============================================================================
+// khronos_oracle.cpp — TEST INFRASTRUCTURE ONLY (parity oracle + CPU baseline)
+//
+// A CPU restatement, in plain C++ (templated on float/double), of the FDTD
+// time-step hot path of Khronos.jl and of the index maps it depends on.  It
+// is NOT part of the product: only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs may load it.  The product
+// (libkhronos_b200.so) never links, imports or calls anything in oracle/.
+//
+// The reference is Julia and cannot be executed in this container (no julia
+// binary, dependency closure un-vendored), so this is a *port*
+// (cpu_baseline.kind == "port").  Pinning status:
+//   * index maps (GridVolume, PML grid planner, adjacency, aux allocation
+//     pattern, sigma slicing), ADE coefficients, interpolation weights and
+//     source footprints are pinned against the reference's own known-answer
+//     tests (tests/golden/reference_tests.json, transcribed from
+//     /root/reference/test/*.jl with file:line).
+//   * field / DFT / flux VALUES after N steps are pinned by no reference test
+//     (test/test_timestep.jl:34-64 only checks !isnan) -> "parity unpinned"
+//     for values; they are anchored by (i) literal restatement with Julia's
+//     evaluation order and type promotion, (ii) single-chunk == chunked
+//     bit-equality, (iii) f32 -> f64 convergence, (iv) physics checks.
+//
+// Every function cites the reference file:line it restates (paths relative to
+// /root/reference).  Compile with -ffp-contract=off: Julia does not contract
+// a*b+c into FMA unless muladd/@fastmath is used, and none is on this path.
+// ============================================================================
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+namespace {
+
+enum Comp { EX = 0, EY = 1, EZ = 2, HX = 3, HY = 4, HZ = 5, CENTER = 6 };
+
+// ---------------------------------------------------------------------------
+// Dense 3-D array, column-major (x fastest) like Julia. Index is 0-based raw.
+// ---------------------------------------------------------------------------
+template <class T>
+struct Arr3 {
+  std::vector<T> d;
+  int nx = 0, ny = 0, nz = 0;
+  void alloc(int x, int y, int z) {
+    nx = x; ny = y; nz = z;
+    d.assign((size_t)x * y * z, T(0));
+  }
+  bool ok() const { return !d.empty(); }
+  inline T& at(int i, int j, int k) { return d[(size_t)i + (size_t)nx * ((size_t)j + (size_t)ny * k)]; }
+  inline const T& at(int i, int j, int k) const { return d[(size_t)i + (size_t)nx * ((size_t)j + (size_t)ny * k)]; }
+};
+
+// src/utils.jl:26-38 get_component_voxel_count: extra (staggered) cell per axis.
+inline void comp_stagger(int comp, int st[3]) {
+  static const int tab[7][3] = {
+      {0, 1, 1},  // Ex: (Nx, Ny+1, Nz+1)
+      {1, 0, 1},  // Ey
+      {1, 1, 0},  // Ez
+      {1, 0, 0},  // Hx
+      {0, 1, 0},  // Hy
+      {0, 0, 1},  // Hz
+      {0, 0, 0},  // Center
+  };
+  st[0] = tab[comp][0]; st[1] = tab[comp][1]; st[2] = tab[comp][2];
+}
+
+// Julia round(Int, x): ties to even (RoundNearest).
+inline long jl_round(double x) { return (long)std::nearbyint(x); }
+
+// src/utils.jl:486-541 _compute_interpolation_weight_fast
+double interp_weight(const double p3[3], const double lo3[3], const double hi3[3],
+                     const double sz3[3], int ndims, const double d3[3]) {
+  double weight = 1.0;
+  for (int dim = 0; dim < ndims; ++dim) {
+    double p = p3[dim], lo = lo3[dim], hi = hi3[dim], dl = d3[dim], sz = sz3[dim];
+    auto sq = [](double x) { return x * x; };
+    if ((p <= (lo - dl)) || (p >= (hi + dl))) {
+      return 0.0;
+    } else if (sz == 0.0) {
+      weight *= 1 - std::min(std::fabs(p - (lo + hi) * 0.5) / dl, 1.0);
+    } else if (sz < dl) {
+      if ((p >= lo) && (p <= hi)) {
+        weight *= 1 - 0.5 * sq(1.0 - (p - lo) / dl) - 0.5 * sq(1.0 - (hi - p) / dl);
+      } else if ((p <= lo) && (std::fabs(p - lo) < dl)) {
+        if (hi < (p + dl)) weight *= 0.5 * sq(1.0 - (lo - p) / dl) - 0.5 * sq(1.0 - (hi - p) / dl);
+        else weight *= 0.5 * sq(1.0 - (lo - p) / dl);
+      } else if ((p >= hi) && (std::fabs(p - hi) < dl)) {
+        if (lo > (p - dl)) weight *= 0.5 * sq(1.0 - (p - hi) / dl) - 0.5 * sq(1.0 - (p - lo) / dl);
+        else weight *= 0.5 * sq(1.0 - (p - hi) / dl);
+      }
+    } else {
+      if ((p < lo) && (std::fabs(p - lo) < dl)) weight *= 0.5 * sq(1.0 - (lo - p) / dl);
+      else if ((p >= lo) && (std::fabs(p - lo) < dl)) weight *= 1 - 0.5 * sq(1.0 - (p - lo) / dl);
+      else if ((p <= hi) && (std::fabs(p - hi) < dl)) weight *= 1 - 0.5 * sq(1.0 - (hi - p) / dl);
+      else if ((p > hi) && (std::fabs(p - hi) < dl)) weight *= 0.5 * sq(1.0 - (p - hi) / dl);
+    }
+  }
+  return weight;
+}
+
+// src/Susceptibility.jl:74-85 compute_ade_coefficients (Float64 math; dt is the
+// T-typed sim.Δt promoted to Float64).
+struct ADECoef {
+  double gamma1_inv, gamma1, omega0_dt_sq, sigma_omega0_dt_sq, drude_coeff;
+  int is_drude;
+};
+ADECoef ade_coefficients(double omega_0, double gamma, double dt) {
+  const double pi = 3.141592653589793;
+  ADECoef c;
+  double gamma_pi_dt = gamma * pi * dt;
+  c.gamma1 = 1.0 - gamma_pi_dt;
+  c.gamma1_inv = 1.0 / (1.0 + gamma_pi_dt);
+  double w = (2 * pi) * omega_0 * dt;
+  c.omega0_dt_sq = w * w;
+  c.sigma_omega0_dt_sq = c.omega0_dt_sq;
+  c.drude_coeff = gamma * (2 * pi) * dt * dt;
+  c.is_drude = (omega_0 == 0.0) ? 1 : 0;
+  return c;
+}
+
+// ---------------------------------------------------------------------------
+// Chunk plan pieces (integers only)
+// ---------------------------------------------------------------------------
+struct Region { int s[3], e[3]; };
+struct Flags { int pml[3]; };
+
+// src/Chunking.jl:570-603 _compute_adjacency
+void compute_adjacency(const std::vector<Region>& ch, int ndims, std::vector<int>& out /* (i,j,axis) 1-based */) {
+  int n = (int)ch.size();
+  for (int i = 0; i < n; ++i)
+    for (int j = i + 1; j < n; ++j)
+      for (int axis = 0; axis < ndims; ++axis) {
+        bool touches = (ch[i].e[axis] == ch[j].s[axis] - 1) || (ch[j].e[axis] == ch[i].s[axis] - 1);
+        if (!touches) continue;
+        bool ov = true;
+        for (int o = 0; o < ndims; ++o) {
+          if (o == axis) continue;
+          if (ch[i].e[o] < ch[j].s[o] || ch[j].e[o] < ch[i].s[o]) { ov = false; break; }
+        }
+        if (ov) { out.push_back(i + 1); out.push_back(j + 1); out.push_back(axis + 1); }
+      }
+}
+
+// src/Chunking.jl:1863-1909 _make_overlap_halo_ranges. Ranges are (first,last)
+// pairs in each chunk's local cell indices (ghost = 0 or N+1).
+void overlap_halo_ranges(const Region& src, const Region& dst, int axis, bool src_upper, bool dst_lower,
+                         int sr[6], int dr[6]) {
+  int sd[3], dd[3];
+  for (int d = 0; d < 3; ++d) {
+    sd[d] = std::max(1, src.e[d] - src.s[d] + 1);
+    dd[d] = std::max(1, dst.e[d] - dst.s[d] + 1);
+    sr[2 * d] = 1; sr[2 * d + 1] = sd[d];
+    dr[2 * d] = 1; dr[2 * d + 1] = dd[d];
+  }
+  if (src_upper) { sr[2 * axis] = sd[axis]; sr[2 * axis + 1] = sd[axis]; }
+  else { sr[2 * axis] = 1; sr[2 * axis + 1] = 1; }
+  if (dst_lower) { dr[2 * axis] = 0; dr[2 * axis + 1] = 0; }
+  else { dr[2 * axis] = dd[axis] + 1; dr[2 * axis + 1] = dd[axis] + 1; }
+  for (int d = 0; d < 3; ++d) {
+    if (d == axis) continue;
+    int os = std::max(src.s[d], dst.s[d]);
+    int oe = std::min(src.e[d], dst.e[d]);
+    if (os > oe) { sr[2 * d] = 1; sr[2 * d + 1] = 0; dr[2 * d] = 1; dr[2 * d + 1] = 0; }
+    else {
+      sr[2 * d] = os - src.s[d] + 1; sr[2 * d + 1] = oe - src.s[d] + 1;
+      dr[2 * d] = os - dst.s[d] + 1; dr[2 * d + 1] = oe - dst.s[d] + 1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Time sources (src/Sources/TimeSources.jl:61-64, 123-132)
+// ---------------------------------------------------------------------------
+template <class T>
+struct TimeSrc {
+  int kind = 0;  // 0 = CW, 1 = Gaussian pulse
+  T fcen = 0, width = 0, peak_time = 0, cutoff = 0;
+};
+
+template <class T>
+std::complex<T> eval_time_source(const TimeSrc<T>& s, double t) {
+  const T pi_T = (T)3.141592653589793;
+  if (s.kind == 0) {
+    // exp(-Complex{T}(im) * T(2) * T(π) * fcen * T(t)): every factor multiplies
+    // the imaginary part left to right in T.
+    T im = -T(1);
+    im = im * T(2);
+    im = im * pi_T;
+    im = im * s.fcen;
+    im = im * (T)t;
+    return std::complex<T>((T)std::cos((double)im), (T)std::sin((double)im));
+  } else {
+    T tt = (T)t - s.peak_time;
+    if (tt > s.cutoff) return std::complex<T>(0, 0);
+    T two_pi = T(2) * pi_T;
+    T env_arg = (-tt * tt) / (T(2) * s.width * s.width);
+    T env = (T)std::exp((double)env_arg);
+    T im = -two_pi;  // -two_pi * Complex(im) -> imaginary part -two_pi
+    im = im * s.fcen;
+    im = im * tt;
+    std::complex<T> ph((T)std::cos((double)im), (T)std::sin((double)im));
+    return std::complex<T>(env * ph.real(), env * ph.imag());
+  }
+}
+
+// ---------------------------------------------------------------------------
+// The simulation object
+// ---------------------------------------------------------------------------
+template <class T>
+struct Pole {
+  ADECoef c;
+  Arr3<T> sigma;  // global (Nx,Ny,Nz), shared by x/y/z (src/Geometry.jl:1291-1302)
+};
+
+template <class T>
+struct Source {
+  int comp;
+  int start[3], dims[3];
+  std::vector<std::complex<T>> amp;  // dims, column-major
+  TimeSrc<T> ts;
+};
+
+template <class T>
+struct DFTMon {
+  int comp;
+  int start[3], end[3], n[3];
+  std::vector<T> freqs;
+  int decimation;
+  std::vector<std::complex<T>> M;  // (nx,ny,nz,nf)
+};
+
+template <class T>
+struct Chunk {
+  int s[3], n[3];
+  bool pml[3] = {false, false, false};
+  // raw field arrays with ghost layers; dims = n + stagger + 2 (src/Chunking.jl:1053-1061)
+  Arr3<T> E[3], H[3], B[3], D[3];
+  Arr3<T> CB[3], UB[3], WB[3], CD[3], UD[3], WD[3];
+  Arr3<T> SB[3], SD[3], PD[3];
+  std::vector<T> sig[2][3];  // [0]=B group, [1]=D group; empty == `nothing`
+  // per-pole state (src/Geometry.jl:1278-1303)
+  std::vector<Arr3<T>> P[3], Pp[3];
+};
+
+template <class T>
+struct Sim {
+  // --- user parameters -----------------------------------------------------
+  double cell_size_u[3], cell_center[3], resolution, courant;
+  bool has_boundaries = false;
+  T pml[3][2];
+  // --- derived grid (src/DataStructures.jl:732-741) -------------------------
+  int N[3];
+  T cell_size[3], dl[3], dt;
+  // --- boundary data (src/Boundaries.jl:99-164) -----------------------------
+  std::vector<T> sigma[2][3];  // [group][axis], length 2N+1; empty == nothing
+  // --- materials (global, cells 1..N only; gidx never exceeds N) ------------
+  bool eps_is_array = false, mu_is_array = false;
+  T eps_inv = 1, mu_inv = 1;
+  Arr3<T> eps_inv_a[3], mu_inv_a[3];
+  Arr3<T> sigD[3], sigB[3];  // material conductivity; !ok() == nothing
+  std::vector<Pole<T>> poles;
+  std::vector<Source<T>> sources;
+  std::vector<DFTMon<T>> monitors;
+  // --- runtime ---------------------------------------------------------------
+  int mode = 0;  // 0: single chunk, literal KA dispatch; 1: PML-grid chunks, canonical cascade
+  std::vector<Chunk<T>> chunks;
+  std::vector<Region> regions;
+  std::vector<int> adjacency;
+  long timestep = 0;
+  bool sources_active = true;
+  bool prepared = false;
+  int nthreads = 0;
+
+  void derive_grid() {
+    for (int a = 0; a < 3; ++a) {
+      N[a] = (int)std::floor(cell_size_u[a] * resolution);
+      cell_size[a] = (T)cell_size_u[a];
+      dl[a] = (T)(cell_size_u[a] / (double)N[a]);
+    }
+    T m = std::min(dl[0], std::min(dl[1], dl[2]));
+    dt = (T)((double)m * courant);
+  }
+
+  // src/Boundaries.jl:23-38 sigma_helper; :64-72 compute_sigma
+  T sigma_helper(int idx, int Ns, T dx, T Dt, T length_left, T length_right) const {
+    auto u0 = [&](T pml_length) -> double {
+      T den = T(4) * pml_length;  // 4 * L * 1 / 3 evaluated left to right in T
+      den = den * T(1);
+      den = den / T(3);
+      return (-std::log(1e-15) / (double)den) * (0.5 * (double)Dt);
+    };
+    auto u = [&](T x) -> double {
+      T x2 = x * x;
+      T sgn = (x > 0) ? T(1) : ((x < 0) ? T(-1) : T(0));
+      return ((double)x2 * 0.5) * (double)(sgn + T(1));
+    };
+    T total_length = (T)Ns * dx / T(2);
+    T real_idx = (T)idx * dx / T(2);
+    if (real_idx < length_left) {
+      return (T)(u0(length_left) * u((length_left - real_idx) / length_left));
+    } else if ((total_length - real_idx) < length_right) {
+      return (T)(u0(length_right) * u((length_right - (total_length - real_idx)) / length_right));
+    }
+    return T(0);
+  }
+  std::vector<T> compute_sigma(int Ns, T dx, T Dt, T ll, T lr) const {
+    std::vector<T> s((size_t)Ns, T(0));
+    if ((ll != T(0)) || (lr != T(0)))
+      for (int idx = 1; idx <= Ns; ++idx) s[idx - 1] = sigma_helper(idx, Ns, dx, Dt, ll, lr);
+    return s;
+  }
+  void init_boundaries() {
+    for (int g = 0; g < 2; ++g)
+      for (int a = 0; a < 3; ++a) sigma[g][a].clear();
+    if (!has_boundaries) return;
+    for (int g = 0; g < 2; ++g)
+      for (int a = 0; a < 3; ++a) sigma[g][a] = compute_sigma(2 * N[a] + 1, dl[a], dt, pml[a][0], pml[a][1]);
+  }
+
+  // src/utils.jl:139-170 yee shift (Float64 SVector built from T-typed halves)
+  void yee_shift(int comp, double sh[3]) const {
+    int st[3];
+    comp_stagger(comp, st);
+    // A component is shifted by -Δ/2 along exactly the axes where it has the
+    // extra staggered cell... except the pairing in utils.jl:139-154:
+    //   Ex: (0,-Δy/2,-Δz/2)  Ey: (-Δx/2,0,-Δz/2)  Ez: (-Δx/2,-Δy/2,0)
+    //   Hx: (-Δx/2,0,0)      Hy: (0,-Δy/2,0)      Hz: (0,0,-Δz/2)
+    for (int a = 0; a < 3; ++a) sh[a] = st[a] ? (double)(-dl[a] / T(2)) : 0.0;
+  }
+  // src/utils.jl:156-170 get_component_origin
+  void component_origin(int comp, double o[3]) const {
+    double sh[3];
+    yee_shift(comp, sh);
+    for (int a = 0; a < 3; ++a) {
+      // cell_center (Float64) - cell_size (T) / 2 + Δ (T) / 2
+      double v = cell_center[a] - (double)(cell_size[a] / T(2));
+      v = v + (double)(dl[a] / T(2));
+      o[a] = v + sh[a];
+    }
+  }
+  // src/utils.jl:176-195 get_grid_idx; :201-211 lower/upper; :103-113 GridVolume
+  void grid_idx(const double point[3], int comp, double out[3]) const {
+    double sh[3];
+    yee_shift(comp, sh);
+    for (int a = 0; a < 3; ++a) {
+      double vmin = cell_center[a] - (double)(cell_size[a] / T(2));
+      double vmax = cell_center[a] + (double)(cell_size[a] / T(2));
+      double c2c = (double)(dl[a] / T(2));
+      double mn = (vmin + c2c) + sh[a];
+      double mx = (vmax - c2c) - sh[a];
+      double p = std::min(point[a], mx);
+      p = std::max(p, mn);
+      double idx = (p - mn) / (double)dl[a] + 1;
+      if (std::isnan(idx)) idx = 0;
+      out[a] = idx;
+    }
+  }
+  void grid_volume(const double center[3], const double size[3], int comp, int s[3], int e[3]) const {
+    double lo[3], hi[3], a[3], b[3];
+    for (int d = 0; d < 3; ++d) { lo[d] = center[d] - size[d] / 2; hi[d] = center[d] + size[d] / 2; }
+    grid_idx(lo, comp, a);
+    grid_idx(hi, comp, b);
+    for (int d = 0; d < 3; ++d) { s[d] = (int)std::floor(a[d]); e[d] = (int)std::ceil(b[d]); }
+  }
+
+  // src/Chunking.jl:622-737 _pml_grid_regions (3-D). nranks>0 == is_distributed().
+  std::vector<Region> pml_grid_regions(int nranks) const {
+    std::vector<std::pair<int, int>> iv[3];
+    for (int a = 0; a < 3; ++a) {
+      T pl = has_boundaries ? pml[a][0] : T(0), pr = has_boundaries ? pml[a][1] : T(0);
+      int left_end = (pl > T(0)) ? (int)std::ceil(pl / dl[a]) : 0;
+      int right_start = (pr > T(0)) ? N[a] - (int)std::ceil(pr / dl[a]) + 1 : N[a] + 1;
+      if (left_end >= 1) iv[a].push_back({1, left_end});
+      int is = left_end + 1, ie = right_start - 1;
+      if (is <= ie) iv[a].push_back({is, ie});
+      if (right_start <= N[a]) iv[a].push_back({right_start, N[a]});
+      if (iv[a].empty()) iv[a].push_back({1, N[a]});
+    }
+    if (nranks > 0) {
+      int best_axis = -1, best_len = 0;
+      for (int a = 0; a < 3; ++a)
+        for (auto& p : iv[a])
+          if (p.first > 1 && p.second < N[a]) {
+            int len = p.second - p.first + 1;
+            if (len > best_len) { best_len = len; best_axis = a; }
+          }
+      if (best_axis >= 0 && best_len > 0) {
+        std::vector<std::pair<int, int>> nv;
+        for (auto& p : iv[best_axis]) {
+          int s = p.first, e = p.second;
+          if (s > 1 && e < N[best_axis] && (e - s + 1) == best_len) {
+            int total = e - s + 1;
+            for (int k = 1; k <= nranks; ++k) {
+              int ss = s + (int)jl_round((double)((long)(k - 1) * total) / nranks);
+              int se = s + (int)jl_round((double)((long)k * total) / nranks) - 1;
+              if (ss <= se) nv.push_back({ss, se});
+            }
+          } else nv.push_back(p);
+        }
+        iv[best_axis] = nv;
+      }
+    }
+    std::vector<Region> out;
+    for (auto& x : iv[0])
+      for (auto& y : iv[1])
+        for (auto& z : iv[2]) {
+          Region r;
+          r.s[0] = x.first; r.e[0] = x.second;
+          r.s[1] = y.first; r.e[1] = y.second;
+          r.s[2] = z.first; r.e[2] = z.second;
+          out.push_back(r);
+        }
+    return out;
+  }
+  // src/Chunking.jl:108-138 _pml_overlaps_chunk_axis
+  bool pml_overlaps_axis(const Region& r, int a) const {
+    if (!has_boundaries) return false;
+    T pl = pml[a][0], pr = pml[a][1];
+    if (pl == T(0) && pr == T(0)) return false;
+    int left_end = (pl > T(0)) ? (int)std::ceil(pl / dl[a]) : 0;
+    int right_start = (pr > T(0)) ? N[a] - (int)std::ceil(pr / dl[a]) + 1 : N[a] + 1;
+    if (left_end > 0 && r.s[a] <= left_end) return true;
+    if (right_start <= N[a] && r.e[a] >= right_start) return true;
+    return false;
+  }
+
+  // src/Geometry.jl:708-789 _apply_absorbers! — σ arrays are component sized
+  // (N_axis = N + stagger); only cells <= N are ever read by the kernels.
+  void apply_absorber(int axis, int side /*0 left,1 right*/, int num_layers, int p, double sigma_max_in) {
+    T L = (T)num_layers * dl[axis];
+    T sigma_max = (sigma_max_in > 0) ? (T)sigma_max_in : (T)(-(double)(p + 1) * std::log(1e-6) / (2.0 * (double)L));
+    for (int g = 0; g < 2; ++g)
+      for (int c = 0; c < 3; ++c) {
+        Arr3<T>& arr = (g == 0) ? sigD[c] : sigB[c];
+        if (!arr.ok()) arr.alloc(N[0], N[1], N[2]);
+        int st[3];
+        comp_stagger(g == 0 ? c : 3 + c, st);
+        int N_axis = N[axis] + st[axis];
+        for (int layer = 1; layer <= std::min(num_layers, N_axis); ++layer) {
+          double dn = (double)(num_layers - layer + 1) / (double)num_layers;
+          T val = (T)((double)sigma_max * std::pow(dn, p));
+          int idx = (side == 1) ? (N_axis - layer + 1) : layer;
+          if (idx > N[axis]) continue;  // outside the cells the kernels read
+          int a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
+          for (int v = 0; v < N[a2]; ++v)
+            for (int u = 0; u < N[a1]; ++u) {
+              int q[3];
+              q[axis] = idx - 1; q[a1] = u; q[a2] = v;
+              arr.at(q[0], q[1], q[2]) += val;
+            }
+        }
+      }
+  }
+
+  // ------------------------------------------------------------------------
+  // preparation: allocate chunks (src/Chunking.jl:1069-1146, 1355-1378)
+  // ------------------------------------------------------------------------
+  bool any_sigD() const { return sigD[0].ok() || sigD[1].ok() || sigD[2].ok(); }
+  bool any_sigB() const { return sigB[0].ok() || sigB[1].ok() || sigB[2].ok(); }
+
+  void alloc_field(Arr3<T>& a, int comp, const int n[3]) {
+    int st[3];
+    comp_stagger(comp, st);
+    a.alloc(n[0] + st[0] + 2, n[1] + st[1] + 2, n[2] + st[2] + 2);
+  }
+
+  void prepare(int mode_, int nranks) {
+    mode = mode_;
+    init_boundaries();
+    chunks.clear();
+    regions.clear();
+    adjacency.clear();
+    if (mode == 0 || !has_boundaries) {
+      Region r;
+      for (int a = 0; a < 3; ++a) { r.s[a] = 1; r.e[a] = N[a]; }
+      regions.push_back(r);
+    } else {
+      regions = pml_grid_regions(nranks);
+      compute_adjacency(regions, 3, adjacency);
+    }
+    bool src_comp[6] = {false, false, false, false, false, false};
+    for (auto& s : sources) src_comp[s.comp] = true;
+    for (auto& r : regions) {
+      Chunk<T> c;
+      for (int a = 0; a < 3; ++a) { c.s[a] = r.s[a]; c.n[a] = r.e[a] - r.s[a] + 1; }
+      bool single = (regions.size() == 1 && mode == 0);
+      for (int a = 0; a < 3; ++a) c.pml[a] = single ? has_boundaries : pml_overlaps_axis(r, a);
+      bool anyp = c.pml[0] || c.pml[1] || c.pml[2];
+      for (int d = 0; d < 3; ++d) {
+        alloc_field(c.E[d], d, c.n);
+        alloc_field(c.D[d], d, c.n);
+        alloc_field(c.H[d], 3 + d, c.n);
+        alloc_field(c.B[d], 3 + d, c.n);
+        int nx = (d + 1) % 3, pv = (d + 2) % 3;
+        // U <=> PML on next axis; W <=> PML on own axis; C <=> sigma && (next||prev)
+        if (c.pml[nx]) { alloc_field(c.UB[d], 3 + d, c.n); alloc_field(c.UD[d], d, c.n); }
+        if (c.pml[d]) { alloc_field(c.WB[d], 3 + d, c.n); alloc_field(c.WD[d], d, c.n); }
+        if (any_sigB() && (c.pml[nx] || c.pml[pv])) alloc_field(c.CB[d], 3 + d, c.n);
+        if (any_sigD() && (c.pml[nx] || c.pml[pv])) alloc_field(c.CD[d], d, c.n);
+        if (src_comp[d]) alloc_field(c.SD[d], d, c.n);
+        if (src_comp[3 + d]) alloc_field(c.SB[d], 3 + d, c.n);
+        if (!poles.empty()) {
+          // fPD sized (nr+2)^3 (src/Geometry.jl:1259-1269)
+          c.PD[d].alloc(c.n[0] + 2, c.n[1] + 2, c.n[2] + 2);
+          c.P[d].resize(poles.size());
+          c.Pp[d].resize(poles.size());
+          for (size_t p = 0; p < poles.size(); ++p) {
+            c.P[d][p].alloc(c.n[0] + 2, c.n[1] + 2, c.n[2] + 2);
+            c.Pp[d][p].alloc(c.n[0] + 2, c.n[1] + 2, c.n[2] + 2);
+          }
+        }
+      }
+      // sigma: single chunk shares global arrays; PML chunks get local slices
+      // (src/Chunking.jl:1333-1345) with zero vectors on non-PML axes
+      // (:1366-1377); non-PML chunks get nothing.
+      if (single) {
+        for (int g = 0; g < 2; ++g)
+          for (int a = 0; a < 3; ++a) c.sig[g][a] = sigma[g][a];
+      } else if (anyp) {
+        for (int g = 0; g < 2; ++g)
+          for (int a = 0; a < 3; ++a) {
+            std::vector<T> loc((size_t)2 * c.n[a] + 1, T(0));
+            if (c.pml[a])
+              for (int i = 1; i <= c.n[a]; ++i) {
+                int gi = 2 * (i + c.s[a] - 1) - 1;
+                if (gi >= 1 && gi <= (int)sigma[g][a].size()) loc[2 * i - 2] = sigma[g][a][gi - 1];
+              }
+            c.sig[g][a] = loc;
+          }
+      }
+      chunks.push_back(std::move(c));
+    }
+    for (auto& m : monitors) m.M.assign((size_t)m.n[0] * m.n[1] * m.n[2] * m.freqs.size(), std::complex<T>(0, 0));
+    timestep = 0;
+    sources_active = true;
+    prepared = true;
+  }
+
+  // ------------------------------------------------------------------------
+  // Kernels. `update_field_from_curl` (src/Kernels/Helpers.jl:30-33)
+  // ------------------------------------------------------------------------
+  static inline T upd(T A, T Bv, T B_old, T s) { return (((T(1) - s) * A + Bv) - B_old) / (T(1) + s); }
+  static inline T upd_noold(T A, T Bv, T s) { return ((T(1) - s) * A + Bv) / (T(1) + s); }
+
+  // Literal single-chunk dispatch of generic_curl! (src/Kernels/Helpers.jl:39-270)
+  // for the Nothing-patterns that occur in single-chunk mode:
+  //   C,U arrays + σD value            -> :39-69
+  //   C nothing, U array, σD nothing   -> :113-139
+  //   C,U nothing, σ_next/σ_prev nothing, σD value -> :141-154
+  //   all nothing                      -> :188-201
+  static inline T generic_curl_literal(T K, T* C, T* U, T* Tf, bool has_sD, T sD, bool has_pml_sigma, T sn, T sp) {
+    if (C && U) {
+      if (sD == T(0)) {
+        T U_old = *U;
+        *U = upd_noold(*U, K, sn);
+        T Tn = upd(*Tf, *U, U_old, sp);
+        *Tf = Tn;
+        return Tn;
+      } else {
+        T C_old = *C;
+        *C = upd_noold(*C, K, sD);
+        T U_old = *U;
+        *U = upd(*U, *C, C_old, sn);
+        T Tn = upd(*Tf, *U, U_old, sp);
+        *Tf = Tn;
+        return Tn;
+      }
+    }
+    if (!C && U) {
+      if (sn == T(0)) {
+        T Tn = upd_noold(*Tf, K, sp);
+        *Tf = Tn;
+        return Tn;
+      } else {
+        T U_old = *U;
+        *U = upd_noold(*U, K, sn);
+        T Tn = upd(*Tf, *U, U_old, sp);
+        *Tf = Tn;
+        return Tn;
+      }
+    }
+    (void)has_pml_sigma;
+    if (has_sD) {
+      T Tn = upd_noold(*Tf, K, sD);
+      *Tf = Tn;
+      return Tn;
+    }
+    T Tn = *Tf + K;
+    *Tf = Tn;
+    return Tn;
+  }
+
+  // Canonical, value-driven cascade (SURVEY §8(c') decisions 1-3): the complete
+  // C -> U -> T cascade the raw CUDA PML kernels apply from flags
+  // (src/Kernels/CUDAKernels.jl:153-177), extended with the material-σ C stage
+  // of Helpers.jl:60-68. Used in chunked mode, where aux arrays exist only
+  // where the chunk flags say so.
+  static inline T generic_curl_canonical(T K, T* C, T* U, T* Tf, T sD, T sn, T sp) {
+    T in = K;
+    if (sD != T(0)) {
+      if (sn != T(0) || sp != T(0)) {  // a PML stage follows: C exists by the allocation rule
+        T C_old = *C;
+        *C = upd_noold(*C, K, sD);
+        in = *C - C_old;
+      } else {
+        T Tn = upd_noold(*Tf, K, sD);
+        *Tf = Tn;
+        return Tn;
+      }
+    }
+    if (sn != T(0) && U) {
+      T U_old = *U;
+      *U = upd_noold(*U, in, sn);
+      in = *U - U_old;
+    }
+    T Tn = (sp != T(0)) ? upd_noold(*Tf, in, sp) : (*Tf + in);
+    *Tf = Tn;
+    return Tn;
+  }
+
+  inline T mat(bool is_arr, T scalar, const Arr3<T>* a, int d, const Chunk<T>& c, int ix, int iy, int iz) const {
+    if (!is_arr) return scalar;
+    return a[d].at(c.s[0] + ix - 2, c.s[1] + iy - 2, c.s[2] + iz - 2);
+  }
+
+  // step_curl! (src/Kernels/ReferenceKernels.jl:276-313) for one chunk.
+  // group 0: B from E (idx_curl=+1); group 1: D from H (idx_curl=-1).
+  void step_curl(Chunk<T>& c, int group) {
+    const int ic = (group == 0) ? 1 : -1;
+    Arr3<T>* A = (group == 0) ? c.E : c.H;
+    Arr3<T>* Tf = (group == 0) ? c.B : c.D;
+    Arr3<T>* Cf = (group == 0) ? c.CB : c.CD;
+    Arr3<T>* Uf = (group == 0) ? c.UB : c.UD;
+    const Arr3<T>* sgm = (group == 0) ? sigB : sigD;
+    const std::vector<T>* sg = c.sig[group];
+    const bool has_pml_sigma = !sg[0].empty();
+    const T Dt = dt;
+    const T idx_ = T(1) / dl[0], idy_ = T(1) / dl[1], idz_ = T(1) / dl[2];
+    const int mode_l = mode;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int iz = 1; iz <= c.n[2]; ++iz)
+      for (int iy = 1; iy <= c.n[1]; ++iy)
+        for (int ix = 1; ix <= c.n[0]; ++ix) {
+          const int fx = ix, fy = iy, fz = iz;  // 0-based raw == Julia (ix+1)-1
+          // curl (src/Kernels/Helpers.jl:286-298); K = Δt * curl
+          T dAy_dz = idz_ * (A[1].at(fx, fy, fz + ic) - A[1].at(fx, fy, fz));
+          T dAz_dy = idy_ * (A[2].at(fx, fy + ic, fz) - A[2].at(fx, fy, fz));
+          T dAz_dx = idx_ * (A[2].at(fx + ic, fy, fz) - A[2].at(fx, fy, fz));
+          T dAx_dz = idz_ * (A[0].at(fx, fy, fz + ic) - A[0].at(fx, fy, fz));
+          T dAx_dy = idy_ * (A[0].at(fx, fy + ic, fz) - A[0].at(fx, fy, fz));
+          T dAy_dx = idx_ * (A[1].at(fx + ic, fy, fz) - A[1].at(fx, fy, fz));
+          T K[3] = {Dt * (dAy_dz - dAz_dy), Dt * (dAz_dx - dAx_dz), Dt * (dAx_dy - dAy_dx)};
+          const int li[3] = {ix, iy, iz};
+          for (int d = 0; d < 3; ++d) {
+            int nx = (d + 1) % 3, pv = (d + 2) % 3;
+            bool has_sD = sgm[d].ok();
+            // get_σD: scale_by_half(Δt * σD[idx]) (Helpers.jl:273-279)
+            T sD = has_sD ? (T)0.5 * (Dt * sgm[d].at(c.s[0] + ix - 2, c.s[1] + iy - 2, c.s[2] + iz - 2)) : T(0);
+            T sn = has_pml_sigma ? sg[nx][2 * li[nx] - 2] : T(0);
+            T sp = has_pml_sigma ? sg[pv][2 * li[pv] - 2] : T(0);
+            T* Cp = Cf[d].ok() ? &Cf[d].at(fx, fy, fz) : nullptr;
+            T* Up = Uf[d].ok() ? &Uf[d].at(fx, fy, fz) : nullptr;
+            T* Tp = &Tf[d].at(fx, fy, fz);
+            if (mode_l == 0) generic_curl_literal(K[d], Cp, Up, Tp, has_sD, sD, has_pml_sigma, sn, sp);
+            else generic_curl_canonical(K[d], Cp, Up, Tp, sD, sn, sp);
+          }
+        }
+  }
+
+  // update_field! (src/Kernels/ReferenceKernels.jl:468-512) + update_field_generic
+  // (src/Kernels/Helpers.jl:323-366)
+  void update_field(Chunk<T>& c, int group) {
+    Arr3<T>* A = (group == 0) ? c.H : c.E;
+    Arr3<T>* Tf = (group == 0) ? c.B : c.D;
+    Arr3<T>* Wf = (group == 0) ? c.WB : c.WD;
+    Arr3<T>* Sf = (group == 0) ? c.SB : c.SD;
+    Arr3<T>* Pf = (group == 0) ? nullptr : c.PD;
+    const std::vector<T>* sg = c.sig[group];
+    const bool has_pml_sigma = !sg[0].empty();
+    const bool m_arr = (group == 0) ? mu_is_array : eps_is_array;
+    const T m_sc = (group == 0) ? mu_inv : eps_inv;
+    const Arr3<T>* m_a = (group == 0) ? mu_inv_a : eps_inv_a;
+    const bool sa = sources_active;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int iz = 1; iz <= c.n[2]; ++iz)
+      for (int iy = 1; iy <= c.n[1]; ++iy)
+        for (int ix = 1; ix <= c.n[0]; ++ix) {
+          const int li[3] = {ix, iy, iz};
+          for (int d = 0; d < 3; ++d) {
+            T m_inv = mat(m_arr, m_sc, m_a, d, c, ix, iy, iz);
+            T net = Tf[d].at(ix, iy, iz);
+            if (sa && Sf[d].ok()) net += Sf[d].at(ix, iy, iz);
+            if (Pf && Pf[d].ok()) net -= Pf[d].at(ix, iy, iz);
+            if (sa && Sf[d].ok()) Sf[d].at(ix, iy, iz) = T(0);
+            bool w_path = Wf[d].ok() && has_pml_sigma;
+            if (w_path) {
+              T s = sg[d][2 * li[d] - 2];
+              if (s == T(0)) {
+                A[d].at(ix, iy, iz) = m_inv * net;
+              } else {
+                T W_old = Wf[d].at(ix, iy, iz);
+                T Wn = m_inv * net;
+                Wf[d].at(ix, iy, iz) = Wn;
+                A[d].at(ix, iy, iz) = (A[d].at(ix, iy, iz) + (T(1) + s) * Wn) - (T(1) - s) * W_old;
+              }
+            } else {
+              A[d].at(ix, iy, iz) = m_inv * net;
+            }
+          }
+        }
+  }
+
+  // Halo exchange between chunks (src/Chunking.jl:1657-1699, 2106-2172): all
+  // three components of the group, both directions, per adjacency.
+  void exchange_halos(int group) {
+    for (size_t q = 0; q + 2 < adjacency.size(); q += 3) {
+      int i = adjacency[q] - 1, j = adjacency[q + 1] - 1, axis = adjacency[q + 2] - 1;
+      for (int dir = 0; dir < 2; ++dir) {
+        int si = dir == 0 ? i : j, di = dir == 0 ? j : i;
+        int sr[6], dr[6];
+        overlap_halo_ranges(regions[si], regions[di], axis, dir == 0, dir == 0, sr, dr);
+        for (int d = 0; d < 3; ++d) {
+          Arr3<T>& S = (group == 0) ? chunks[si].H[d] : chunks[si].E[d];
+          Arr3<T>& Dd = (group == 0) ? chunks[di].H[d] : chunks[di].E[d];
+          for (int z = 0; z <= sr[5] - sr[4]; ++z)
+            for (int y = 0; y <= sr[3] - sr[2]; ++y)
+              for (int x = 0; x <= sr[1] - sr[0]; ++x)
+                Dd.at(dr[0] + x, dr[2] + y, dr[4] + z) = S.at(sr[0] + x, sr[2] + y, sr[4] + z);
+        }
+      }
+    }
+  }
+
+  // global cell -> owning chunk lookup (cells outside 1..N belong to nobody)
+  int owner(int gi, int gj, int gk) const {
+    for (size_t q = 0; q < chunks.size(); ++q) {
+      const Chunk<T>& c = chunks[q];
+      if (gi >= c.s[0] && gi < c.s[0] + c.n[0] && gj >= c.s[1] && gj < c.s[1] + c.n[1] && gk >= c.s[2] &&
+          gk < c.s[2] + c.n[2])
+        return (int)q;
+    }
+    return -1;
+  }
+
+  // update_source! (src/Sources/Sources.jl:346-357) via step_sources! (:330-340)
+  void step_sources(int group, double t) {
+    for (auto& s : sources) {
+      bool is_h = s.comp >= 3;
+      if ((group == 0) != is_h) continue;
+      int d = s.comp % 3;
+      std::complex<T> a = eval_time_source(s.ts, t);
+      for (int z = 0; z < s.dims[2]; ++z)
+        for (int y = 0; y < s.dims[1]; ++y)
+          for (int x = 0; x < s.dims[0]; ++x) {
+            int gi = s.start[0] + x, gj = s.start[1] + y, gk = s.start[2] + z;
+            int q = owner(gi, gj, gk);
+            if (q < 0) continue;  // staggered extra cell: never consumed by the update kernel
+            Chunk<T>& c = chunks[q];
+            Arr3<T>& S = is_h ? c.SB[d] : c.SD[d];
+            std::complex<T> A = s.amp[(size_t)x + (size_t)s.dims[0] * ((size_t)y + (size_t)s.dims[1] * z)];
+            T re = a.real() * A.real() - a.imag() * A.imag();
+            S.at(gi - c.s[0] + 1, gj - c.s[1] + 1, gk - c.s[2] + 1) += re;
+          }
+    }
+  }
+
+  T field_at(int comp, int gi, int gj, int gk) const {
+    int q = owner(gi, gj, gk);
+    if (q < 0) return T(0);
+    const Chunk<T>& c = chunks[q];
+    const Arr3<T>& F = comp < 3 ? c.E[comp] : c.H[comp - 3];
+    return F.at(gi - c.s[0] + 1, gj - c.s[1] + 1, gk - c.s[2] + 1);
+  }
+
+  // update_dft_monitor! (src/Monitors/Monitors.jl:361-379); time_fac cast
+  // (:323); canonical = each global cell counted once (SURVEY §8(c') #4).
+  void update_monitors(int group, double time) {
+    const double two_pi = 2 * 3.141592653589793;
+    T tf_im = (T)(two_pi * time);
+    for (auto& m : monitors) {
+      bool is_h = m.comp >= 3;
+      if ((group == 0) != is_h) continue;
+      if (m.decimation > 1 && (timestep % m.decimation) != 0) continue;
+      size_t ncell = (size_t)m.n[0] * m.n[1] * m.n[2];
+      for (size_t k = 0; k < m.freqs.size(); ++k) {
+        T ph = m.freqs[k] * tf_im;
+        T er = (T)std::cos((double)ph), ei = (T)std::sin((double)ph);
+        T wr = dt * er, wi = dt * ei;
+#pragma omp parallel for schedule(static)
+        for (int z = 0; z < m.n[2]; ++z)
+          for (int y = 0; y < m.n[1]; ++y)
+            for (int x = 0; x < m.n[0]; ++x) {
+              T F = field_at(m.comp, m.start[0] + x, m.start[1] + y, m.start[2] + z);
+              std::complex<T>& M = m.M[k * ncell + (size_t)x + (size_t)m.n[0] * ((size_t)y + (size_t)m.n[1] * z)];
+              M = std::complex<T>(M.real() + wr * F, M.imag() + wi * F);
+            }
+      }
+    }
+  }
+
+  // step_polarization! (src/Kernels/Dispersive.jl:186-228) with the three
+  // kernels :25-117.
+  void step_polarization() {
+    if (poles.empty()) return;
+    for (auto& c : chunks) {
+      for (int d = 0; d < 3; ++d) std::fill(c.PD[d].d.begin(), c.PD[d].d.end(), T(0));
+      // (zero kernel only touches 1..N; the ghosts are never written, so a
+      // full fill is identical)
+      for (size_t p = 0; p < poles.size(); ++p) {
+        const ADECoef& k = poles[p].c;
+        T g1i = (T)k.gamma1_inv, g1 = (T)k.gamma1, w2 = (T)k.omega0_dt_sq, sw2 = (T)k.sigma_omega0_dt_sq,
+          dc = (T)k.drude_coeff;
+#pragma omp parallel for collapse(2) schedule(static)
+        for (int iz = 1; iz <= c.n[2]; ++iz)
+          for (int iy = 1; iy <= c.n[1]; ++iy)
+            for (int ix = 1; ix <= c.n[0]; ++ix) {
+              T sg = poles[p].sigma.at(c.s[0] + ix - 2, c.s[1] + iy - 2, c.s[2] + iz - 2);
+              if (sg != T(0)) {
+                for (int d = 0; d < 3; ++d) {
+                  T pv = c.P[d][p].at(ix, iy, iz);
+                  T Ev = c.E[d].at(ix, iy, iz);
+                  T nv;
+                  if (k.is_drude) nv = g1i * ((T(2) * pv - g1 * c.Pp[d][p].at(ix, iy, iz)) + dc * sg * Ev);
+                  else {
+                    T coeff_p = T(2) - w2;
+                    nv = g1i * ((coeff_p * pv - g1 * c.Pp[d][p].at(ix, iy, iz)) + sw2 * sg * Ev);
+                  }
+                  c.P[d][p].at(ix, iy, iz) = nv;
+                  c.Pp[d][p].at(ix, iy, iz) = pv;
+                }
+              }
+              for (int d = 0; d < 3; ++d) c.PD[d].at(ix, iy, iz) += c.P[d][p].at(ix, iy, iz);
+            }
+      }
+    }
+  }
+
+  // step! (src/Kernels/Kernels.jl:20-88); t = Float64(timestep * Δt) with the
+  // product formed in T (src/Simulation.jl:22).
+  void step() {
+    double t = (double)((T)timestep * dt);
+    double t_half = t + (double)(dt / T(2));
+    if (sources_active) step_sources(0, t);
+    for (auto& c : chunks) { step_curl(c, 0); update_field(c, 0); }
+    if (chunks.size() > 1) exchange_halos(0);
+    update_monitors(0, t);
+    if (sources_active) step_sources(1, t_half);
+    for (auto& c : chunks) { step_curl(c, 1); update_field(c, 1); }
+    if (chunks.size() > 1) exchange_halos(1);
+    step_polarization();
+    update_monitors(1, t_half);
+    timestep += 1;
+  }
+};
+
+struct Handle {
+  int dtype;  // 0 f32, 1 f64
+  Sim<float>* f = nullptr;
+  Sim<double>* d = nullptr;
+};
+
+#define DISPATCH(h, ...)                                      \
+  do {                                                        \
+    if ((h)->dtype == 0) { auto& S = *(h)->f; __VA_ARGS__; }  \
+    else { auto& S = *(h)->d; __VA_ARGS__; }                  \
+  } while (0)
+
+template <class T>
+void copy_in(Arr3<T>& dst, const double* src, int nx, int ny, int nz) {
+  dst.alloc(nx, ny, nz);
+  for (size_t q = 0; q < dst.d.size(); ++q) dst.d[q] = (T)src[q];
+}
+
+}  // namespace
+
+extern "C" {
+
+void* ko_create(int dtype, const double* cell_size, const double* cell_center, double resolution, double courant,
+                int has_boundaries, const double* pml6) {
+  Handle* h = new Handle;
+  h->dtype = dtype;
+  auto init = [&](auto& S) {
+    for (int a = 0; a < 3; ++a) { S.cell_size_u[a] = cell_size[a]; S.cell_center[a] = cell_center[a]; }
+    S.resolution = resolution;
+    S.courant = courant;
+    S.has_boundaries = has_boundaries != 0;
+    using TT = std::remove_reference_t<decltype(S.dt)>;
+    for (int a = 0; a < 3; ++a) { S.pml[a][0] = (TT)(pml6 ? pml6[2 * a] : 0.0); S.pml[a][1] = (TT)(pml6 ? pml6[2 * a + 1] : 0.0); }
+    S.derive_grid();
+    S.init_boundaries();
+  };
+  if (dtype == 0) { h->f = new Sim<float>; init(*h->f); }
+  else { h->d = new Sim<double>; init(*h->d); }
+  return h;
+}
+
+void ko_destroy(void* hv) {
+  Handle* h = (Handle*)hv;
+  delete h->f;
+  delete h->d;
+  delete h;
+}
+
+void ko_grid(void* hv, int* N, double* dl, double* dt) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, { for (int a = 0; a < 3; ++a) { N[a] = S.N[a]; dl[a] = (double)S.dl[a]; } *dt = (double)S.dt; });
+}
+
+void ko_gridvolume(void* hv, const double* center, const double* size, int comp, int* start, int* end) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, S.grid_volume(center, size, comp, start, end));
+}
+
+void ko_component_origin(void* hv, int comp, double* o) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, S.component_origin(comp, o));
+}
+
+int ko_sigma(void* hv, int axis, int group, double* out) {
+  Handle* h = (Handle*)hv;
+  int n = 0;
+  DISPATCH(h, {
+    auto& v = S.sigma[group][axis];
+    n = (int)v.size();
+    if (out) for (int i = 0; i < n; ++i) out[i] = (double)v[i];
+  });
+  return n;
+}
+
+int ko_plan_pml_grid(void* hv, int nranks, int* out6, int* flags3, int max_regions) {
+  Handle* h = (Handle*)hv;
+  int n = 0;
+  DISPATCH(h, {
+    auto r = S.pml_grid_regions(nranks);
+    n = (int)r.size();
+    for (int q = 0; q < n && q < max_regions; ++q) {
+      for (int a = 0; a < 3; ++a) { out6[6 * q + a] = r[q].s[a]; out6[6 * q + 3 + a] = r[q].e[a]; }
+      if (flags3) for (int a = 0; a < 3; ++a) flags3[3 * q + a] = S.pml_overlaps_axis(r[q], a) ? 1 : 0;
+    }
+  });
+  return n;
+}
+
+int ko_adjacency(int nregions, const int* regions6, int* out3, int max_adj) {
+  std::vector<Region> r((size_t)nregions);
+  for (int q = 0; q < nregions; ++q)
+    for (int a = 0; a < 3; ++a) { r[q].s[a] = regions6[6 * q + a]; r[q].e[a] = regions6[6 * q + 3 + a]; }
+  std::vector<int> adj;
+  compute_adjacency(r, 3, adj);
+  int m = (int)adj.size() / 3;
+  for (int q = 0; q < m && q < max_adj; ++q)
+    for (int a = 0; a < 3; ++a) out3[3 * q + a] = adj[3 * q + a];
+  return m;
+}
+
+void ko_halo_ranges(const int* src6, const int* dst6, int axis, int src_upper, int dst_lower, int* sr, int* dr) {
+  Region s, d;
+  for (int a = 0; a < 3; ++a) { s.s[a] = src6[a]; s.e[a] = src6[3 + a]; d.s[a] = dst6[a]; d.e[a] = dst6[3 + a]; }
+  overlap_halo_ranges(s, d, axis, src_upper != 0, dst_lower != 0, sr, dr);
+}
+
+double ko_interp_weight(const double* p, const double* lo, const double* hi, const double* sz, int ndims,
+                        const double* dl) {
+  return interp_weight(p, lo, hi, sz, ndims, dl);
+}
+
+void ko_ade_coefficients(double omega0, double gamma, double dt, double* out6) {
+  ADECoef c = ade_coefficients(omega0, gamma, dt);
+  out6[0] = c.gamma1_inv; out6[1] = c.gamma1; out6[2] = c.omega0_dt_sq;
+  out6[3] = c.sigma_omega0_dt_sq; out6[4] = c.drude_coeff; out6[5] = c.is_drude;
+}
+
+void ko_eval_time_source(int dtype, int kind, const double* p4, double t, double* re_im) {
+  if (dtype == 0) {
+    TimeSrc<float> s; s.kind = kind; s.fcen = (float)p4[0]; s.width = (float)p4[1]; s.peak_time = (float)p4[2]; s.cutoff = (float)p4[3];
+    auto a = eval_time_source(s, t); re_im[0] = a.real(); re_im[1] = a.imag();
+  } else {
+    TimeSrc<double> s; s.kind = kind; s.fcen = p4[0]; s.width = p4[1]; s.peak_time = p4[2]; s.cutoff = p4[3];
+    auto a = eval_time_source(s, t); re_im[0] = a.real(); re_im[1] = a.imag();
+  }
+}
+
+// kind: 0 eps_inv, 1 mu_inv (scalar)
+void ko_set_material_scalar(void* hv, int kind, double v) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, {
+    using TT = std::remove_reference_t<decltype(S.dt)>;
+    if (kind == 0) { S.eps_inv = (TT)v; S.eps_is_array = false; }
+    else { S.mu_inv = (TT)v; S.mu_is_array = false; }
+  });
+}
+
+// kind: 0..2 eps_inv_{x,y,z}; 3..5 mu_inv; 6..8 sigma_D; 9..11 sigma_B. Dense (Nx,Ny,Nz).
+void ko_set_material_array(void* hv, int kind, const double* a) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, {
+    int d = kind % 3, g = kind / 3;
+    auto& dst = (g == 0) ? S.eps_inv_a[d] : (g == 1) ? S.mu_inv_a[d] : (g == 2) ? S.sigD[d] : S.sigB[d];
+    copy_in(dst, a, S.N[0], S.N[1], S.N[2]);
+    if (g == 0) S.eps_is_array = true;
+    if (g == 1) S.mu_is_array = true;
+  });
+}
+
+int ko_get_material_array(void* hv, int kind, double* out) {
+  Handle* h = (Handle*)hv;
+  int ok = 0;
+  DISPATCH(h, {
+    int d = kind % 3, g = kind / 3;
+    auto& src = (g == 0) ? S.eps_inv_a[d] : (g == 1) ? S.mu_inv_a[d] : (g == 2) ? S.sigD[d] : S.sigB[d];
+    ok = src.ok() ? 1 : 0;
+    if (ok && out) for (size_t q = 0; q < src.d.size(); ++q) out[q] = (double)src.d[q];
+  });
+  return ok;
+}
+
+void ko_add_absorber(void* hv, int axis, int side, int num_layers, int sigma_order, double sigma_max) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, S.apply_absorber(axis, side, num_layers, sigma_order, sigma_max));
+}
+
+void ko_add_pole(void* hv, double omega0, double gamma, const double* sigma) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, {
+    using TT = std::remove_reference_t<decltype(S.dt)>;
+    Pole<TT> p;
+    p.c = ade_coefficients(omega0, gamma, (double)S.dt);
+    copy_in(p.sigma, sigma, S.N[0], S.N[1], S.N[2]);
+    S.poles.push_back(std::move(p));
+  });
+}
+
+int ko_add_source(void* hv, int comp, const int* start, const int* dims, const double* amp_re_im, int tkind,
+                  const double* tp4) {
+  Handle* h = (Handle*)hv;
+  int id = -1;
+  DISPATCH(h, {
+    using TT = std::remove_reference_t<decltype(S.dt)>;
+    Source<TT> s;
+    s.comp = comp;
+    size_t n = 1;
+    for (int a = 0; a < 3; ++a) { s.start[a] = start[a]; s.dims[a] = dims[a]; n *= (size_t)dims[a]; }
+    s.amp.resize(n);
+    for (size_t q = 0; q < n; ++q) s.amp[q] = std::complex<TT>((TT)amp_re_im[2 * q], (TT)amp_re_im[2 * q + 1]);
+    s.ts.kind = tkind; s.ts.fcen = (TT)tp4[0]; s.ts.width = (TT)tp4[1]; s.ts.peak_time = (TT)tp4[2]; s.ts.cutoff = (TT)tp4[3];
+    S.sources.push_back(std::move(s));
+    id = (int)S.sources.size() - 1;
+  });
+  return id;
+}
+
+int ko_add_dft(void* hv, int comp, const int* start, const int* end, int nf, const double* freqs, int decimation) {
+  Handle* h = (Handle*)hv;
+  int id = -1;
+  DISPATCH(h, {
+    using TT = std::remove_reference_t<decltype(S.dt)>;
+    DFTMon<TT> m;
+    m.comp = comp;
+    for (int a = 0; a < 3; ++a) { m.start[a] = start[a]; m.end[a] = end[a]; m.n[a] = end[a] - start[a] + 1; }
+    for (int k = 0; k < nf; ++k) m.freqs.push_back((TT)freqs[k]);
+    m.decimation = decimation;
+    S.monitors.push_back(std::move(m));
+    id = (int)S.monitors.size() - 1;
+  });
+  return id;
+}
+
+void ko_prepare(void* hv, int mode, int nranks) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, S.prepare(mode, nranks));
+}
+
+int ko_num_chunks(void* hv) {
+  Handle* h = (Handle*)hv;
+  int n = 0;
+  DISPATCH(h, n = (int)S.chunks.size());
+  return n;
+}
+
+// aux allocation pattern of chunk q: out[0..17] = CB,UB,WB,CD,UD,WD x (x,y,z)
+void ko_chunk_aux_pattern(void* hv, int q, int* out18, int* start3, int* n3, int* pml3) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, {
+    auto& c = S.chunks[q];
+    for (int d = 0; d < 3; ++d) {
+      out18[d] = c.CB[d].ok(); out18[3 + d] = c.UB[d].ok(); out18[6 + d] = c.WB[d].ok();
+      out18[9 + d] = c.CD[d].ok(); out18[12 + d] = c.UD[d].ok(); out18[15 + d] = c.WD[d].ok();
+      start3[d] = c.s[d]; n3[d] = c.n[d]; pml3[d] = c.pml[d];
+    }
+  });
+}
+
+int ko_chunk_sigma(void* hv, int q, int group, int axis, double* out) {
+  Handle* h = (Handle*)hv;
+  int n = 0;
+  DISPATCH(h, {
+    auto& v = S.chunks[q].sig[group][axis];
+    n = (int)v.size();
+    if (out) for (int i = 0; i < n; ++i) out[i] = (double)v[i];
+  });
+  return n;
+}
+
+void ko_step(void* hv, int nsteps) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, { for (int i = 0; i < nsteps; ++i) S.step(); });
+}
+
+void ko_set_sources_active(void* hv, int v) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, S.sources_active = v != 0);
+}
+
+long ko_timestep(void* hv) {
+  Handle* h = (Handle*)hv;
+  long t = 0;
+  DISPATCH(h, t = S.timestep);
+  return t;
+}
+
+// which: 0 = E/H (comp 0..5), 1 = D/B (comp 0..2 -> D, 3..5 -> B). Output is
+// the dense (Nx,Ny,Nz) box of cells 1..N in global indexing.
+void ko_get_field(void* hv, int which, int comp, double* out) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, {
+    size_t nx = S.N[0], ny = S.N[1];
+    for (auto& c : S.chunks) {
+      auto& F = (which == 0) ? (comp < 3 ? c.E[comp] : c.H[comp - 3]) : (comp < 3 ? c.D[comp] : c.B[comp - 3]);
+      for (int iz = 1; iz <= c.n[2]; ++iz)
+        for (int iy = 1; iy <= c.n[1]; ++iy)
+          for (int ix = 1; ix <= c.n[0]; ++ix)
+            out[(size_t)(c.s[0] + ix - 2) + nx * ((size_t)(c.s[1] + iy - 2) + ny * (size_t)(c.s[2] + iz - 2))] =
+                (double)F.at(ix, iy, iz);
+    }
+  });
+}
+
+// Set E/H (and the consistent D = E/eps_inv, B = H/mu_inv) over cells 1..N.
+void ko_set_field(void* hv, int comp, const double* in) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, {
+    using TT = std::remove_reference_t<decltype(S.dt)>;
+    size_t nx = S.N[0], ny = S.N[1];
+    for (auto& c : S.chunks) {
+      int d = comp % 3;
+      auto& F = comp < 3 ? c.E[d] : c.H[d];
+      auto& Tf = comp < 3 ? c.D[d] : c.B[d];
+      for (int iz = 1; iz <= c.n[2]; ++iz)
+        for (int iy = 1; iy <= c.n[1]; ++iy)
+          for (int ix = 1; ix <= c.n[0]; ++ix) {
+            TT v = (TT)in[(size_t)(c.s[0] + ix - 2) + nx * ((size_t)(c.s[1] + iy - 2) + ny * (size_t)(c.s[2] + iz - 2))];
+            F.at(ix, iy, iz) = v;
+            TT m = comp < 3 ? S.mat(S.eps_is_array, S.eps_inv, S.eps_inv_a, d, c, ix, iy, iz)
+                            : S.mat(S.mu_is_array, S.mu_inv, S.mu_inv_a, d, c, ix, iy, iz);
+            Tf.at(ix, iy, iz) = v / m;
+          }
+    }
+    if (S.chunks.size() > 1) S.exchange_halos(comp < 3 ? 1 : 0);
+  });
+}
+
+// DFT accumulator of monitor id: out is (re,im) pairs, (nx,ny,nz,nf) column-major.
+size_t ko_get_dft(void* hv, int id, double* out) {
+  Handle* h = (Handle*)hv;
+  size_t n = 0;
+  DISPATCH(h, {
+    auto& m = S.monitors[id];
+    n = m.M.size();
+    if (out) for (size_t q = 0; q < n; ++q) { out[2 * q] = (double)m.M[q].real(); out[2 * q + 1] = (double)m.M[q].imag(); }
+  });
+  return n;
+}
+
+// get_flux (src/Monitors/FluxMonitor.jl:92-156) on four DFT monitors
+// (e1,e2,h1,h2) that share a normal axis. Float64 host arithmetic.
+void ko_flux(void* hv, int normal_axis /*0..2*/, const int* ids4, double* flux_out) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, {
+    typedef std::complex<double> cd;
+    auto* m = &S.monitors[0];
+    const auto& e1 = m[ids4[0]]; const auto& e2 = m[ids4[1]]; const auto& h1 = m[ids4[2]]; const auto& h2 = m[ids4[3]];
+    int nf = (int)e1.freqs.size();
+    int t1 = normal_axis == 0 ? 1 : 0;
+    int t2 = normal_axis == 2 ? 1 : 2;
+    int n1 = std::min(std::min(e1.n[t1], e2.n[t1]), std::min(h1.n[t1], h2.n[t1]));
+    int n2 = std::min(std::min(e1.n[t2], e2.n[t2]), std::min(h1.n[t2], h2.n[t2]));
+    double dA = (double)S.dl[t1] * (double)S.dl[t2];
+    auto val = [&](const auto& mm, int i1, int i2, int kf) -> cd {
+      // _avg_dim: average the two planes along the normal if the box is 2 thick.
+      // The division by 2 is done on Complex{T} (Array(md.fields) keeps T).
+      using TT = std::remove_reference_t<decltype(S.dt)>;
+      size_t ncell = (size_t)mm.n[0] * mm.n[1] * mm.n[2];
+      auto at = [&](int q) {
+        int idx[3];
+        idx[normal_axis] = q; idx[t1] = i1; idx[t2] = i2;
+        return mm.M[(size_t)kf * ncell + (size_t)idx[0] + (size_t)mm.n[0] * ((size_t)idx[1] + (size_t)mm.n[1] * idx[2])];
+      };
+      if (mm.n[normal_axis] >= 2) {
+        std::complex<TT> a = at(0), b = at(1);
+        std::complex<TT> s(a.real() + b.real(), a.imag() + b.imag());
+        return cd((double)(s.real() / TT(2)), (double)(s.imag() / TT(2)));
+      }
+      std::complex<TT> a = at(0);
+      return cd((double)a.real(), (double)a.imag());
+    };
+    for (int kf = 0; kf < nf; ++kf) {
+      double s = 0.0;
+      for (int i2 = 0; i2 < n2; ++i2)
+        for (int i1 = 0; i1 < n1; ++i1) {
+          // real(et1*conj(ht2) - et2*conj(ht1)) in Complex{T}, then * dA (Float64)
+          using TT = std::remove_reference_t<decltype(S.dt)>;
+          cd a = val(e1, i1, i2, kf), b = val(e2, i1, i2, kf), c = val(h1, i1, i2, kf), d2 = val(h2, i1, i2, kf);
+          std::complex<TT> et1((TT)a.real(), (TT)a.imag()), et2((TT)b.real(), (TT)b.imag());
+          std::complex<TT> ht1((TT)c.real(), (TT)c.imag()), ht2((TT)d2.real(), (TT)d2.imag());
+          TT re1 = et1.real() * ht2.real() + et1.imag() * ht2.imag();
+          TT re2 = et2.real() * ht1.real() + et2.imag() * ht1.imag();
+          s += (double)(re1 - re2) * dA;
+        }
+      flux_out[kf] = s;
+    }
+  });
+}
+
+}  // extern "C"

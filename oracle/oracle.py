@@ -1,0 +1,303 @@
+"""ctypes front-end of the CPU parity oracle (oracle/khronos_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py may import this module; the
+product package (khronos.jl_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+EX, EY, EZ, HX, HY, HZ, CENTER = range(7)
+COMP_NAMES = ["Ex", "Ey", "Ez", "Hx", "Hy", "Hz"]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libkhronos_oracle.so")
+    src = os.path.join(_HERE, "khronos_oracle.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"], env={k: v for k, v in os.environ.items() if k != "CXX"})
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libkhronos_oracle.so")
+        if not os.path.exists(so):
+            build()
+        L = C.CDLL(so)
+        dp = C.POINTER(C.c_double)
+        ip = C.POINTER(C.c_int)
+        L.ko_create.restype = C.c_void_p
+        L.ko_create.argtypes = [C.c_int, dp, dp, C.c_double, C.c_double, C.c_int, dp]
+        L.ko_destroy.argtypes = [C.c_void_p]
+        L.ko_grid.argtypes = [C.c_void_p, ip, dp, dp]
+        L.ko_gridvolume.argtypes = [C.c_void_p, dp, dp, C.c_int, ip, ip]
+        L.ko_component_origin.argtypes = [C.c_void_p, C.c_int, dp]
+        L.ko_sigma.restype = C.c_int
+        L.ko_sigma.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
+        L.ko_plan_pml_grid.restype = C.c_int
+        L.ko_plan_pml_grid.argtypes = [C.c_void_p, C.c_int, ip, ip, C.c_int]
+        L.ko_adjacency.restype = C.c_int
+        L.ko_adjacency.argtypes = [C.c_int, ip, ip, C.c_int]
+        L.ko_halo_ranges.argtypes = [ip, ip, C.c_int, C.c_int, C.c_int, ip, ip]
+        L.ko_interp_weight.restype = C.c_double
+        L.ko_interp_weight.argtypes = [dp, dp, dp, dp, C.c_int, dp]
+        L.ko_ade_coefficients.argtypes = [C.c_double, C.c_double, C.c_double, dp]
+        L.ko_eval_time_source.argtypes = [C.c_int, C.c_int, dp, C.c_double, dp]
+        L.ko_set_material_scalar.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.ko_set_material_array.argtypes = [C.c_void_p, C.c_int, dp]
+        L.ko_get_material_array.restype = C.c_int
+        L.ko_get_material_array.argtypes = [C.c_void_p, C.c_int, dp]
+        L.ko_add_absorber.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]
+        L.ko_add_pole.argtypes = [C.c_void_p, C.c_double, C.c_double, dp]
+        L.ko_add_source.restype = C.c_int
+        L.ko_add_source.argtypes = [C.c_void_p, C.c_int, ip, ip, dp, C.c_int, dp]
+        L.ko_add_dft.restype = C.c_int
+        L.ko_add_dft.argtypes = [C.c_void_p, C.c_int, ip, ip, C.c_int, dp, C.c_int]
+        L.ko_prepare.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ko_num_chunks.restype = C.c_int
+        L.ko_num_chunks.argtypes = [C.c_void_p]
+        L.ko_chunk_aux_pattern.argtypes = [C.c_void_p, C.c_int, ip, ip, ip, ip]
+        L.ko_chunk_sigma.restype = C.c_int
+        L.ko_chunk_sigma.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, dp]
+        L.ko_step.argtypes = [C.c_void_p, C.c_int]
+        L.ko_set_sources_active.argtypes = [C.c_void_p, C.c_int]
+        L.ko_timestep.restype = C.c_long
+        L.ko_timestep.argtypes = [C.c_void_p]
+        L.ko_get_field.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
+        L.ko_set_field.argtypes = [C.c_void_p, C.c_int, dp]
+        L.ko_get_dft.restype = C.c_size_t
+        L.ko_get_dft.argtypes = [C.c_void_p, C.c_int, dp]
+        L.ko_flux.argtypes = [C.c_void_p, C.c_int, ip, dp]
+        _LIB = L
+    return _LIB
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _i(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def interp_weight(p, lo, hi, size, ndims, delta):
+    args = [_d(x) for x in (p, lo, hi, size)]
+    dl = _d(delta)
+    return lib().ko_interp_weight(args[0][1], args[1][1], args[2][1], args[3][1], int(ndims), dl[1])
+
+
+def ade_coefficients(omega0, gamma, dt):
+    out = np.zeros(6)
+    lib().ko_ade_coefficients(float(omega0), float(gamma), float(dt), out.ctypes.data_as(C.POINTER(C.c_double)))
+    return dict(gamma1_inv=out[0], gamma1=out[1], omega0_dt_sq=out[2], sigma_omega0_dt_sq=out[3],
+                drude_coeff=out[4], is_drude=bool(out[5]))
+
+
+def eval_time_source(dtype, kind, params4, t):
+    p = _d(params4)
+    out = np.zeros(2)
+    lib().ko_eval_time_source(0 if dtype in ("f32", np.float32) else 1, int(kind), p[1], float(t),
+                              out.ctypes.data_as(C.POINTER(C.c_double)))
+    return complex(out[0], out[1])
+
+
+def adjacency(regions):
+    r, rp = _i(np.asarray(regions).reshape(-1, 6))
+    out = np.zeros((4096, 3), dtype=np.int32)
+    m = lib().ko_adjacency(len(r), rp, out.ctypes.data_as(C.POINTER(C.c_int)), 4096)
+    return out[:m].copy()
+
+
+def halo_ranges(src6, dst6, axis, src_upper, dst_lower):
+    s, sp = _i(src6)
+    d, dp_ = _i(dst6)
+    sr = np.zeros(6, dtype=np.int32)
+    dr = np.zeros(6, dtype=np.int32)
+    lib().ko_halo_ranges(sp, dp_, int(axis), int(src_upper), int(dst_lower),
+                         sr.ctypes.data_as(C.POINTER(C.c_int)), dr.ctypes.data_as(C.POINTER(C.c_int)))
+    return sr, dr
+
+
+class OracleSim:
+    """One simulation in the CPU oracle.  Arrays cross as float64 and are cast
+    to the working type T inside (values given must already be T-representable
+    where bit-exactness matters)."""
+
+    def __init__(self, dtype, cell_size, cell_center, resolution, courant=0.5, boundaries=None):
+        self.L = lib()
+        self.dtype = np.float32 if dtype in ("f32", np.float32, "Float32") else np.float64
+        cs, csp = _d(cell_size)
+        cc, ccp = _d(cell_center)
+        if boundaries is None:
+            self.h = self.L.ko_create(0 if self.dtype == np.float32 else 1, csp, ccp, float(resolution),
+                                      float(courant), 0, None)
+        else:
+            b, bp = _d(np.asarray(boundaries, dtype=np.float64).reshape(6))
+            self.h = self.L.ko_create(0 if self.dtype == np.float32 else 1, csp, ccp, float(resolution),
+                                      float(courant), 1, bp)
+        N = np.zeros(3, dtype=np.int32)
+        dl = np.zeros(3)
+        dt = C.c_double()
+        self.L.ko_grid(self.h, N.ctypes.data_as(C.POINTER(C.c_int)), dl.ctypes.data_as(C.POINTER(C.c_double)),
+                       C.byref(dt))
+        self.N = tuple(int(x) for x in N)
+        self.dl = tuple(float(x) for x in dl)
+        self.dt = dt.value
+        self._monitors = []
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.ko_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ---- index maps -------------------------------------------------------
+    def grid_volume(self, center, size, comp):
+        c, cp = _d(center)
+        s, sp = _d(size)
+        st = np.zeros(3, dtype=np.int32)
+        en = np.zeros(3, dtype=np.int32)
+        self.L.ko_gridvolume(self.h, cp, sp, int(comp), st.ctypes.data_as(C.POINTER(C.c_int)),
+                             en.ctypes.data_as(C.POINTER(C.c_int)))
+        return st, en
+
+    def component_origin(self, comp):
+        o = np.zeros(3)
+        self.L.ko_component_origin(self.h, int(comp), o.ctypes.data_as(C.POINTER(C.c_double)))
+        return o
+
+    def sigma(self, axis, group=0):
+        n = self.L.ko_sigma(self.h, axis, group, None)
+        if n == 0:
+            return None
+        out = np.zeros(n)
+        self.L.ko_sigma(self.h, axis, group, out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out.astype(self.dtype)
+
+    def plan_pml_grid(self, nranks=0):
+        out = np.zeros((4096, 6), dtype=np.int32)
+        fl = np.zeros((4096, 3), dtype=np.int32)
+        n = self.L.ko_plan_pml_grid(self.h, int(nranks), out.ctypes.data_as(C.POINTER(C.c_int)),
+                                    fl.ctypes.data_as(C.POINTER(C.c_int)), 4096)
+        return out[:n].copy(), fl[:n].copy()
+
+    # ---- problem description ----------------------------------------------
+    def set_material_scalar(self, kind, v):
+        self.L.ko_set_material_scalar(self.h, {"eps_inv": 0, "mu_inv": 1}[kind], float(v))
+
+    _KINDS = {"eps_inv": 0, "mu_inv": 3, "sigma_D": 6, "sigma_B": 9}
+
+    def set_material_array(self, kind, comp, arr):
+        """arr: (Nx,Ny,Nz) numpy array (any order; converted to x-fastest)."""
+        a = np.asarray(arr, dtype=np.float64)
+        assert a.shape == self.N, (a.shape, self.N)
+        flat = np.ascontiguousarray(a.transpose(2, 1, 0)).ravel()
+        self.L.ko_set_material_array(self.h, self._KINDS[kind] + comp, flat.ctypes.data_as(C.POINTER(C.c_double)))
+
+    def get_material_array(self, kind, comp):
+        out = np.zeros(self.N[::-1])
+        ok = self.L.ko_get_material_array(self.h, self._KINDS[kind] + comp, out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out.transpose(2, 1, 0).astype(self.dtype) if ok else None
+
+    def add_absorber(self, axis, side, num_layers=40, sigma_order=3, sigma_max=0.0):
+        self.L.ko_add_absorber(self.h, axis, side, num_layers, sigma_order, float(sigma_max))
+
+    def add_pole(self, omega0, gamma, sigma):
+        a = np.asarray(sigma, dtype=np.float64)
+        assert a.shape == self.N
+        flat = np.ascontiguousarray(a.transpose(2, 1, 0)).ravel()
+        self.L.ko_add_pole(self.h, float(omega0), float(gamma), flat.ctypes.data_as(C.POINTER(C.c_double)))
+
+    def add_source(self, comp, start, amp, time_kind, time_params):
+        """amp: complex (nx,ny,nz) array; start: 1-based global start index of
+        the source's GridVolume; time_params = (fcen, width, peak_time, cutoff)."""
+        amp = np.asarray(amp, dtype=np.complex128)
+        dims = amp.shape
+        flat = np.ascontiguousarray(amp.transpose(2, 1, 0)).ravel()
+        ri = np.empty(2 * flat.size)
+        ri[0::2] = flat.real
+        ri[1::2] = flat.imag
+        s, sp = _i(start)
+        d, dp_ = _i(dims)
+        tp, tpp = _d(time_params)
+        return self.L.ko_add_source(self.h, int(comp), sp, dp_, ri.ctypes.data_as(C.POINTER(C.c_double)),
+                                    int(time_kind), tpp)
+
+    def add_dft(self, comp, start, end, freqs, decimation=1):
+        s, sp = _i(start)
+        e, ep = _i(end)
+        f, fp = _d(freqs)
+        mid = self.L.ko_add_dft(self.h, int(comp), sp, ep, len(f), fp, int(decimation))
+        self._monitors.append((tuple(int(x) for x in (e - s + 1)), len(f)))
+        return mid
+
+    # ---- run ----------------------------------------------------------------
+    def prepare(self, mode="single", nranks=0):
+        self.L.ko_prepare(self.h, 0 if mode == "single" else 1, int(nranks))
+
+    def num_chunks(self):
+        return self.L.ko_num_chunks(self.h)
+
+    def chunk_info(self, q):
+        pat = np.zeros(18, dtype=np.int32)
+        st = np.zeros(3, dtype=np.int32)
+        n = np.zeros(3, dtype=np.int32)
+        pml = np.zeros(3, dtype=np.int32)
+        ip = C.POINTER(C.c_int)
+        self.L.ko_chunk_aux_pattern(self.h, q, pat.ctypes.data_as(ip), st.ctypes.data_as(ip), n.ctypes.data_as(ip),
+                                    pml.ctypes.data_as(ip))
+        names = ["CB", "UB", "WB", "CD", "UD", "WD"]
+        aux = {names[g] + "xyz"[d]: bool(pat[3 * g + d]) for g in range(6) for d in range(3)}
+        return dict(start=st, n=n, pml=pml.astype(bool), aux=aux)
+
+    def chunk_sigma(self, q, group, axis):
+        n = self.L.ko_chunk_sigma(self.h, q, group, axis, None)
+        if n == 0:
+            return None
+        out = np.zeros(n)
+        self.L.ko_chunk_sigma(self.h, q, group, axis, out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out.astype(self.dtype)
+
+    def step(self, n=1):
+        self.L.ko_step(self.h, int(n))
+
+    @property
+    def timestep(self):
+        return self.L.ko_timestep(self.h)
+
+    def get_field(self, comp, which="EH"):
+        out = np.zeros(self.N[::-1])
+        self.L.ko_get_field(self.h, 0 if which == "EH" else 1, int(comp), out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out.transpose(2, 1, 0)
+
+    def set_field(self, comp, arr):
+        a = np.asarray(arr, dtype=np.float64)
+        flat = np.ascontiguousarray(a.transpose(2, 1, 0)).ravel()
+        self.L.ko_set_field(self.h, int(comp), flat.ctypes.data_as(C.POINTER(C.c_double)))
+
+    def get_dft(self, mid):
+        dims, nf = self._monitors[mid]
+        n = self.L.ko_get_dft(self.h, mid, None)
+        out = np.zeros(2 * n)
+        self.L.ko_get_dft(self.h, mid, out.ctypes.data_as(C.POINTER(C.c_double)))
+        z = out[0::2] + 1j * out[1::2]
+        return z.reshape((nf,) + dims[::-1]).transpose(3, 2, 1, 0)  # (nx,ny,nz,nf)
+
+    def flux(self, normal_axis, ids4):
+        i4, ip = _i(ids4)
+        nf = self._monitors[ids4[0]][1]
+        out = np.zeros(nf)
+        self.L.ko_flux(self.h, int(normal_axis), ip, out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out
