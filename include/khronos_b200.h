@@ -1,0 +1,154 @@
+/*
+ * khronos_b200.h — C ABI of libkhronos_b200.so
+ *
+ * B200-native (sm_100a) replacement of the Khronos.jl FDTD time-step hot path.
+ * The reference (pure Julia, /root/reference/src) has no FFI today; every entry
+ * point below replaces one Julia call site, cited as file:line relative to the
+ * reference tree.  The Julia shim that binds these with `ccall` is shown in
+ * INTEGRATION.md; the same ABI is driven from Python (ctypes) by the host-side
+ * mirror in khronos.jl_b200/.
+ *
+ * Conventions
+ *   - every function returns int32 status: 0 = ok, non-zero = error; the message
+ *     is available from khr_last_error() (thread-local, valid until the next call)
+ *   - plain-old-data only: pointers, sizes, scalars.  No callbacks, no exceptions
+ *     cross the boundary.
+ *   - "dense" host arrays are column-major (x fastest) like Julia arrays, element
+ *     type = the context dtype (float or double), extent (Nx,Ny,Nz_local) over the
+ *     cells 1..N this context owns, no ghost layers.
+ *   - indices are 1-based cell indices exactly as the reference computes them
+ *     (GridVolume.start_idx etc.), global in x/y and global in z (the library
+ *     subtracts the slab origin itself).
+ *   - ownership: the library owns all device storage (padded, 128-byte aligned
+ *     rows; SURVEY.md §8(b) convention B).  khr_field_view exposes the raw device
+ *     pointer + strides so the host can wrap it zero-copy.
+ *   - threading: one caller thread at a time per context; all calls are
+ *     asynchronous on the context's stream except khr_sync and the *_read calls.
+ */
+#ifndef KHRONOS_B200_H
+#define KHRONOS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct khr_ctx khr_ctx;
+
+enum { KHR_F32 = 0, KHR_F64 = 1 };
+/* field components, the order of src/Fields.jl / DataStructures.jl:100-148 */
+enum { KHR_EX = 0, KHR_EY = 1, KHR_EZ = 2, KHR_HX = 3, KHR_HY = 4, KHR_HZ = 5 };
+/* field groups: the reference's :H half-step (B/H from curl E) and :E half-step */
+enum { KHR_GROUP_H = 0, KHR_GROUP_E = 1 };
+/* per-voxel material arrays (Geometry.jl:460-477): kind*3 + component */
+enum { KHR_MAT_EPS_INV = 0, KHR_MAT_MU_INV = 1, KHR_MAT_SIGMA_D = 2, KHR_MAT_SIGMA_B = 3 };
+/* time profiles (Sources/TimeSources.jl:61-64, 123-132); HOST = amplitude pushed
+ * every step with khr_source_set_amplitude (CustomSourceData, :165-171) */
+enum { KHR_TIME_CW = 0, KHR_TIME_GAUSSIAN = 1, KHR_TIME_HOST = 2 };
+
+/* Grid + slab description.  Replaces the SimulationData fields the kernels read
+ * (DataStructures.jl:732-741) and, for nranks > 1, the rank's band of the
+ * z-slab decomposition (Chunking.jl:696-716, Distributed.jl:104-148). */
+typedef struct khr_grid_desc {
+  int32_t dtype;        /* KHR_F32 | KHR_F64 */
+  int32_t n[3];         /* global cell counts Nx,Ny,Nz */
+  double dl[3];         /* Δx,Δy,Δz already rounded to dtype */
+  double dt;            /* Δt already rounded to dtype */
+  int32_t z_start;      /* first global z cell owned by this context (1-based) */
+  int32_t nz_local;     /* number of z cells owned */
+  int32_t rank, nranks; /* position in the slab decomposition */
+} khr_grid_desc;
+
+const char* khr_last_error(void);
+int32_t khr_version(void);
+
+/* Simulation.jl:249-280 (kernel/constant caching block) -> library init */
+int32_t khr_ctx_create(int32_t device, const khr_grid_desc* grid, khr_ctx** out);
+int32_t khr_ctx_destroy(khr_ctx* ctx);
+
+/* Boundaries.jl:99-164 init_boundaries: upload one 1-D PML profile of length
+ * 2N+1 (host, dtype elements); kernels sample sigma[2i-1] (Helpers.jl:277).
+ * group: KHR_GROUP_H -> σB*, KHR_GROUP_E -> σD*. */
+int32_t khr_set_pml_sigma(khr_ctx* ctx, int32_t group, int32_t axis, const void* sigma, int32_t len);
+
+/* Geometry.jl:450-663 init_geometry outputs: scalar ε⁻¹/μ⁻¹ or per-voxel arrays,
+ * and the material conductivities σD/σB (absorbers, Geometry.jl:708-789). */
+int32_t khr_set_material_scalar(khr_ctx* ctx, int32_t kind, double value);
+int32_t khr_set_material_array(khr_ctx* ctx, int32_t kind, int32_t comp, const void* dense);
+
+/* Geometry.jl:1136-1355 init_polarization! output for one pole: σ array shared by
+ * x/y/z (Geometry.jl:1291-1302) and the pole parameters; coefficients follow
+ * Susceptibility.jl:74-85. */
+int32_t khr_pole_register(khr_ctx* ctx, double omega0, double gamma, const void* sigma_dense, int32_t* pole_id);
+
+/* Sources.jl:35-38 add_sources / SourceData: spatial amplitude box (complex,
+ * interleaved re/im, extent dims, column-major) at start_idx; time profile
+ * parameters tp = {fcen, width, peak_time, cutoff} (dtype-rounded by the caller). */
+int32_t khr_source_register(khr_ctx* ctx, int32_t comp, const int32_t start[3], const int32_t dims[3],
+                            const void* amp_complex, int32_t time_kind, const double tp[4], int32_t* source_id);
+/* Sources.jl:288-328 step_source_chunk!: scalar_amplitude for a KHR_TIME_HOST source */
+int32_t khr_source_set_amplitude(khr_ctx* ctx, int32_t source_id, double re, double im);
+/* Kernels.jl:27-35: sources_active switch (1 on, 0 off; default: automatic from cutoffs) */
+int32_t khr_set_sources_active(khr_ctx* ctx, int32_t mode /* -1 auto, 0 off, 1 on */);
+
+/* Monitors.jl:202-272 init_monitors for one DFTMonitorData: component, index box
+ * [start,end] in the component grid, frequencies (dtype-rounded), decimation. */
+int32_t khr_monitor_register(khr_ctx* ctx, int32_t comp, const int32_t start[3], const int32_t end[3], int32_t nfreq,
+                             const double* freqs, int32_t decimation, int32_t* monitor_id);
+
+/* builds region/work tables, allocates PML auxiliary slabs; call once after all
+ * registrations (tail of prepare_simulation!, Simulation.jl:198-280) */
+int32_t khr_finalize_plan(khr_ctx* ctx);
+
+/* --- stepping ------------------------------------------------------------- */
+/* Kernels.jl:20-88 step!: n full time steps (sources, H, H-DFT, E + ADE, E-DFT) */
+int32_t khr_step(khr_ctx* ctx, int32_t nsteps);
+/* Kernels.jl:164-296 step_H_fused! (+ Sources.jl:330-340 magnetic sources, + halo) */
+int32_t khr_step_h(khr_ctx* ctx);
+/* Kernels.jl:298-454 step_E_fused! + Dispersive.jl:186-228 step_polarization! (fused) */
+int32_t khr_step_e(khr_ctx* ctx);
+/* Monitors.jl:274-329 update_monitor for every DFT monitor of the group at `time` */
+int32_t khr_dft_update(khr_ctx* ctx, int32_t group, double time);
+/* Kernels.jl:87 increment_timestep! / Simulation.jl:22 */
+int32_t khr_get_timestep(khr_ctx* ctx, int64_t* timestep);
+int32_t khr_set_timestep(khr_ctx* ctx, int64_t timestep);
+/* Simulation.jl:571-637 reset_fields! */
+int32_t khr_reset_fields(khr_ctx* ctx);
+
+/* --- distributed (Distributed.jl:57-72 init_nccl!, :448-506 halo) --------- */
+int32_t khr_comm_unique_id(void* out128);
+int32_t khr_comm_init(khr_ctx* ctx, const void* unique_id128, int32_t nranks, int32_t rank);
+/* Chunking.jl:2106-2130 exchange_halos!(sim, :H | :E) — blocking form for API parity */
+int32_t khr_halo_exchange(khr_ctx* ctx, int32_t group);
+
+/* --- data access ---------------------------------------------------------- */
+/* Visualization.jl:294-333 _pull_fields_from_device: dense (Nx,Ny,Nz_local) copy of cells 1..N */
+int32_t khr_field_read(khr_ctx* ctx, int32_t comp, void* dense_out);
+int32_t khr_field_write(khr_ctx* ctx, int32_t comp, const void* dense_in);
+/* raw device view: element (ix,iy,iz_local) (1-based cells, 0 = lower ghost) lives at
+ * ptr[offset + ix*stride[0] + iy*stride[1] + iz*stride[2]] */
+int32_t khr_field_view(khr_ctx* ctx, int32_t comp, void** dev_ptr, int64_t stride[3], int64_t* offset);
+/* FluxMonitor.jl:99-102 Array(md.fields): complex (nx,ny,nz,nf) interleaved re/im */
+int32_t khr_monitor_read(khr_ctx* ctx, int32_t monitor_id, void* complex_out);
+int32_t khr_monitor_view(khr_ctx* ctx, int32_t monitor_id, void** dev_ptr, int64_t dims[4]);
+/* Simulation.jl:440-445 stop_when_dft_decayed: sqrt(sum |M|^2) of one monitor */
+int32_t khr_monitor_norm(khr_ctx* ctx, int32_t monitor_id, double* norm);
+
+int32_t khr_sync(khr_ctx* ctx);
+int32_t khr_get_stream(khr_ctx* ctx, void** cuda_stream);
+
+/* --- measurement helpers (bench.py / profiles) ---------------------------- */
+/* device time of the last khr_step() call in ms (CUDA events on the ctx stream)
+ * and the number of kernels launched by it */
+int32_t khr_last_step_timing(khr_ctx* ctx, double* ms, int64_t* kernel_launches);
+/* voxel-class census used by the bytes model: counts of cells with 0,1,2,3 PML axes */
+int32_t khr_voxel_census(khr_ctx* ctx, int64_t counts[4]);
+/* bytes of device memory held by the context */
+int32_t khr_device_bytes(khr_ctx* ctx, int64_t* bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KHRONOS_B200_H */

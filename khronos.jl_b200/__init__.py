@@ -1,0 +1,21 @@
+"""khronos.jl_b200 — B200-native (sm_100a) FDTD time-step path of Khronos.jl.
+
+The package holds only what the hot path needs: `csrc/` (the CUDA kernels and
+the C ABI declared in include/khronos_b200.h), the ctypes binding, and the
+host-side mirror of the reference's Simulation / run / monitor interface.
+Import as `khronos_b200` (see khronos_b200.py at the repository root — the
+directory name carries a dot and cannot be imported directly).
+"""
+from . import _lib, chunking, grid
+from .grid import EX, EY, EZ, HX, HY, HZ, Grid, interpolation_weight
+from .simulation import (Absorber, Ball, ContinuousWaveSource, Cuboid, CustomSource, DFTMonitor, DrudeSusceptibility,
+                         FluxMonitor, GaussianPulseSource, LorentzianSusceptibility, Material, Object, Simulation,
+                         UniformSource, run, run_benchmark, step)
+from ._lib import KhronosError, build
+
+__all__ = [
+    "Absorber", "Ball", "ContinuousWaveSource", "Cuboid", "CustomSource", "DFTMonitor", "DrudeSusceptibility",
+    "FluxMonitor", "GaussianPulseSource", "LorentzianSusceptibility", "Material", "Object", "Simulation",
+    "UniformSource", "run", "run_benchmark", "step", "Grid", "interpolation_weight", "KhronosError", "build",
+    "EX", "EY", "EZ", "HX", "HY", "HZ", "chunking", "grid",
+]

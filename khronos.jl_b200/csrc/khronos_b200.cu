@@ -1,0 +1,1088 @@
+// ============================================================================
+// khronos_b200.cu — host side of libkhronos_b200.so: context, storage layout,
+// work-table planner, per-step orchestration, DFT, halo exchange, C ABI.
+// Reference call sites are cited in include/khronos_b200.h next to each entry.
+//
+// There is deliberately NO CPU fallback in this file: every compute entry
+// point launches the sm_100a kernels of step_kernels.cuh or fails with an error.
+// ============================================================================
+#include "../../include/khronos_b200.h"
+#include "step_kernels.cuh"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace khr {
+
+static thread_local std::string g_err;
+static int32_t fail(const std::string& m) {
+  g_err = m;
+  return 1;
+}
+#define CUDA_OK(expr)                                                                               \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      throw std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"; \
+  } while (0)
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// ---- NCCL through dlopen: the library must not pull a second libnccl into a
+// process that already carries one (torch bundles its own).
+struct Id128 {
+  char b[128];
+};
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /*ncclUniqueId by value, 128 bytes*/ Id128, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static void load_nccl() {
+  if (g_nccl.h) return;
+  void* h = nullptr;
+  // 1) symbols already in the process (torch's bundled NCCL)
+  if (dlsym(RTLD_DEFAULT, "ncclCommInitRank")) h = RTLD_DEFAULT;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (int i = 0; !h && i < 2; ++i) h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+  if (!h) throw std::string("NCCL not found (dlopen libnccl.so.2 failed): ") + (dlerror() ? dlerror() : "");
+  auto sym = [&](const char* n) {
+    void* p = dlsym(h, n);
+    if (!p) throw std::string("NCCL symbol missing: ") + n;
+    return p;
+  };
+  g_nccl.GetUniqueId = (int (*)(void*))sym("ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))sym("ncclCommInitRank");
+  g_nccl.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+  g_nccl.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))sym("ncclSend");
+  g_nccl.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))sym("ncclRecv");
+  g_nccl.GroupStart = (int (*)())sym("ncclGroupStart");
+  g_nccl.GroupEnd = (int (*)())sym("ncclGroupEnd");
+  g_nccl.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+  g_nccl.h = h;
+}
+#define NCCL_OK(expr)                                                                      \
+  do {                                                                                     \
+    int _r = (expr);                                                                       \
+    if (_r != 0) throw std::string(#expr) + ": " + khr::g_nccl.GetErrorString(_r);              \
+  } while (0)
+
+// ----------------------------------------------------------------------------
+struct Base {
+  virtual ~Base() {}
+  khr_grid_desc g;
+  virtual void set_pml_sigma(int group, int axis, const void* s, int len) = 0;
+  virtual void set_material_scalar(int kind, double v) = 0;
+  virtual void set_material_array(int kind, int comp, const void* dense) = 0;
+  virtual int pole_register(double omega0, double gamma, const void* sigma) = 0;
+  virtual int source_register(int comp, const int32_t* start, const int32_t* dims, const void* amp, int kind,
+                              const double* tp) = 0;
+  virtual void source_set_amplitude(int id, double re, double im) = 0;
+  virtual int monitor_register(int comp, const int32_t* s, const int32_t* e, int nf, const double* f, int dec) = 0;
+  virtual void finalize() = 0;
+  virtual void step(int n) = 0;
+  virtual void step_h() = 0;
+  virtual void step_e() = 0;
+  virtual void dft_update(int group, double time) = 0;
+  virtual void reset_fields() = 0;
+  virtual void comm_init(const void* id, int nranks, int rank) = 0;
+  virtual void halo_exchange(int group) = 0;
+  virtual void field_read(int comp, void* out) = 0;
+  virtual void field_write(int comp, const void* in) = 0;
+  virtual void field_view(int comp, void** p, int64_t* stride, int64_t* off) = 0;
+  virtual void monitor_read(int id, void* out) = 0;
+  virtual void monitor_view(int id, void** p, int64_t* dims) = 0;
+  virtual double monitor_norm(int id) = 0;
+  virtual void sync() = 0;
+  virtual void census(int64_t* c) = 0;
+  int64_t timestep = 0;
+  int sources_mode = -1;
+  bool sources_active = true;
+  cudaStream_t stream = nullptr, comm_stream = nullptr;
+  double last_ms = 0;
+  int64_t last_launches = 0;
+  int64_t dev_bytes = 0;
+  int device = 0;
+};
+
+template <class T>
+struct TimeSrc {
+  int kind;
+  T fcen, width, peak, cutoff;
+  T host_re = 0, host_im = 0;
+};
+
+// Sources/TimeSources.jl:61-64 (CW), :123-132 (Gaussian): every factor multiplies the
+// imaginary part left to right in T; exp(i x) = (cos x, sin x) evaluated in T.
+template <class T>
+static void eval_time_source(const TimeSrc<T>& s, double t, T* re, T* im) {
+  const T pi_T = (T)3.141592653589793;
+  if (s.kind == KHR_TIME_CW) {
+    T a = -T(1);
+    a = a * T(2);
+    a = a * pi_T;
+    a = a * s.fcen;
+    a = a * (T)t;
+    *re = std::cos(a);
+    *im = std::sin(a);
+  } else if (s.kind == KHR_TIME_GAUSSIAN) {
+    T tt = (T)t - s.peak;
+    if (tt > s.cutoff) { *re = 0; *im = 0; return; }
+    T two_pi = T(2) * pi_T;
+    T env = std::exp((-tt * tt) / (T(2) * s.width * s.width));
+    T a = -two_pi;
+    a = a * s.fcen;
+    a = a * tt;
+    *re = env * std::cos(a);
+    *im = env * std::sin(a);
+  } else {
+    if ((T)t > s.cutoff) { *re = 0; *im = 0; return; }
+    *re = s.host_re;
+    *im = s.host_im;
+  }
+}
+
+template <class T>
+struct Impl : Base {
+  // ---- geometry of the storage ----
+  int N[3];          // local cells (Nx, Ny, Nz_local)
+  int PX, PY, PZ;    // ghosted field box
+  int MPX;           // material row pitch
+  size_t fsize, msize;
+  T dt, dl[3];
+  // ---- device arrays ----
+  T* F[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  T* m_arr[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // [0]=mu_inv (H group) [1]=eps_inv
+  T m_scalar[2] = {T(1), T(1)};
+  T* sigM[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // [0]=sigma_B [1]=sigma_D
+  T* Cst[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+  T* W[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+  T* U[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+  size_t slab_elems[3] = {0, 0, 0};
+  T* coef[2][3][3] = {};  // [group][axis][sg|om|ip]
+  std::vector<T> h_sig[2][3];  // per-cell sigma (value at 2i-1), local cells, host
+  bool have_sigma[2][3] = {{false, false, false}, {false, false, false}};
+  Slab slab[3];
+  int lo_end[3] = {0, 0, 0}, hi_start[3] = {0, 0, 0};
+  int cxp = 0, cy = 0, cz = 0;
+  int sd_box[2][6];  // bounding boxes (local cells) of non-zero sigma_B / sigma_D, empty if lo > hi
+  bool has_sd[2] = {false, false};
+
+  struct Pole {
+    T* sigma = nullptr;
+    T* P[2][3];  // ping-pong
+    int cur = 0;
+    T g1i, g1, cp, cd;
+    int box[6];
+  };
+  std::vector<Pole> poles;
+  struct Source {
+    int comp;
+    int s[3], d[3];  // local start (z already shifted), extent
+    T* amp = nullptr;
+    TimeSrc<T> ts;
+    T ao_re = 0, ao_im = 0;
+  };
+  std::vector<Source> sources;
+  struct Monitor {
+    int comp;
+    int s[3], e[3], n[3];  // global index box
+    std::vector<T> freqs;
+    T* d_freqs = nullptr;
+    T* M = nullptr;
+    int decimation;
+    size_t elems;  // complex elements
+    bool local;    // any part on this rank
+  };
+  std::vector<Monitor> monitors;
+  MonDesc<T>* d_mons = nullptr;
+  int* d_due = nullptr;
+  int* h_due = nullptr;
+  std::vector<int> last_due[2];
+
+  // work tables: [group][mode][lx index]
+  struct Table {
+    std::vector<WorkItem> items;
+    WorkItem* d = nullptr;
+  };
+  // phase 0 = boundary planes that feed the halo exchange, phase 1 = the rest
+  Table tab[2][2][3][3];
+  bool finalized = false;
+  // distributed
+  void* comm = nullptr;
+  cudaEvent_t ev_boundary = nullptr, ev_comm = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  int64_t launches = 0;
+
+  std::vector<void*> allocs;
+  T* dalloc(size_t n, bool zero = true) {
+    void* p = nullptr;
+    size_t bytes = (n + 64) * sizeof(T);
+    CUDA_OK(cudaMalloc(&p, bytes));
+    if (zero) CUDA_OK(cudaMemsetAsync(p, 0, bytes, stream));
+    allocs.push_back(p);
+    dev_bytes += (int64_t)bytes;
+    return (T*)p;
+  }
+
+  Impl(int dev, const khr_grid_desc& gd) {
+    g = gd;
+    device = dev;
+    CUDA_OK(cudaSetDevice(dev));
+    CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&ev_boundary, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&ev_comm, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreate(&ev_t0));
+    CUDA_OK(cudaEventCreate(&ev_t1));
+    N[0] = gd.n[0]; N[1] = gd.n[1]; N[2] = gd.nz_local;
+    PX = round_up(N[0] + 36, 32);
+    PY = N[1] + 2;
+    PZ = N[2] + 2;
+    MPX = round_up(N[0], 32);
+    fsize = (size_t)PX * PY * PZ;
+    msize = (size_t)MPX * N[1] * N[2];
+    dt = (T)gd.dt;
+    for (int a = 0; a < 3; ++a) dl[a] = (T)gd.dl[a];
+    for (int c = 0; c < 6; ++c) F[c] = dalloc(fsize);
+    for (int gq = 0; gq < 2; ++gq) { sd_box[gq][0] = 1; sd_box[gq][3] = 0; }
+  }
+  ~Impl() override {
+    cudaSetDevice(device);
+    cudaDeviceSynchronize();
+    for (void* p : allocs) cudaFree(p);
+    if (h_due) cudaFreeHost(h_due);
+    if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+    cudaEventDestroy(ev_boundary); cudaEventDestroy(ev_comm); cudaEventDestroy(ev_t0); cudaEventDestroy(ev_t1);
+    cudaStreamDestroy(stream); cudaStreamDestroy(comm_stream);
+  }
+
+  inline size_t fidx(int ix, int iy, int iz) const { return (size_t)(ix + XO) + (size_t)PX * ((size_t)iy + (size_t)PY * iz); }
+  inline size_t midx(int ix, int iy, int iz) const {
+    return (size_t)(ix - 1) + (size_t)MPX * ((size_t)(iy - 1) + (size_t)N[1] * (iz - 1));
+  }
+
+  void set_pml_sigma(int group, int axis, const void* s, int len) override {
+    if (finalized) throw std::string("khr_set_pml_sigma after khr_finalize_plan");
+    int Ng = g.n[axis];
+    if (len != 2 * Ng + 1) throw std::string("sigma profile length must be 2N+1");
+    const T* sp = (const T*)s;
+    int nl = N[axis];
+    int off = (axis == 2) ? g.z_start - 1 : 0;
+    std::vector<T>& v = h_sig[group][axis];
+    v.assign((size_t)nl, T(0));
+    // kernels sample sigma[2i-1] (1-based) for cell i (Helpers.jl:277)
+    for (int i = 1; i <= nl; ++i) v[i - 1] = sp[2 * (i + off) - 2];
+    have_sigma[group][axis] = true;
+  }
+  void set_material_scalar(int kind, double v) override {
+    if (kind == KHR_MAT_EPS_INV) m_scalar[1] = (T)v;
+    else if (kind == KHR_MAT_MU_INV) m_scalar[0] = (T)v;
+    else throw std::string("scalar material must be eps_inv or mu_inv");
+  }
+  // dense (Nx,Ny,Nzl) host -> material layout device
+  T* upload_material(const void* dense, int* box6) {
+    const T* src = (const T*)dense;
+    std::vector<T> h(msize + 64, T(0));
+    int b[6] = {1 << 30, 1 << 30, 1 << 30, 0, 0, 0};
+    for (int z = 1; z <= N[2]; ++z)
+      for (int y = 1; y <= N[1]; ++y) {
+        const T* row = src + (size_t)N[0] * ((size_t)(y - 1) + (size_t)N[1] * (z - 1));
+        T* dst = h.data() + midx(1, y, z);
+        bool nz = false;
+        int xl = 1 << 30, xh = 0;
+        for (int x = 0; x < N[0]; ++x) {
+          dst[x] = row[x];
+          if (row[x] != T(0)) { nz = true; xl = std::min(xl, x + 1); xh = std::max(xh, x + 1); }
+        }
+        if (nz) {
+          b[0] = std::min(b[0], xl); b[3] = std::max(b[3], xh);
+          b[1] = std::min(b[1], y); b[4] = std::max(b[4], y);
+          b[2] = std::min(b[2], z); b[5] = std::max(b[5], z);
+        }
+      }
+    T* d = dalloc(msize, false);
+    CUDA_OK(cudaMemcpyAsync(d, h.data(), (msize + 64) * sizeof(T), cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    if (box6) for (int q = 0; q < 6; ++q) box6[q] = b[q];
+    return d;
+  }
+  static void box_union(int* a, const int* b) {
+    if (b[0] > b[3]) return;
+    if (a[0] > a[3]) { for (int q = 0; q < 6; ++q) a[q] = b[q]; return; }
+    for (int q = 0; q < 3; ++q) { a[q] = std::min(a[q], b[q]); a[3 + q] = std::max(a[3 + q], b[3 + q]); }
+  }
+  void set_material_array(int kind, int comp, const void* dense) override {
+    if (finalized) throw std::string("khr_set_material_array after khr_finalize_plan");
+    if (comp < 0 || comp > 2) throw std::string("component must be 0..2");
+    int box[6];
+    T* d = upload_material(dense, box);
+    if (kind == KHR_MAT_EPS_INV) m_arr[1][comp] = d;
+    else if (kind == KHR_MAT_MU_INV) m_arr[0][comp] = d;
+    else if (kind == KHR_MAT_SIGMA_D) { sigM[1][comp] = d; has_sd[1] = true; box_union(sd_box[1], box); }
+    else if (kind == KHR_MAT_SIGMA_B) { sigM[0][comp] = d; has_sd[0] = true; box_union(sd_box[0], box); }
+    else throw std::string("unknown material kind");
+  }
+  int pole_register(double omega0, double gamma, const void* sigma) override {
+    if (finalized) throw std::string("khr_pole_register after khr_finalize_plan");
+    if ((int)poles.size() >= MAXPOLE) throw std::string("too many ADE poles (max 4)");
+    // Susceptibility.jl:74-85 compute_ade_coefficients, Float64 then cast (Dispersive.jl:213-218)
+    const double pi = 3.141592653589793;
+    double dtd = (double)dt;
+    double gpd = gamma * pi * dtd;
+    double g1 = 1.0 - gpd, g1i = 1.0 / (1.0 + gpd);
+    double w = (2 * pi) * omega0 * dtd;
+    double w2 = w * w;
+    double drude = gamma * (2 * pi) * dtd * dtd;
+    Pole p;
+    p.g1 = (T)g1; p.g1i = (T)g1i;
+    if (omega0 == 0.0) { p.cp = T(2); p.cd = (T)drude; }
+    else { p.cp = T(2) - (T)w2; p.cd = (T)w2; }
+    p.sigma = upload_material(sigma, p.box);
+    for (int q = 0; q < 2; ++q)
+      for (int d = 0; d < 3; ++d) p.P[q][d] = dalloc(msize);
+    poles.push_back(p);
+    return (int)poles.size() - 1;
+  }
+  int source_register(int comp, const int32_t* start, const int32_t* dims, const void* amp, int kind,
+                      const double* tp) override {
+    if (finalized) throw std::string("khr_source_register after khr_finalize_plan");
+    Source s;
+    s.comp = comp;
+    size_t n = 1;
+    for (int a = 0; a < 3; ++a) { s.s[a] = start[a]; s.d[a] = dims[a]; n *= (size_t)dims[a]; }
+    s.s[2] -= g.z_start - 1;
+    s.amp = dalloc(2 * n, false);
+    CUDA_OK(cudaMemcpyAsync(s.amp, amp, 2 * n * sizeof(T), cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    s.ts.kind = kind;
+    s.ts.fcen = (T)tp[0]; s.ts.width = (T)tp[1]; s.ts.peak = (T)tp[2]; s.ts.cutoff = (T)tp[3];
+    sources.push_back(s);
+    return (int)sources.size() - 1;
+  }
+  void source_set_amplitude(int id, double re, double im) override {
+    if (id < 0 || id >= (int)sources.size()) throw std::string("bad source id");
+    sources[id].ts.host_re = (T)re;
+    sources[id].ts.host_im = (T)im;
+  }
+  int monitor_register(int comp, const int32_t* s, const int32_t* e, int nf, const double* f, int dec) override {
+    if (finalized) throw std::string("khr_monitor_register after khr_finalize_plan");
+    Monitor m;
+    m.comp = comp;
+    size_t n = 1;
+    for (int a = 0; a < 3; ++a) { m.s[a] = s[a]; m.e[a] = e[a]; m.n[a] = e[a] - s[a] + 1; n *= (size_t)std::max(m.n[a], 0); }
+    for (int k = 0; k < nf; ++k) m.freqs.push_back((T)f[k]);
+    m.decimation = std::max(dec, 1);
+    m.elems = n * (size_t)nf;
+    m.M = dalloc(2 * m.elems);
+    m.d_freqs = dalloc((size_t)nf, false);
+    CUDA_OK(cudaMemcpyAsync(m.d_freqs, m.freqs.data(), nf * sizeof(T), cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    monitors.push_back(m);
+    return (int)monitors.size() - 1;
+  }
+
+  // ---- planning -------------------------------------------------------------
+  static bool boxes_hit(const int* b, int x0, int x1, int y0, int y1, int z0, int z1) {
+    if (b[0] > b[3]) return false;
+    return b[0] <= x1 && b[3] >= x0 && b[1] <= y1 && b[4] >= y0 && b[2] <= z1 && b[5] >= z0;
+  }
+  static int lx_index(int w) { return w >= 96 ? 2 : (w >= 48 ? 1 : 0); }
+
+  void finalize() override {
+    if (finalized) throw std::string("khr_finalize_plan called twice");
+    // per-axis PML cell sets from both groups' profiles
+    std::vector<char> pml[3];
+    for (int a = 0; a < 3; ++a) {
+      pml[a].assign((size_t)N[a] + 2, 0);
+      for (int gq = 0; gq < 2; ++gq)
+        if (have_sigma[gq][a])
+          for (int i = 1; i <= N[a]; ++i)
+            if (h_sig[gq][a][i - 1] != T(0)) pml[a][i] = 1;
+      // longest run of non-PML cells separates the lower from the upper slab
+      int best_s = 1, best_len = 0, cur_s = 1, cur_len = 0;
+      bool any = false;
+      for (int i = 1; i <= N[a]; ++i) {
+        if (!pml[a][i]) {
+          if (cur_len == 0) cur_s = i;
+          ++cur_len;
+          if (cur_len > best_len) { best_len = cur_len; best_s = cur_s; }
+        } else { cur_len = 0; any = true; }
+      }
+      if (!any) { lo_end[a] = 0; hi_start[a] = N[a] + 1; }
+      else if (best_len == 0) { lo_end[a] = N[a]; hi_start[a] = N[a] + 1; }
+      else { lo_end[a] = best_s - 1; hi_start[a] = best_s + best_len; }
+    }
+    // slab compaction
+    {
+      int n4 = round_up(N[0], 4);
+      int low = round_up(lo_end[0], 4);
+      int hib = hi_start[0] <= N[0] ? 1 + 4 * ((hi_start[0] - 1) / 4) : n4 + 1;
+      if (low >= hib - 1) { low = n4; hib = n4 + 1; }
+      slab[0].lo_w = low; slab[0].hi_base = hib;
+      int cx = low + (n4 - hib + 1);
+      cxp = std::max(round_up(cx, 32), 32);
+      slab_elems[0] = (size_t)cxp * N[1] * N[2];
+      if (cx == 0) slab_elems[0] = 0;
+      slab[1].lo_w = lo_end[1]; slab[1].hi_base = hi_start[1];
+      cy = lo_end[1] + (N[1] - hi_start[1] + 1);
+      slab_elems[1] = (size_t)MPX * cy * N[2];
+      slab[2].lo_w = lo_end[2]; slab[2].hi_base = hi_start[2];
+      cz = lo_end[2] + (N[2] - hi_start[2] + 1);
+      slab_elems[2] = (size_t)MPX * N[1] * cz;
+    }
+    for (int gq = 0; gq < 2; ++gq)
+      for (int d = 0; d < 3; ++d) {
+        int nx = (d + 1) % 3;
+        if (slab_elems[d]) W[gq][d] = dalloc(slab_elems[d]);
+        if (slab_elems[nx]) U[gq][d] = dalloc(slab_elems[nx]);
+        bool anyp = slab_elems[0] || slab_elems[1] || slab_elems[2];
+        if (has_sd[gq] && anyp) Cst[gq][d] = dalloc(msize);
+        if (has_sd[gq] && !sigM[gq][d]) {  // absent component == zero conductivity
+          sigM[gq][d] = dalloc(msize);
+        }
+      }
+    // coefficient vectors
+    for (int gq = 0; gq < 2; ++gq)
+      for (int a = 0; a < 3; ++a) {
+        int len = round_up(N[a], 4) + 8;
+        std::vector<T> s((size_t)len, T(0)), o((size_t)len, T(1)), ip((size_t)len, T(1));
+        if (have_sigma[gq][a])
+          for (int i = 0; i < N[a]; ++i) {
+            T v = h_sig[gq][a][i];
+            s[i] = v; o[i] = T(1) - v; ip[i] = T(1) / (T(1) + v);
+          }
+        for (int q = 0; q < 3; ++q) coef[gq][a][q] = dalloc((size_t)len, false);
+        CUDA_OK(cudaMemcpyAsync(coef[gq][a][0], s.data(), len * sizeof(T), cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaMemcpyAsync(coef[gq][a][1], o.data(), len * sizeof(T), cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaMemcpyAsync(coef[gq][a][2], ip.data(), len * sizeof(T), cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+      }
+    build_tables();
+    // monitors
+    if (!monitors.empty()) {
+      std::vector<MonDesc<T>> h(monitors.size());
+      for (size_t q = 0; q < monitors.size(); ++q) {
+        Monitor& m = monitors[q];
+        MonDesc<T>& d = h[q];
+        d.M = m.M; d.F = F[m.comp]; d.freqs = m.d_freqs; d.nf = (int)m.freqs.size();
+        d.decimation = m.decimation; d.group = m.comp >= 3 ? 0 : 1;
+        // this rank accumulates the planes it owns; the top rank also owns the
+        // staggered extra plane Nz+1 (never updated, zero, but part of the box)
+        int zlo = g.z_start, zhi = g.z_start + N[2] - 1;
+        if (g.rank == g.nranks - 1) zhi += 1;
+        if (g.rank == 0) zlo = std::min(zlo, 0);
+        int s2 = std::max(m.s[2], zlo), e2 = std::min(m.e[2], zhi);
+        m.local = (e2 >= s2) && m.n[0] > 0 && m.n[1] > 0;
+        for (int a = 0; a < 2; ++a) { d.s[a] = m.s[a]; d.n[a] = m.n[a]; d.moff[a] = 0; d.mn[a] = m.n[a]; }
+        d.mn[2] = m.n[2];
+        d.s[2] = s2 - (g.z_start - 1);
+        d.n[2] = m.local ? (e2 - s2 + 1) : 0;
+        d.moff[2] = s2 - m.s[2];
+      }
+      d_mons = (MonDesc<T>*)dalloc((sizeof(MonDesc<T>) * h.size() + sizeof(T) - 1) / sizeof(T), false);
+      CUDA_OK(cudaMemcpyAsync(d_mons, h.data(), sizeof(MonDesc<T>) * h.size(), cudaMemcpyHostToDevice, stream));
+      d_due = (int*)dalloc((2 * monitors.size() * sizeof(int) + sizeof(T) - 1) / sizeof(T) + 1, false);
+      CUDA_OK(cudaMallocHost((void**)&h_due, 2 * monitors.size() * sizeof(int)));
+      CUDA_OK(cudaStreamSynchronize(stream));
+    }
+    CUDA_OK(cudaStreamSynchronize(stream));
+    finalized = true;
+  }
+
+  // split [1..n] at the PML edges; `gran` aligns the cut points outward (x only)
+  struct Range { int s, e; bool pml; };
+  std::vector<Range> axis_ranges(int a, int gran) const {
+    std::vector<Range> r;
+    int n = N[a];
+    int lo = lo_end[a], hi = hi_start[a];
+    if (lo <= 0 && hi > n) { r.push_back({1, n, false}); return r; }
+    int lo_cut = std::min(n, round_up(lo, gran));                      // last cell of the lower PML range
+    int hi_cut = hi <= n ? 1 + gran * ((hi - 1) / gran) : n + 1;      // first cell of the upper PML range
+    if (lo_cut >= hi_cut - 1) { r.push_back({1, n, true}); return r; }
+    if (lo_cut >= 1) r.push_back({1, lo_cut, true});
+    r.push_back({lo_cut + 1, hi_cut - 1, false});
+    if (hi_cut <= n) r.push_back({hi_cut, n, true});
+    return r;
+  }
+
+  void build_tables() {
+    const int ZSEG = 32;
+    std::vector<Range> xr = axis_ranges(0, 32), yr = axis_ranges(1, 1), zr = axis_ranges(2, 1);
+    // boundary planes for the halo exchange get their own thin z ranges
+    std::vector<Range> zr2;
+    for (auto r : zr) {
+      if (g.nranks > 1) {
+        // H half-step sends the top plane, E half-step the bottom plane: isolate both
+        int s = r.s, e = r.e;
+        if (s == 1 && g.rank > 0 && e > s) { zr2.push_back({1, 1, r.pml}); s = 2; }
+        if (e == N[2] && g.rank < g.nranks - 1 && e > s) { zr2.push_back({s, e - 1, r.pml}); zr2.push_back({e, e, r.pml}); }
+        else zr2.push_back({s, e, r.pml});
+      } else zr2.push_back(r);
+    }
+    for (int gq = 0; gq < 2; ++gq) {
+      int pole_box[6] = {1, 1, 1, 0, 0, 0};
+      if (gq == 1) for (auto& p : poles) box_union(pole_box, p.box);
+      for (auto& X : xr) {
+        int lxi = lx_index(X.e - X.s + 1);
+        int lx = 8 << lxi;
+        int tw = 4 * lx, th = CTA / lx;
+        for (auto& Z : zr2)
+          for (int z0 = Z.s; z0 <= Z.e; z0 += ZSEG) {
+            int zn = std::min(ZSEG, Z.e - z0 + 1);
+            for (auto& Y : yr)
+              for (int y0 = Y.s; y0 <= Y.e; y0 += th) {
+                int yh = std::min(th, Y.e - y0 + 1);
+                for (int x0 = X.s; x0 <= X.e; x0 += tw) {
+                  int xw = std::min(tw, X.e - x0 + 1);
+                  WorkItem it{x0, xw, y0, yh, z0, zn, 0, 0};
+                  bool extras = false;
+                  for (auto& s : sources) {
+                    bool sh = (s.comp >= 3) == (gq == 0);
+                    int b[6] = {s.s[0], s.s[1], s.s[2], s.s[0] + s.d[0] - 1, s.s[1] + s.d[1] - 1, s.s[2] + s.d[2] - 1};
+                    if (sh && boxes_hit(b, x0, x0 + xw - 1, y0, y0 + yh - 1, z0, z0 + zn - 1)) { extras = true; it.flags |= 1; }
+                  }
+                  if (has_sd[gq] && boxes_hit(sd_box[gq], x0, x0 + xw - 1, y0, y0 + yh - 1, z0, z0 + zn - 1)) extras = true;
+                  if (gq == 1 && boxes_hit(pole_box, x0, x0 + xw - 1, y0, y0 + yh - 1, z0, z0 + zn - 1)) extras = true;
+                  int mode = extras ? 2 : ((X.pml || Y.pml || Z.pml) ? 1 : 0);
+                  int phase = 1;
+                  if (g.nranks > 1) {
+                    if (gq == 0 && g.rank < g.nranks - 1 && z0 + zn - 1 == N[2]) phase = 0;
+                    if (gq == 1 && g.rank > 0 && z0 == 1) phase = 0;
+                  }
+                  tab[gq][phase][mode][lxi].items.push_back(it);
+                }
+              }
+          }
+      }
+      for (int ph = 0; ph < 2; ++ph)
+        for (int m = 0; m < 3; ++m)
+          for (int l = 0; l < 3; ++l) {
+            Table& t = tab[gq][ph][m][l];
+            if (t.items.empty()) continue;
+            size_t bytes = t.items.size() * sizeof(WorkItem);
+            t.d = (WorkItem*)dalloc((bytes + sizeof(T) - 1) / sizeof(T), false);
+            CUDA_OK(cudaMemcpyAsync(t.d, t.items.data(), bytes, cudaMemcpyHostToDevice, stream));
+          }
+    }
+    CUDA_OK(cudaStreamSynchronize(stream));
+  }
+
+  // ---- stepping -------------------------------------------------------------
+  template <int GROUP, int MODE, bool MARR>
+  void launch_lx(const StepParams<T>& p, int lxi, int nitems) {
+    if (lxi == 2) step_kernel<T, GROUP, 32, MODE, MARR><<<nitems, CTA, 0, stream>>>(p);
+    else if (lxi == 1) step_kernel<T, GROUP, 16, MODE, MARR><<<nitems, CTA, 0, stream>>>(p);
+    else step_kernel<T, GROUP, 8, MODE, MARR><<<nitems, CTA, 0, stream>>>(p);
+    ++launches;
+  }
+  template <int GROUP>
+  void launch_group(StepParams<T>& p, int phase, bool marr) {
+    for (int m = 0; m < 3; ++m)
+      for (int l = 0; l < 3; ++l) {
+        Table& t = tab[GROUP][phase][m][l];
+        if (t.items.empty()) continue;
+        p.items = t.d;
+        int n = (int)t.items.size();
+        if (marr) {
+          if (m == 0) launch_lx<GROUP, 0, true>(p, l, n);
+          else if (m == 1) launch_lx<GROUP, 1, true>(p, l, n);
+          else launch_lx<GROUP, 2, true>(p, l, n);
+        } else {
+          if (m == 0) launch_lx<GROUP, 0, false>(p, l, n);
+          else if (m == 1) launch_lx<GROUP, 1, false>(p, l, n);
+          else launch_lx<GROUP, 2, false>(p, l, n);
+        }
+      }
+    CUDA_OK(cudaGetLastError());
+  }
+
+  double time_now() const { return (double)((T)timestep * dt); }  // Simulation.jl:22 round_time
+
+  void fill_params(StepParams<T>& p, int gq, double t_src) {
+    memset(&p, 0, sizeof(p));
+    for (int d = 0; d < 3; ++d) {
+      p.A[d] = gq == 0 ? F[d] : F[3 + d];
+      p.F[d] = gq == 0 ? F[3 + d] : F[d];
+      p.m_arr[d] = m_arr[gq][d];
+      p.sg[d] = coef[gq][d][0]; p.om[d] = coef[gq][d][1]; p.ip[d] = coef[gq][d][2];
+      p.W[d] = W[gq][d]; p.U[d] = U[gq][d];
+      p.slab[d] = slab[d];
+      p.sigD[d] = sigM[gq][d];
+      p.C[d] = Cst[gq][d];
+      p.n[d] = N[d];
+      p.idl[d] = T(1) / dl[d];  // inv(Δ) (Helpers.jl:283)
+    }
+    p.plane = (long long)PX * PY;
+    p.px = PX;
+    p.dt = dt;
+    p.m_inv = m_scalar[gq];
+    p.mpx = MPX;
+    p.mplane = (long long)MPX * N[1];
+    p.cxp = cxp; p.cy = cy; p.cz = cz;
+    // sources of this group
+    p.nsrc = 0;
+    for (auto& s : sources) {
+      if ((s.comp >= 3) != (gq == 0)) continue;
+      if (p.nsrc >= MAXSRC) throw std::string("too many sources in one field group (max 8)");
+      SrcDesc<T>& d = p.src[p.nsrc++];
+      d.amp = s.amp; d.comp = s.comp % 3;
+      for (int a = 0; a < 3; ++a) { d.s[a] = s.s[a]; d.d[a] = s.d[a]; }
+      T re = 0, im = 0;
+      if (sources_active) eval_time_source(s.ts, t_src, &re, &im);
+      d.an_re = re; d.an_im = im; d.ao_re = s.ao_re; d.ao_im = s.ao_im;
+      s.ao_re = re; s.ao_im = im;
+    }
+    p.npole = 0;
+    if (gq == 1)
+      for (auto& pl : poles) {
+        PoleDesc<T>& d = p.pole[p.npole++];
+        d.sigma = pl.sigma;
+        for (int c = 0; c < 3; ++c) { d.Pc[c] = pl.P[pl.cur][c]; d.Pp[c] = pl.P[1 - pl.cur][c]; }
+        d.g1i = pl.g1i; d.g1 = pl.g1; d.cp = pl.cp; d.cd = pl.cd;
+      }
+  }
+
+  void update_sources_active(double t) {
+    // Kernels.jl:27-35: sticky switch-off once t > last cutoff; CW never cuts off
+    if (sources_mode == 0) { sources_active = false; return; }
+    if (sources_mode == 1) { sources_active = true; return; }
+    if (!sources_active || sources.empty()) return;
+    double last = -1e300;
+    for (auto& s : sources) {
+      if (s.ts.kind == KHR_TIME_CW) return;
+      last = std::max(last, (double)s.ts.cutoff);
+    }
+    if (t > last) sources_active = false;
+  }
+
+  void need_final() const {
+    if (!finalized) throw std::string("khr_finalize_plan has not been called");
+  }
+
+  // send/recv of the two tangential components' boundary plane with the z neighbours
+  void post_halo(int gq) {
+    if (g.nranks <= 1) return;
+    if (!comm) throw std::string("nranks > 1 but khr_comm_init was not called");
+    size_t cnt = (size_t)PX * PY * sizeof(T);
+    CUDA_OK(cudaEventRecord(ev_boundary, stream));
+    CUDA_OK(cudaStreamWaitEvent(comm_stream, ev_boundary, 0));
+    NCCL_OK(g_nccl.GroupStart());
+    for (int c = 0; c < 2; ++c) {
+      if (gq == 0) {
+        // H: my top interior plane -> +z neighbour's lower ghost (E update reads H[k-1])
+        T* f = F[3 + c];
+        if (g.rank < g.nranks - 1) NCCL_OK(g_nccl.Send(f + (size_t)PX * PY * N[2], cnt, /*ncclChar*/ 0, g.rank + 1, comm, comm_stream));
+        if (g.rank > 0) NCCL_OK(g_nccl.Recv(f, cnt, 0, g.rank - 1, comm, comm_stream));
+      } else {
+        // E: my bottom interior plane -> -z neighbour's upper ghost (H update reads E[k+1])
+        T* f = F[c];
+        if (g.rank > 0) NCCL_OK(g_nccl.Send(f + (size_t)PX * PY, cnt, 0, g.rank - 1, comm, comm_stream));
+        if (g.rank < g.nranks - 1) NCCL_OK(g_nccl.Recv(f + (size_t)PX * PY * (N[2] + 1), cnt, 0, g.rank + 1, comm, comm_stream));
+      }
+    }
+    NCCL_OK(g_nccl.GroupEnd());
+    CUDA_OK(cudaEventRecord(ev_comm, comm_stream));
+  }
+  void wait_halo() {
+    if (g.nranks <= 1) return;
+    CUDA_OK(cudaStreamWaitEvent(stream, ev_comm, 0));
+  }
+
+  void half_step(int gq, double t_src) {
+    StepParams<T> p;
+    fill_params(p, gq, t_src);
+    bool marr = m_arr[gq][0] != nullptr;
+    if (marr && (!m_arr[gq][1] || !m_arr[gq][2])) throw std::string("per-voxel material needs all three components");
+    if (g.nranks > 1) {
+      // boundary planes first, ship them while the interior updates
+      if (gq == 0) launch_group<0>(p, 0, marr); else launch_group<1>(p, 0, marr);
+      post_halo(gq);
+      if (gq == 0) launch_group<0>(p, 1, marr); else launch_group<1>(p, 1, marr);
+      wait_halo();
+    } else {
+      if (gq == 0) launch_group<0>(p, 1, marr); else launch_group<1>(p, 1, marr);
+    }
+    if (gq == 1) for (auto& pl : poles) pl.cur = 1 - pl.cur;
+  }
+
+  void step_h() override {
+    need_final();
+    double t = time_now();
+    update_sources_active(t);
+    half_step(0, t);
+  }
+  void step_e() override {
+    need_final();
+    double t = time_now() + (double)(dt / T(2));
+    half_step(1, t);
+  }
+  void dft_update(int group, double time) override {
+    need_final();
+    if (monitors.empty()) return;
+    int nd = 0;
+    long long maxcells = 0;
+    for (size_t q = 0; q < monitors.size(); ++q) {
+      Monitor& m = monitors[q];
+      if ((m.comp >= 3) != (group == 0)) continue;
+      if (!m.local) continue;
+      if (m.decimation > 1 && (timestep % m.decimation) != 0) continue;  // Kernels.jl:465-497
+      h_due[group * monitors.size() + nd++] = (int)q;
+      maxcells = std::max(maxcells, (long long)m.n[0] * m.n[1] * m.n[2]);
+    }
+    if (nd == 0) return;
+    // the due list only changes when decimations differ; upload on change only
+    std::vector<int> now(h_due + group * monitors.size(), h_due + group * monitors.size() + nd);
+    if (now != last_due[group]) {
+      CUDA_OK(cudaMemcpyAsync(d_due + group * monitors.size(), h_due + group * monitors.size(), nd * sizeof(int),
+                              cudaMemcpyHostToDevice, stream));
+      CUDA_OK(cudaStreamSynchronize(stream));
+      last_due[group] = now;
+    }
+    const double two_pi = 2 * 3.141592653589793;
+    T tf = (T)(two_pi * time);  // Monitors.jl:323 complex_backend_number(im*2π*time)
+    dim3 grid((unsigned)((maxcells + 255) / 256), (unsigned)nd);
+    dft_kernel<T><<<grid, 256, 0, stream>>>(d_mons, d_due + group * monitors.size(), tf, dt, (long long)PX * PY, PX);
+    ++launches;
+    CUDA_OK(cudaGetLastError());
+  }
+  void step(int n) override {
+    need_final();
+    launches = 0;
+    CUDA_OK(cudaEventRecord(ev_t0, stream));
+    for (int i = 0; i < n; ++i) {
+      double t = time_now();
+      double th = t + (double)(dt / T(2));
+      update_sources_active(t);
+      half_step(0, t);
+      dft_update(0, t);
+      half_step(1, th);
+      dft_update(1, th);
+      timestep += 1;
+    }
+    CUDA_OK(cudaEventRecord(ev_t1, stream));
+    last_launches = launches;
+    last_ms = -1;
+  }
+  void reset_fields() override {
+    for (int c = 0; c < 6; ++c) CUDA_OK(cudaMemsetAsync(F[c], 0, fsize * sizeof(T), stream));
+    for (int gq = 0; gq < 2; ++gq)
+      for (int d = 0; d < 3; ++d) {
+        int nx = (d + 1) % 3;
+        if (W[gq][d]) CUDA_OK(cudaMemsetAsync(W[gq][d], 0, slab_elems[d] * sizeof(T), stream));
+        if (U[gq][d]) CUDA_OK(cudaMemsetAsync(U[gq][d], 0, slab_elems[nx] * sizeof(T), stream));
+        if (Cst[gq][d]) CUDA_OK(cudaMemsetAsync(Cst[gq][d], 0, msize * sizeof(T), stream));
+      }
+    for (auto& p : poles)
+      for (int q = 0; q < 2; ++q)
+        for (int d = 0; d < 3; ++d) CUDA_OK(cudaMemsetAsync(p.P[q][d], 0, msize * sizeof(T), stream));
+    for (auto& m : monitors) CUDA_OK(cudaMemsetAsync(m.M, 0, 2 * m.elems * sizeof(T), stream));
+    for (auto& s : sources) { s.ao_re = 0; s.ao_im = 0; }
+    timestep = 0;
+    sources_active = true;
+  }
+  void comm_init(const void* id, int nranks, int rank) override {
+    if (nranks != g.nranks || rank != g.rank) throw std::string("khr_comm_init: rank/nranks differ from the grid descriptor");
+    load_nccl();
+    Id128 u;
+    memcpy(u.b, id, 128);
+    CUDA_OK(cudaSetDevice(device));
+    NCCL_OK(g_nccl.CommInitRank(&comm, nranks, u, rank));
+  }
+  void halo_exchange(int gq) override {
+    post_halo(gq);
+    wait_halo();
+    CUDA_OK(cudaStreamSynchronize(stream));
+  }
+
+  void field_read(int comp, void* out) override {
+    std::vector<T> h(fsize);
+    CUDA_OK(cudaStreamSynchronize(stream));
+    CUDA_OK(cudaMemcpy(h.data(), F[comp], fsize * sizeof(T), cudaMemcpyDeviceToHost));
+    T* o = (T*)out;
+    for (int z = 1; z <= N[2]; ++z)
+      for (int y = 1; y <= N[1]; ++y)
+        memcpy(o + (size_t)N[0] * ((size_t)(y - 1) + (size_t)N[1] * (z - 1)), h.data() + fidx(1, y, z), N[0] * sizeof(T));
+  }
+  void field_write(int comp, const void* in) override {
+    need_final();
+    std::vector<T> h(fsize, T(0));
+    const T* src = (const T*)in;
+    for (int z = 1; z <= N[2]; ++z)
+      for (int y = 1; y <= N[1]; ++y)
+        memcpy(h.data() + fidx(1, y, z), src + (size_t)N[0] * ((size_t)(y - 1) + (size_t)N[1] * (z - 1)), N[0] * sizeof(T));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    CUDA_OK(cudaMemcpy(F[comp], h.data(), fsize * sizeof(T), cudaMemcpyHostToDevice));
+    // keep the W history consistent with the stored field (W = m^-1 * net = A)
+    int gq = comp >= 3 ? 0 : 1, d = comp % 3;
+    if (W[gq][d]) {
+      std::vector<T> w(slab_elems[d] + 64, T(0));
+      for (int z = 1; z <= N[2]; ++z)
+        for (int y = 1; y <= N[1]; ++y)
+          for (int x = 1; x <= N[0]; ++x) {
+            int i[3] = {x, y, z};
+            if (h_sig[gq][d].empty() || h_sig[gq][d][i[d] - 1] == T(0)) continue;
+            size_t wi;
+            if (d == 0) wi = (size_t)(slab[0].idx(1 + 4 * ((x - 1) / 4)) + (x - 1) % 4) + (size_t)cxp * ((size_t)(y - 1) + (size_t)N[1] * (z - 1));
+            else if (d == 1) wi = (size_t)(x - 1) + (size_t)MPX * ((size_t)slab[1].idx(y) + (size_t)cy * (z - 1));
+            else wi = (size_t)(x - 1) + (size_t)MPX * ((size_t)(y - 1) + (size_t)N[1] * slab[2].idx(z));
+            w[wi] = h[fidx(x, y, z)];
+          }
+      CUDA_OK(cudaMemcpy(W[gq][d], w.data(), slab_elems[d] * sizeof(T), cudaMemcpyHostToDevice));
+    }
+  }
+  void field_view(int comp, void** p, int64_t* stride, int64_t* off) override {
+    *p = F[comp];
+    stride[0] = 1; stride[1] = PX; stride[2] = (int64_t)PX * PY;
+    *off = XO;
+  }
+  void monitor_read(int id, void* out) override {
+    if (id < 0 || id >= (int)monitors.size()) throw std::string("bad monitor id");
+    CUDA_OK(cudaStreamSynchronize(stream));
+    CUDA_OK(cudaMemcpy(out, monitors[id].M, 2 * monitors[id].elems * sizeof(T), cudaMemcpyDeviceToHost));
+  }
+  void monitor_view(int id, void** p, int64_t* dims) override {
+    if (id < 0 || id >= (int)monitors.size()) throw std::string("bad monitor id");
+    Monitor& m = monitors[id];
+    *p = m.M;
+    dims[0] = m.n[0]; dims[1] = m.n[1]; dims[2] = m.n[2]; dims[3] = (int64_t)m.freqs.size();
+  }
+  double monitor_norm(int id) override {
+    if (id < 0 || id >= (int)monitors.size()) throw std::string("bad monitor id");
+    std::vector<T> h(2 * monitors[id].elems);
+    monitor_read(id, h.data());
+    double s = 0;
+    for (T v : h) s += (double)v * (double)v;
+    return std::sqrt(s);
+  }
+  void sync() override {
+    CUDA_OK(cudaStreamSynchronize(stream));
+    CUDA_OK(cudaStreamSynchronize(comm_stream));
+    if (last_ms < 0) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, ev_t0, ev_t1) == cudaSuccess) last_ms = ms;
+      else { cudaGetLastError(); last_ms = 0; }
+    }
+  }
+  void census(int64_t* c) override {
+    need_final();
+    int64_t np[3], nn[3];
+    for (int a = 0; a < 3; ++a) {
+      int64_t k = 0;
+      for (int i = 1; i <= N[a]; ++i) {
+        bool on = false;
+        for (int gq = 0; gq < 2; ++gq)
+          if (have_sigma[gq][a] && h_sig[gq][a][i - 1] != T(0)) on = true;
+        k += on;
+      }
+      np[a] = k; nn[a] = N[a] - k;
+    }
+    c[0] = nn[0] * nn[1] * nn[2];
+    c[1] = np[0] * nn[1] * nn[2] + nn[0] * np[1] * nn[2] + nn[0] * nn[1] * np[2];
+    c[2] = np[0] * np[1] * nn[2] + np[0] * nn[1] * np[2] + nn[0] * np[1] * np[2];
+    c[3] = np[0] * np[1] * np[2];
+  }
+};
+
+}  // namespace khr
+
+// ============================================================================
+// C ABI
+// ============================================================================
+struct khr_ctx {
+  khr::Base* impl;
+};
+
+#define KHR_TRY(...)                               \
+  try {                                            \
+    __VA_ARGS__;                                   \
+    return 0;                                      \
+  } catch (const std::string& e) {                 \
+    return khr::fail(e);                           \
+  } catch (const std::exception& e) {              \
+    return khr::fail(e.what());                    \
+  } catch (...) {                                  \
+    return khr::fail("unknown error");             \
+  }
+#define NEED_CTX                                   \
+  if (!ctx || !ctx->impl) return khr::fail("null context");
+
+extern "C" {
+
+const char* khr_last_error(void) { return khr::g_err.c_str(); }
+int32_t khr_version(void) { return 100; }
+
+int32_t khr_ctx_create(int32_t device, const khr_grid_desc* grid, khr_ctx** out) {
+  if (!grid || !out) return khr::fail("null argument");
+  KHR_TRY({
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      throw std::string("no CUDA device available (libkhronos_b200 has no CPU fallback): ") + cudaGetErrorString(e);
+    if (device < 0 || device >= ndev) throw std::string("bad device index");
+    if (grid->n[0] < 1 || grid->n[1] < 1 || grid->n[2] < 1 || grid->nz_local < 1)
+      throw std::string("3-D grids only (Nx,Ny,Nz >= 1); 2-D (Nz == 0) is not supported");
+    if (grid->z_start < 1 || grid->z_start + grid->nz_local - 1 > grid->n[2]) throw std::string("bad z slab");
+    if (grid->nranks < 1 || grid->rank < 0 || grid->rank >= grid->nranks) throw std::string("bad rank");
+    khr_ctx* c = new khr_ctx;
+    if (grid->dtype == KHR_F32) c->impl = new khr::Impl<float>(device, *grid);
+    else if (grid->dtype == KHR_F64) c->impl = new khr::Impl<double>(device, *grid);
+    else { delete c; throw std::string("dtype must be KHR_F32 or KHR_F64"); }
+    *out = c;
+  })
+}
+int32_t khr_ctx_destroy(khr_ctx* ctx) {
+  if (!ctx) return 0;
+  KHR_TRY({ delete ctx->impl; delete ctx; })
+}
+int32_t khr_set_pml_sigma(khr_ctx* ctx, int32_t group, int32_t axis, const void* sigma, int32_t len) {
+  NEED_CTX
+  if (group < 0 || group > 1 || axis < 0 || axis > 2 || !sigma) return khr::fail("bad argument");
+  KHR_TRY(ctx->impl->set_pml_sigma(group, axis, sigma, len))
+}
+int32_t khr_set_material_scalar(khr_ctx* ctx, int32_t kind, double value) {
+  NEED_CTX
+  KHR_TRY(ctx->impl->set_material_scalar(kind, value))
+}
+int32_t khr_set_material_array(khr_ctx* ctx, int32_t kind, int32_t comp, const void* dense) {
+  NEED_CTX
+  if (!dense) return khr::fail("null array");
+  KHR_TRY(ctx->impl->set_material_array(kind, comp, dense))
+}
+int32_t khr_pole_register(khr_ctx* ctx, double omega0, double gamma, const void* sigma_dense, int32_t* pole_id) {
+  NEED_CTX
+  if (!sigma_dense) return khr::fail("null array");
+  KHR_TRY({ int id = ctx->impl->pole_register(omega0, gamma, sigma_dense); if (pole_id) *pole_id = id; })
+}
+int32_t khr_source_register(khr_ctx* ctx, int32_t comp, const int32_t start[3], const int32_t dims[3],
+                            const void* amp_complex, int32_t time_kind, const double tp[4], int32_t* source_id) {
+  NEED_CTX
+  if (comp < 0 || comp > 5 || !start || !dims || !amp_complex || !tp) return khr::fail("bad argument");
+  if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1) return khr::fail("empty source box");
+  KHR_TRY({ int id = ctx->impl->source_register(comp, start, dims, amp_complex, time_kind, tp); if (source_id) *source_id = id; })
+}
+int32_t khr_source_set_amplitude(khr_ctx* ctx, int32_t source_id, double re, double im) {
+  NEED_CTX
+  KHR_TRY(ctx->impl->source_set_amplitude(source_id, re, im))
+}
+int32_t khr_set_sources_active(khr_ctx* ctx, int32_t mode) {
+  NEED_CTX
+  ctx->impl->sources_mode = mode;
+  if (mode == 1) ctx->impl->sources_active = true;
+  if (mode == 0) ctx->impl->sources_active = false;
+  return 0;
+}
+int32_t khr_monitor_register(khr_ctx* ctx, int32_t comp, const int32_t start[3], const int32_t end[3], int32_t nfreq,
+                             const double* freqs, int32_t decimation, int32_t* monitor_id) {
+  NEED_CTX
+  if (comp < 0 || comp > 5 || !start || !end || nfreq < 1 || !freqs) return khr::fail("bad argument");
+  KHR_TRY({ int id = ctx->impl->monitor_register(comp, start, end, nfreq, freqs, decimation); if (monitor_id) *monitor_id = id; })
+}
+int32_t khr_finalize_plan(khr_ctx* ctx) {
+  NEED_CTX
+  KHR_TRY(ctx->impl->finalize())
+}
+int32_t khr_step(khr_ctx* ctx, int32_t nsteps) {
+  NEED_CTX
+  KHR_TRY(ctx->impl->step(nsteps))
+}
+int32_t khr_step_h(khr_ctx* ctx) {
+  NEED_CTX
+  KHR_TRY(ctx->impl->step_h())
+}
+int32_t khr_step_e(khr_ctx* ctx) {
+  NEED_CTX
+  KHR_TRY(ctx->impl->step_e())
+}
+int32_t khr_dft_update(khr_ctx* ctx, int32_t group, double time) {
+  NEED_CTX
+  KHR_TRY(ctx->impl->dft_update(group, time))
+}
+int32_t khr_get_timestep(khr_ctx* ctx, int64_t* timestep) {
+  NEED_CTX
+  *timestep = ctx->impl->timestep;
+  return 0;
+}
+int32_t khr_set_timestep(khr_ctx* ctx, int64_t timestep) {
+  NEED_CTX
+  ctx->impl->timestep = timestep;
+  return 0;
+}
+int32_t khr_reset_fields(khr_ctx* ctx) {
+  NEED_CTX
+  KHR_TRY(ctx->impl->reset_fields())
+}
+int32_t khr_comm_unique_id(void* out128) {
+  KHR_TRY({ khr::load_nccl(); NCCL_OK(khr::g_nccl.GetUniqueId(out128)); })
+}
+int32_t khr_comm_init(khr_ctx* ctx, const void* unique_id128, int32_t nranks, int32_t rank) {
+  NEED_CTX
+  KHR_TRY(ctx->impl->comm_init(unique_id128, nranks, rank))
+}
+int32_t khr_halo_exchange(khr_ctx* ctx, int32_t group) {
+  NEED_CTX
+  KHR_TRY(ctx->impl->halo_exchange(group))
+}
+int32_t khr_field_read(khr_ctx* ctx, int32_t comp, void* dense_out) {
+  NEED_CTX
+  if (comp < 0 || comp > 5 || !dense_out) return khr::fail("bad argument");
+  KHR_TRY(ctx->impl->field_read(comp, dense_out))
+}
+int32_t khr_field_write(khr_ctx* ctx, int32_t comp, const void* dense_in) {
+  NEED_CTX
+  if (comp < 0 || comp > 5 || !dense_in) return khr::fail("bad argument");
+  KHR_TRY(ctx->impl->field_write(comp, dense_in))
+}
+int32_t khr_field_view(khr_ctx* ctx, int32_t comp, void** dev_ptr, int64_t stride[3], int64_t* offset) {
+  NEED_CTX
+  if (comp < 0 || comp > 5) return khr::fail("bad component");
+  KHR_TRY(ctx->impl->field_view(comp, dev_ptr, stride, offset))
+}
+int32_t khr_monitor_read(khr_ctx* ctx, int32_t monitor_id, void* complex_out) {
+  NEED_CTX
+  KHR_TRY(ctx->impl->monitor_read(monitor_id, complex_out))
+}
+int32_t khr_monitor_view(khr_ctx* ctx, int32_t monitor_id, void** dev_ptr, int64_t dims[4]) {
+  NEED_CTX
+  KHR_TRY(ctx->impl->monitor_view(monitor_id, dev_ptr, dims))
+}
+int32_t khr_monitor_norm(khr_ctx* ctx, int32_t monitor_id, double* norm) {
+  NEED_CTX
+  KHR_TRY(*norm = ctx->impl->monitor_norm(monitor_id))
+}
+int32_t khr_sync(khr_ctx* ctx) {
+  NEED_CTX
+  KHR_TRY(ctx->impl->sync())
+}
+int32_t khr_get_stream(khr_ctx* ctx, void** cuda_stream) {
+  NEED_CTX
+  *cuda_stream = (void*)ctx->impl->stream;
+  return 0;
+}
+int32_t khr_last_step_timing(khr_ctx* ctx, double* ms, int64_t* kernel_launches) {
+  NEED_CTX
+  KHR_TRY({ ctx->impl->sync(); if (ms) *ms = ctx->impl->last_ms; if (kernel_launches) *kernel_launches = ctx->impl->last_launches; })
+}
+int32_t khr_voxel_census(khr_ctx* ctx, int64_t counts[4]) {
+  NEED_CTX
+  KHR_TRY(ctx->impl->census(counts))
+}
+int32_t khr_device_bytes(khr_ctx* ctx, int64_t* bytes) {
+  NEED_CTX
+  *bytes = ctx->impl->dev_bytes;
+  return 0;
+}
+
+}  // extern "C"

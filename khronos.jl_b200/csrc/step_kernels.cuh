@@ -1,0 +1,556 @@
+// ============================================================================
+// step_kernels.cuh — the Yee half-step kernels of libkhronos_b200 (sm_100a)
+//
+// One kernel family covers both half-steps of Khronos.jl's step!
+// (reference: src/Kernels/Kernels.jl:164-296 step_H_fused!, :298-454
+// step_E_fused!) for every voxel class:
+//   * curl + constitutive update      (Helpers.jl:286-298, ReferenceKernels.jl:323-362)
+//   * the C -> U -> T -> W PML cascade (Helpers.jl:30-33, 39-270, 323-366)
+//   * material conductivity sigma_D/B (Helpers.jl:141-154, 273-279)
+//   * current sources                 (Sources/Sources.jl:346-357)
+//   * Drude/Lorentz ADE polarisation  (Dispersive.jl:25-117, fused into the E half-step)
+//
+// Design (B200: HBM-bound stencil, no tensor cores):
+//   - every thread owns 4 consecutive x cells (one 128-bit load per array for
+//     Float32), LX lanes span a 4*LX-cell row, 256/LX rows per CTA; the CTA
+//     marches up z over its work item, carrying the z-neighbour plane in
+//     registers so every E/H array is read from HBM once per half-step
+//   - x neighbours come from warp shuffles (one scalar edge load per row)
+//   - the flux fields B/D are *eliminated everywhere*: all stages are linear,
+//     so the cascade is run on mu^-1/eps^-1-scaled quantities and the T stage
+//     acts on the stored field itself (A where sigma_own == 0, W otherwise).
+//     A PML voxel therefore moves only U (sigma_next != 0) and W (sigma_own != 0)
+//     in addition to the 9/12 interior words: 4w/8w/12w extra per half-step for
+//     1/2/3 PML axes instead of the reference's 10w/14w/18w.
+//   - auxiliary arrays are stored only on the slabs where their sigma != 0
+//   - all bypasses are value driven (sigma == 0), exactly like the reference's
+//     (Helpers.jl:53, 337), so one contiguous array per GPU reproduces the
+//     single-chunk semantics; the reference's 27-chunk plan is never needed.
+// ============================================================================
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace khr {
+
+constexpr int XO = 31;        // storage x offset: cell ix lives at sx = ix + XO (cell 1 is 128 B aligned)
+constexpr int MAXSRC = 8;     // sources per field group handled in one launch
+constexpr int MAXPOLE = 4;    // ADE poles handled in one launch
+constexpr int CTA = 256;
+
+struct WorkItem {
+  int x0, xw;   // first cell (x0 % 4 == 1) and number of cells in x
+  int y0, yh;   // first row and number of rows (<= 256/LX)
+  int z0, zn;   // first local plane and number of planes marched
+  int flags;    // bit0: tile may contain a source of this group
+  int pad;
+};
+
+// compact index along a PML axis: cells 1..lo_w map to 0..lo_w-1, cells >= hi_base
+// map to lo_w + (i - hi_base)
+struct Slab {
+  int lo_w, hi_base;
+  __host__ __device__ inline int idx(int i) const { return i <= lo_w ? i - 1 : lo_w + (i - hi_base); }
+};
+
+template <class T>
+struct SrcDesc {
+  const T* amp;       // complex interleaved, extent (dx,dy,dz)
+  int comp;           // 0..2 within the group
+  int s[3], d[3];     // local start cell, extent
+  T an_re, an_im;     // amplitude a(t) of this step
+  T ao_re, ao_im;     // amplitude applied in the previous step (0 if none)
+};
+
+template <class T>
+struct PoleDesc {
+  const T* sigma;     // material layout
+  const T* Pc[3];     // P^n
+  T* Pp[3];           // P^{n-1}; receives P^{n+1} (host swaps afterwards)
+  T g1i, g1, cp, cd;  // gamma1_inv, gamma1, coefficient of P^n, coefficient of sigma*E
+};
+
+template <class T>
+struct StepParams {
+  const T* A[3];      // curl operand (E for the H half-step, H for the E half-step)
+  T* F[3];            // updated field
+  long long plane;    // PX*PY
+  int px;             // PX
+  int n[3];           // local cells
+  T dt, idl[3];
+  // constitutive factor
+  T m_inv;
+  const T* m_arr[3];  // material layout or null
+  int mpx;            // material row pitch
+  long long mplane;   // mpx*Ny
+  // PML coefficient vectors per axis, index i-1: sigma, 1-sigma, 1/(1+sigma)
+  const T* sg[3];
+  const T* om[3];
+  const T* ip[3];
+  // auxiliary slabs: W[d] lives on the slab of axis d, U[d] on the slab of axis next(d)
+  T* W[3];
+  T* U[3];
+  Slab slab[3];
+  int cxp;            // x-slab row pitch
+  int cy, cz;         // compact extents of the y / z slabs
+  // material conductivity (absorbers): sigma arrays + C stage arrays (material layout)
+  const T* sigD[3];
+  T* C[3];
+  // sources
+  int nsrc;
+  SrcDesc<T> src[MAXSRC];
+  // ADE
+  int npole;
+  PoleDesc<T> pole[MAXPOLE];
+  const WorkItem* items;
+};
+
+template <class T>
+struct alignas(sizeof(T) * 4) V4 {
+  T v[4];
+};
+template <class T>
+__device__ __forceinline__ V4<T> ld4(const T* p) {
+  return *reinterpret_cast<const V4<T>*>(p);
+}
+template <class T>
+__device__ __forceinline__ void st4(T* p, const V4<T>& a) {
+  *reinterpret_cast<V4<T>*>(p) = a;
+}
+template <class T>
+__device__ __forceinline__ V4<T> zero4() {
+  V4<T> a;
+  a.v[0] = a.v[1] = a.v[2] = a.v[3] = T(0);
+  return a;
+}
+
+template <class T>
+struct Co {  // PML coefficients of one cell along one axis
+  T s, om, ip;
+};
+
+// ----------------------------------------------------------------------------
+// One component of the general cascade for the 4 cells of a thread.
+//   k      : m^-1 * K (scaled curl increment)
+//   cn/cp/co: coefficients along next/prev/own axis (per element)
+//   useU/useW: thread-level "any sigma != 0" on the next/own axis
+//   a      : field values (in: old, out: new)
+//   s_old/s_new: m^-1-scaled additive terms riding on the stored field
+//                (source S and polarisation -P) of the previous / this step
+//   sd     : 0.5*dt*sigma_D per element (0 when absent); Cp: C-stage array or null
+// ----------------------------------------------------------------------------
+template <class T, bool EXTRAS>
+__device__ __forceinline__ void cascade(const T (&k)[4], const Co<T> (&cn)[4], const Co<T> (&cp)[4],
+                                        const Co<T> (&co)[4], bool useU, bool useW, T* __restrict__ Up,
+                                        T* __restrict__ Wp, T (&a)[4], const T (&s_old)[4], const T (&s_new)[4],
+                                        bool has_sd, const T (&sd)[4], T* __restrict__ Cp, const bool (&valid)[4]) {
+  T in[4];
+  T omt[4], ipt[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    in[e] = k[e];
+    omt[e] = cp[e].om;
+    ipt[e] = cp[e].ip;
+  }
+  if (EXTRAS && has_sd) {
+    bool anyc = false;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) anyc |= (sd[e] != T(0)) && (cn[e].s != T(0) || cp[e].s != T(0));
+    V4<T> c = zero4<T>();
+    if (anyc && Cp) c = ld4(Cp);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (sd[e] != T(0)) {
+        if (cn[e].s != T(0) || cp[e].s != T(0)) {
+          // C stage (Helpers.jl:60-68): C <- ((1-sD)C + K)/(1+sD); dC feeds the next stage
+          T c_old = c.v[e];
+          T c_new = ((T(1) - sd[e]) * c_old + in[e]) / (T(1) + sd[e]);
+          in[e] = c_new - c_old;
+          if (valid[e]) c.v[e] = c_new;
+        } else {
+          // single stage (Helpers.jl:141-154): T <- ((1-sD)T + K)/(1+sD)
+          omt[e] = T(1) - sd[e];
+          ipt[e] = T(1) / (T(1) + sd[e]);
+        }
+      }
+    }
+    if (anyc && Cp) st4(Cp, c);
+  }
+  if (useU) {
+    // U stage (Helpers.jl:55-56): U <- ((1-sn)U + in)/(1+sn); bypassed where sn == 0
+    V4<T> u = ld4(Up);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      T un = (cn[e].om * u.v[e] + in[e]) * cn[e].ip;
+      bool on = cn[e].s != T(0);
+      in[e] = on ? (un - u.v[e]) : in[e];
+      if (on && valid[e]) u.v[e] = un;
+    }
+    st4(Up, u);
+  }
+  V4<T> w = zero4<T>();
+  if (useW) w = ld4(Wp);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    bool won = useW && (co[e].s != T(0));
+    // T stage on the stored (scaled) flux: t = m^-1 (T + S - P); the additive
+    // S/P parts are not damped by the reference, so peel them off and put the
+    // new ones back (Helpers.jl:332-335)
+    T t_old = won ? w.v[e] : a[e];
+    T t_new;
+    if constexpr (EXTRAS) t_new = (omt[e] * (t_old - s_old[e]) + in[e]) * ipt[e] + s_new[e];
+    else t_new = (omt[e] * t_old + in[e]) * ipt[e];
+    // W stage (Helpers.jl:336-343)
+    T a_new = won ? ((a[e] + (T(1) + co[e].s) * t_new) - co[e].om * t_old) : t_new;
+    if (valid[e]) {
+      a[e] = a_new;
+      if (won) w.v[e] = t_new;
+    }
+  }
+  if (useW) st4(Wp, w);
+}
+
+// ----------------------------------------------------------------------------
+// The half-step kernel.
+//   GROUP 0: H from curl E (idx_curl = +1); GROUP 1: E from curl H (idx_curl = -1)
+//   MODE 0: pure interior; 1: + PML cascade; 2: + sigma_D/B, sources, ADE poles
+//   MARR   : per-voxel m^-1 arrays (eps^-1 or mu^-1) instead of a scalar
+// ----------------------------------------------------------------------------
+template <class T, int GROUP, int LX, int MODE, bool MARR>
+__global__ void __launch_bounds__(CTA) step_kernel(const __grid_constant__ StepParams<T> p) {
+  constexpr int IC = (GROUP == 0) ? 1 : -1;
+  constexpr bool GENERAL = MODE >= 1;   // PML cascade
+  constexpr bool EXTRAS = MODE == 2;    // + sources, sigma_D/B, ADE poles
+  const WorkItem it = p.items[blockIdx.x];
+  const int lane_x = threadIdx.x % LX;
+  const int row = threadIdx.x / LX;
+  const int gx = it.x0 + 4 * lane_x;
+  const int iy = it.y0 + row;
+  const int lanes = (it.xw + 3) >> 2;
+  const bool act = (lane_x < lanes) && (row < it.yh);
+  // the lane that cannot get its x neighbour from a shuffle
+  const bool edge = (GROUP == 0) ? (lane_x == lanes - 1) : (lane_x == 0);
+  bool valid[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) valid[e] = (4 * lane_x + e) < it.xw;
+
+  const int fo = (gx + XO) + p.px * iy;                    // in-plane field offset
+  const int mo = (gx - 1) + p.mpx * (iy - 1);              // in-plane material offset
+  const T* __restrict__ Ax = p.A[0];
+  const T* __restrict__ Ay = p.A[1];
+  const T* __restrict__ Az = p.A[2];
+  const T dt = p.dt, idx_ = p.idl[0], idy_ = p.idl[1], idz_ = p.idl[2];
+
+  // ---- per-thread constants of the general path ----
+  Co<T> cx[4], cyc;
+  bool hasx = false, hasy = false;
+  int xs_off = 0, ys_off = 0;  // in-slab offsets (without the z part)
+  if constexpr (GENERAL) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { cx[e].s = T(0); cx[e].om = T(1); cx[e].ip = T(1); }
+    cyc.s = T(0); cyc.om = T(1); cyc.ip = T(1);
+    if (act) {
+      V4<T> s = ld4(p.sg[0] + gx - 1), o = ld4(p.om[0] + gx - 1), i = ld4(p.ip[0] + gx - 1);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        cx[e].s = s.v[e]; cx[e].om = o.v[e]; cx[e].ip = i.v[e];
+        hasx |= (s.v[e] != T(0));
+      }
+      cyc.s = p.sg[1][iy - 1]; cyc.om = p.om[1][iy - 1]; cyc.ip = p.ip[1][iy - 1];
+      hasy = cyc.s != T(0);
+      if (hasx) xs_off = p.slab[0].idx(gx) + p.cxp * (iy - 1);
+      if (hasy) ys_off = (gx - 1) + p.mpx * p.slab[1].idx(iy);
+    }
+  }
+  // sources: which table entries can touch this tile (block-uniform mask)
+  unsigned srcmask = 0;
+  if constexpr (EXTRAS) {
+    if (it.flags & 1) {
+      for (int q = 0; q < p.nsrc; ++q) {
+        const SrcDesc<T>& s = p.src[q];
+        bool hit = (s.s[0] < it.x0 + it.xw) && (s.s[0] + s.d[0] > it.x0) && (s.s[1] < it.y0 + it.yh) &&
+                   (s.s[1] + s.d[1] > it.y0) && (s.s[2] < it.z0 + it.zn) && (s.s[2] + s.d[2] > it.z0);
+        if (hit) srcmask |= 1u << q;
+      }
+    }
+  }
+
+  // ---- z-neighbour carry ----
+  V4<T> ax_c = zero4<T>(), ay_c = zero4<T>();  // GROUP 0: current plane; GROUP 1: plane below
+  {
+    const long long b0 = p.plane * (long long)(GROUP == 0 ? it.z0 : it.z0 - 1) + fo;
+    if (act) { ax_c = ld4(Ax + b0); ay_c = ld4(Ay + b0); }
+  }
+
+  for (int iz = it.z0; iz < it.z0 + it.zn; ++iz) {
+    const long long base = p.plane * (long long)iz + fo;
+    V4<T> ax0, ay0, az0, ax_z, ay_z, az_y, ax_y;
+    T ay_x = T(0), az_x = T(0);
+    if (act) {
+      if constexpr (GROUP == 0) {
+        ax0 = ax_c; ay0 = ay_c;
+        ax_z = ld4(Ax + base + p.plane);
+        ay_z = ld4(Ay + base + p.plane);
+      } else {
+        ax_z = ax_c; ay_z = ay_c;
+        ax0 = ld4(Ax + base);
+        ay0 = ld4(Ay + base);
+      }
+      az0 = ld4(Az + base);
+      az_y = ld4(Az + base + IC * p.px);
+      ax_y = ld4(Ax + base + IC * p.px);
+      if (edge) {
+        ay_x = Ay[base + (GROUP == 0 ? 4 : -1)];
+        az_x = Az[base + (GROUP == 0 ? 4 : -1)];
+      }
+    } else {
+      ax0 = ay0 = az0 = ax_z = ay_z = az_y = ax_y = zero4<T>();
+    }
+    // x neighbour by shuffle inside the LX-lane row
+    {
+      T sy, sz;
+      if constexpr (GROUP == 0) {
+        sy = __shfl_down_sync(0xffffffffu, ay0.v[0], 1, LX);
+        sz = __shfl_down_sync(0xffffffffu, az0.v[0], 1, LX);
+      } else {
+        sy = __shfl_up_sync(0xffffffffu, ay0.v[3], 1, LX);
+        sz = __shfl_up_sync(0xffffffffu, az0.v[3], 1, LX);
+      }
+      if (!edge) { ay_x = sy; az_x = sz; }
+    }
+    if (act) {
+      T kx[4], ky[4], kz[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        T ayx, azx;
+        if constexpr (GROUP == 0) {
+          ayx = (e < 3) ? ay0.v[(e + 1) & 3] : ay_x;
+          azx = (e < 3) ? az0.v[(e + 1) & 3] : az_x;
+        } else {
+          ayx = (e > 0) ? ay0.v[(e + 3) & 3] : ay_x;
+          azx = (e > 0) ? az0.v[(e + 3) & 3] : az_x;
+        }
+        // K = dt * curl (Helpers.jl:286-298), same operation order as the reference
+        kx[e] = dt * (idz_ * (ay_z.v[e] - ay0.v[e]) - idy_ * (az_y.v[e] - az0.v[e]));
+        ky[e] = dt * (idx_ * (azx - az0.v[e]) - idz_ * (ax_z.v[e] - ax0.v[e]));
+        kz[e] = dt * (idy_ * (ax_y.v[e] - ax0.v[e]) - idx_ * (ayx - ay0.v[e]));
+      }
+      const long long mbase = p.mplane * (long long)(iz - 1) + mo;
+      if constexpr (MARR) {
+        V4<T> m0 = ld4(p.m_arr[0] + mbase), m1 = ld4(p.m_arr[1] + mbase), m2 = ld4(p.m_arr[2] + mbase);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { kx[e] = m0.v[e] * kx[e]; ky[e] = m1.v[e] * ky[e]; kz[e] = m2.v[e] * kz[e]; }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { kx[e] = p.m_inv * kx[e]; ky[e] = p.m_inv * ky[e]; kz[e] = p.m_inv * kz[e]; }
+      }
+      T* __restrict__ Fx = p.F[0] + base;
+      T* __restrict__ Fy = p.F[1] + base;
+      T* __restrict__ Fz = p.F[2] + base;
+      V4<T> fx = ld4(Fx), fy = ld4(Fy), fz = ld4(Fz);
+
+      if constexpr (!GENERAL) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (valid[e]) { fx.v[e] = fx.v[e] + kx[e]; fy.v[e] = fy.v[e] + ky[e]; fz.v[e] = fz.v[e] + kz[e]; }
+        }
+      } else {
+        // ---- general path ----
+        Co<T> czc;
+        czc.s = p.sg[2][iz - 1]; czc.om = p.om[2][iz - 1]; czc.ip = p.ip[2][iz - 1];
+        const bool hasz = czc.s != T(0);
+        Co<T> cyv[4], czv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { cyv[e] = cyc; czv[e] = czc; }
+        T so[3][4], sn[3][4];
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { so[d][e] = T(0); sn[d][e] = T(0); }
+        // m^-1 per component/element (needed to scale S and P)
+        T mi[3][4];
+        if (EXTRAS && (srcmask != 0 || (GROUP == 1 && p.npole > 0))) {
+          if constexpr (MARR) {
+            V4<T> m0 = ld4(p.m_arr[0] + mbase), m1 = ld4(p.m_arr[1] + mbase), m2 = ld4(p.m_arr[2] + mbase);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { mi[0][e] = m0.v[e]; mi[1][e] = m1.v[e]; mi[2][e] = m2.v[e]; }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { mi[0][e] = mi[1][e] = mi[2][e] = p.m_inv; }
+          }
+        }
+        // sources (Sources.jl:355-356): S = real(a(t) * A[x])
+        if (EXTRAS && srcmask != 0) {
+          for (int q = 0; q < p.nsrc; ++q) {
+            if (!((srcmask >> q) & 1u)) continue;
+            const SrcDesc<T>& s = p.src[q];
+            const int ly = iy - s.s[1], lz = iz - s.s[2];
+            if (ly < 0 || ly >= s.d[1] || lz < 0 || lz >= s.d[2]) continue;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int lx = gx + e - s.s[0];
+              if (lx >= 0 && lx < s.d[0]) {
+                const size_t ai = 2 * ((size_t)lx + (size_t)s.d[0] * ((size_t)ly + (size_t)s.d[1] * (size_t)lz));
+                const T are = s.amp[ai], aim = s.amp[ai + 1];
+                const T vn = s.an_re * are - s.an_im * aim;
+                const T vo = s.ao_re * are - s.ao_im * aim;
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+                  if (d == s.comp) { sn[d][e] += mi[d][e] * vn; so[d][e] += mi[d][e] * vo; }
+              }
+            }
+          }
+        }
+        // polarisation: the stored E carries -eps^-1 P^{n-1}; this step puts -eps^-1 P^n
+        bool pol_on[MAXPOLE];
+        if constexpr (GROUP == 1 && EXTRAS) {
+#pragma unroll
+          for (int q = 0; q < MAXPOLE; ++q) {
+            pol_on[q] = false;
+            if (q < p.npole) {
+              V4<T> sg = ld4(p.pole[q].sigma + mbase);
+              pol_on[q] = (sg.v[0] != T(0)) || (sg.v[1] != T(0)) || (sg.v[2] != T(0)) || (sg.v[3] != T(0));
+              if (pol_on[q]) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                  V4<T> pc = ld4(p.pole[q].Pc[d] + mbase), pp = ld4(p.pole[q].Pp[d] + mbase);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) { sn[d][e] -= mi[d][e] * pc.v[e]; so[d][e] -= mi[d][e] * pp.v[e]; }
+                }
+              }
+            }
+          }
+        }
+        // material conductivity
+        const bool has_sd = EXTRAS && (p.sigD[0] != nullptr);
+        T sd[3][4];
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) sd[d][e] = T(0);
+        if (has_sd) {
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            V4<T> s4 = ld4(p.sigD[d] + mbase);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) sd[d][e] = T(0.5) * (dt * s4.v[e]);
+          }
+        }
+        // aux slab addresses for this plane
+        const long long xsl = hasx ? ((long long)p.cxp * p.n[1] * (long long)(iz - 1) + xs_off) : 0;
+        const long long ysl = hasy ? ((long long)p.mpx * p.cy * (long long)(iz - 1) + ys_off) : 0;
+        const long long zsl = hasz ? (p.mplane * (long long)p.slab[2].idx(iz) + mo) : 0;
+        T ax_[4], ay_[4], az_[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { ax_[e] = fx.v[e]; ay_[e] = fy.v[e]; az_[e] = fz.v[e]; }
+        // x: next = y, prev = z, own = x
+        cascade<T, EXTRAS>(kx, cyv, czv, cx, hasy, hasx, p.U[0] + ysl, p.W[0] + xsl, ax_, so[0], sn[0], has_sd, sd[0],
+                   p.C[0] ? p.C[0] + mbase : nullptr, valid);
+        // y: next = z, prev = x, own = y
+        cascade<T, EXTRAS>(ky, czv, cx, cyv, hasz, hasy, p.U[1] + zsl, p.W[1] + ysl, ay_, so[1], sn[1], has_sd, sd[1],
+                   p.C[1] ? p.C[1] + mbase : nullptr, valid);
+        // z: next = x, prev = y, own = z
+        cascade<T, EXTRAS>(kz, cx, cyv, czv, hasx, hasz, p.U[2] + xsl, p.W[2] + zsl, az_, so[2], sn[2], has_sd, sd[2],
+                   p.C[2] ? p.C[2] + mbase : nullptr, valid);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { fx.v[e] = ax_[e]; fy.v[e] = ay_[e]; fz.v[e] = az_[e]; }
+        // ADE (Dispersive.jl:25-88): P^{n+1} from P^n, P^{n-1} and the new E; written over P^{n-1}
+        if constexpr (GROUP == 1 && EXTRAS) {
+#pragma unroll
+          for (int q = 0; q < MAXPOLE; ++q) {
+            if (q < p.npole && pol_on[q]) {
+              const PoleDesc<T>& pl = p.pole[q];
+              V4<T> sg = ld4(pl.sigma + mbase);
+#pragma unroll
+              for (int d = 0; d < 3; ++d) {
+                V4<T> pc = ld4(pl.Pc[d] + mbase), pp = ld4(pl.Pp[d] + mbase);
+                const V4<T>& en = (d == 0) ? fx : (d == 1) ? fy : fz;
+                V4<T> pn;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  T v = pl.g1i * ((pl.cp * pc.v[e] - pl.g1 * pp.v[e]) + pl.cd * sg.v[e] * en.v[e]);
+                  pn.v[e] = (sg.v[e] != T(0) && valid[e]) ? v : pc.v[e];
+                }
+                st4(pl.Pp[d] + mbase, pn);
+              }
+            }
+          }
+        }
+      }
+      st4(Fx, fx);
+      st4(Fy, fy);
+      st4(Fz, fz);
+    }
+    // carry
+    if constexpr (GROUP == 0) { ax_c = ax_z; ay_c = ay_z; }
+    else { ax_c = ax0; ay_c = ay0; }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Running DFT (Monitors.jl:331-379): M[x,y,z,k] += (dt * exp(i f_k 2 pi t)) * F[x+off]
+// One launch covers every monitor of a field group that is due this step.
+// ----------------------------------------------------------------------------
+template <class T>
+struct MonDesc {
+  T* M;               // complex interleaved (nx,ny,nz,nf)
+  const T* F;         // field array (ghosted layout)
+  const T* freqs;     // nf values
+  int s[3];           // local start cell (may start below 1 in z when clipped by host)
+  int n[3];           // extent of the part this rank accumulates
+  int moff[3];        // offset of that part inside the monitor box
+  int mn[3];          // full monitor box extent (for M strides)
+  int nf;
+  int decimation;
+  int group;
+};
+
+constexpr int DFT_MAXF = 64;
+
+template <class T>
+__device__ __forceinline__ void sincos_T(T x, T* s, T* c);
+template <>
+__device__ __forceinline__ void sincos_T<float>(float x, float* s, float* c) { sincosf(x, s, c); }
+template <>
+__device__ __forceinline__ void sincos_T<double>(double x, double* s, double* c) { sincos(x, s, c); }
+
+template <class T>
+__global__ void __launch_bounds__(256) dft_kernel(const MonDesc<T>* __restrict__ mons, const int* __restrict__ due,
+                                                  T time_fac, T dt, long long plane, int px) {
+  const MonDesc<T> m = mons[due[blockIdx.y]];
+  __shared__ T ph_re[DFT_MAXF], ph_im[DFT_MAXF];
+  const long long ncell = (long long)m.n[0] * m.n[1] * m.n[2];
+  if ((long long)blockIdx.x * blockDim.x >= ncell) return;
+  for (int k0 = 0; k0 < m.nf; k0 += DFT_MAXF) {
+    const int kc = min(DFT_MAXF, m.nf - k0);
+    __syncthreads();
+    if ((int)threadIdx.x < kc) {
+      // phase = T(f_k) * T(2 pi t) in T (Monitors.jl:323, 355); exp(i phase) = (cos, sin)
+      T ph = m.freqs[k0 + threadIdx.x] * time_fac;
+      T s, c;
+      sincos_T<T>(ph, &s, &c);
+      ph_re[threadIdx.x] = dt * c;
+      ph_im[threadIdx.x] = dt * s;
+    }
+    __syncthreads();
+    const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell < ncell) {
+      const int x = (int)(cell % m.n[0]);
+      const int y = (int)((cell / m.n[0]) % m.n[1]);
+      const int z = (int)(cell / ((long long)m.n[0] * m.n[1]));
+      const T f = m.F[plane * (long long)(m.s[2] + z) + (long long)px * (m.s[1] + y) + (m.s[0] + x + XO)];
+      const long long mcell = (long long)(x + m.moff[0]) +
+                              (long long)m.mn[0] * ((long long)(y + m.moff[1]) + (long long)m.mn[1] * (z + m.moff[2]));
+      const long long mstride = (long long)m.mn[0] * m.mn[1] * m.mn[2];
+      for (int k = 0; k < kc; ++k) {
+        T* mp = m.M + 2 * (mcell + mstride * (k0 + k));
+        // complex accumulate: (dt*e) * F
+        T re = mp[0], im = mp[1];
+        mp[0] = re + ph_re[k] * f;
+        mp[1] = im + ph_im[k] * f;
+      }
+    }
+  }
+}
+
+}  // namespace khr

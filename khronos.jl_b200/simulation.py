@@ -1,0 +1,700 @@
+"""Host-side mirror of the Khronos `Simulation` / `run(sim; until=...)` / monitor API.
+
+The reference host is Julia (no toolchain in this image), so the part of
+Khronos that sits *in front of* the time-step hot path is mirrored here in
+Python with the reference's names and argument meaning: `Simulation(...)`,
+`prepare_simulation`, `step`, `run(until=... | until_after_sources=...)`,
+`run_benchmark`, `UniformSource`, `ContinuousWaveSource`, `GaussianPulseSource`,
+`DFTMonitor`, `FluxMonitor`, `get_flux`, `Material`, `Object`, susceptibilities,
+`Absorber`.  Everything per-step is delegated to libkhronos_b200.so through the
+C ABI (`_lib.py`); nothing here computes fields on the host.
+
+Reference: src/DataStructures.jl:714-801, src/Simulation.jl:92-382, 492-527.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from . import chunking
+from .grid import EX, EY, EZ, HX, HY, HZ, Grid, component_stagger, interpolation_weight
+
+# --------------------------------------------------------------------------
+# time profiles (src/Sources/TimeSources.jl)
+# --------------------------------------------------------------------------
+
+
+class ContinuousWaveSource:
+    """TimeSources.jl:48-68. a(t) = exp(-i 2π fcen t); never cuts off."""
+
+    def __init__(self, fcen):
+        self.fcen = float(fcen)
+
+    kind = _lib.TIME_CW
+
+    def params(self, T):
+        return [float(T(self.fcen)), 0.0, 0.0, 0.0]
+
+    def f_max(self):
+        return self.fcen
+
+    def cutoff(self):
+        return None
+
+
+class GaussianPulseSource:
+    """TimeSources.jl:74-136 (constructor arithmetic reproduced in Float64)."""
+
+    kind = _lib.TIME_GAUSSIAN
+
+    def __init__(self, fcen, fwidth, start_time=0.0, cutoff_scale=5.0):
+        width = 1.0 / fwidth
+        cutoff = width * cutoff_scale + start_time
+        self.fwidth = math.sqrt(-2.0 * math.log(1e-7)) / (width * math.pi)
+        while math.exp(-cutoff * cutoff / (2 * width * width)) < 1e-100:
+            cutoff *= 0.9
+        period = 1.0 / fcen
+        # Julia round(): ties to even, like Python's round()
+        self.peak_time = round((cutoff / 2) / period) * period
+        self.fcen, self.width, self.cutoff_ = float(fcen), width, cutoff
+
+    def params(self, T):
+        return [float(T(self.fcen)), float(T(self.width)), float(T(self.peak_time)), float(T(self.cutoff_))]
+
+    def f_max(self):
+        return self.fcen + self.fwidth / 2
+
+    def cutoff(self):
+        return self.cutoff_
+
+
+class CustomSource:
+    """TimeSources.jl:139-183: amplitude supplied by a host callable every step."""
+
+    kind = _lib.TIME_HOST
+
+    def __init__(self, src_func, fcen, fwidth, end_time):
+        self.src_func, self.fcen, self.fwidth, self.end_time = src_func, float(fcen), float(fwidth), float(end_time)
+
+    def params(self, T):
+        return [float(T(self.fcen)), float(T(self.fwidth)), 0.0, float(T(self.end_time))]
+
+    def f_max(self):
+        return self.fcen + self.fwidth / 2
+
+    def cutoff(self):
+        return self.end_time
+
+
+# --------------------------------------------------------------------------
+# spatial sources (src/Sources/SpatialSources.jl:99-155, Sources.jl:40-135)
+# --------------------------------------------------------------------------
+
+
+class UniformSource:
+    def __init__(self, time_profile, component, center, size, amplitude=1.0, profile=None):
+        self.time_profile = time_profile
+        self.components = [component] if np.isscalar(component) else list(component)
+        self.center = [float(v) for v in center]
+        self.size = [float(v) for v in size]
+        self.amplitude = complex(amplitude)
+        # optional spatial profile f(point, component) (stands in for the mode /
+        # plane-wave / Gaussian-beam profiles, whose construction is out of scope)
+        self.profile = profile
+
+
+# --------------------------------------------------------------------------
+# materials / geometry (inputs of the hot path; rasterised by point sampling)
+# --------------------------------------------------------------------------
+
+
+class LorentzianSusceptibility:
+    """Susceptibility.jl:24-28."""
+
+    def __init__(self, omega_0, gamma, sigma):
+        self.omega_0, self.gamma, self.sigma = float(omega_0), float(gamma), float(sigma)
+
+
+def DrudeSusceptibility(gamma, sigma):
+    """Susceptibility.jl:39-40."""
+    return LorentzianSusceptibility(0.0, gamma, sigma)
+
+
+class Material:
+    def __init__(self, epsilon=1.0, mu=1.0, sigma_D=0.0, sigma_B=0.0, susceptibilities=None):
+        self.epsilon, self.mu = float(epsilon), float(mu)
+        self.sigma_D, self.sigma_B = float(sigma_D), float(sigma_B)
+        self.susceptibilities = list(susceptibilities or [])
+
+
+class Ball:
+    def __init__(self, center, radius):
+        self.center, self.radius = [float(v) for v in center], float(radius)
+
+    def contains(self, X, Y, Z):
+        c = self.center
+        return (X - c[0]) ** 2 + (Y - c[1]) ** 2 + (Z - c[2]) ** 2 <= self.radius ** 2
+
+
+class Cuboid:
+    def __init__(self, center, size):
+        self.center, self.size = [float(v) for v in center], [float(v) for v in size]
+
+    def contains(self, X, Y, Z):
+        c, s = self.center, self.size
+        return (np.abs(X - c[0]) <= s[0] / 2) & (np.abs(Y - c[1]) <= s[1] / 2) & (np.abs(Z - c[2]) <= s[2] / 2)
+
+
+class Object:
+    def __init__(self, shape, material):
+        self.shape, self.material = shape, material
+
+
+class Absorber:
+    """Boundaries.jl:17-21."""
+
+    def __init__(self, num_layers=40, sigma_order=3, sigma_max=0.0):
+        self.num_layers, self.sigma_order, self.sigma_max = int(num_layers), int(sigma_order), float(sigma_max)
+
+
+# --------------------------------------------------------------------------
+# monitors (src/Monitors/Monitors.jl:202-272, FluxMonitor.jl:18-70)
+# --------------------------------------------------------------------------
+
+
+class DFTMonitor:
+    def __init__(self, component, center, size, frequencies, decimation=1):
+        self.component = component
+        self.center = [float(v) for v in center]
+        self.size = [float(v) for v in size]
+        self.frequencies = [float(f) for f in frequencies]
+        self.decimation = int(decimation)
+        self.id = None
+        self.start = self.end = None
+
+
+class FluxMonitor:
+    """Four tangential DFT monitors on a plane (FluxMonitor.jl:18-70)."""
+
+    def __init__(self, center, size, frequencies, decimation=1):
+        self.center = [float(v) for v in center]
+        self.size = [float(v) for v in size]
+        self.frequencies = [float(f) for f in frequencies]
+        self.decimation = int(decimation)
+        zero = [i for i, s in enumerate(self.size) if s == 0.0]
+        if len(zero) != 1:
+            raise ValueError("FluxMonitor needs exactly one zero-size axis (the normal)")
+        self.normal = zero[0]
+        t1 = 1 if self.normal == 0 else 0
+        t2 = 1 if self.normal == 2 else 2
+        self.tangential = (t1, t2)
+        self.monitors = [
+            DFTMonitor(EX + t1, center, size, frequencies, decimation),
+            DFTMonitor(EX + t2, center, size, frequencies, decimation),
+            DFTMonitor(HX + t1, center, size, frequencies, decimation),
+            DFTMonitor(HX + t2, center, size, frequencies, decimation),
+        ]
+
+
+# --------------------------------------------------------------------------
+# Simulation
+# --------------------------------------------------------------------------
+
+
+class Simulation:
+    """Khronos.Simulation(; cell_size, cell_center, resolution, sources, boundaries, ...).
+
+    Extra keywords that have no Julia counterpart: `dtype` (the reference selects
+    precision with choose_backend, load_deps.jl:23-64), `device`, and the slab
+    placement `rank` / `nranks` (the reference reads them from MPI,
+    Distributed.jl:25-55).  Per-voxel material arrays may be handed in directly
+    (`eps_inv`, `mu_inv`, `sigma_D`, `sigma_B`: dense (Nx,Ny,Nz) arrays per
+    component, i.e. what init_geometry would have produced).
+    """
+
+    def __init__(self, cell_size, cell_center, resolution, sources, boundaries=None, absorbers=None, geometry=None,
+                 monitors=None, Courant=0.5, dtype=np.float32, device=0, rank=0, nranks=1, eps_inv=None, mu_inv=None,
+                 sigma_D=None, sigma_B=None, poles=None):
+        self.grid = Grid(cell_size, cell_center, resolution, Courant, dtype)
+        self.T = self.grid.T
+        self.sources = list(sources or [])
+        self.boundaries = None if boundaries is None else [[float(a), float(b)] for a, b in boundaries]
+        self.absorbers = absorbers
+        self.geometry = list(geometry or [])
+        self.monitors = list(monitors or [])
+        self.device, self.rank, self.nranks = int(device), int(rank), int(nranks)
+        self.user_arrays = {"eps_inv": eps_inv, "mu_inv": mu_inv, "sigma_D": sigma_D, "sigma_B": sigma_B}
+        self.user_poles = list(poles or [])  # (omega_0, gamma, sigma_array) triples
+        self.ctx = None
+        self.is_prepared = False
+        self.dft_monitors = []
+        self.timestep = 0
+        self.Nx, self.Ny, self.Nz = self.grid.N
+        self.dx, self.dy, self.dz = self.grid.dl
+        self.dt = self.grid.dt
+
+    # -------------------------------------------------------------- helpers
+    def _coords(self, comp):
+        """Coordinates of cells 1..N of a component grid (Geometry.jl _precompute_coords)."""
+        o = self.grid.component_origin(comp)
+        return [o[a] + np.arange(self.grid.N[a], dtype=np.float64) * float(self.grid.dl[a]) for a in range(3)]
+
+    def _rasterize(self):
+        """Point-sampled stand-in for init_geometry (Geometry.jl:450-663): per Yee component,
+        cell i takes the material of the first object containing the component position."""
+        T = self.T
+        g = self.grid
+        arrays = {k: None for k in ("eps_inv", "mu_inv", "sigma_D", "sigma_B")}
+        poles = []
+        if not self.geometry:
+            return arrays, poles
+        need_eps = any(o.material.epsilon != 1.0 for o in self.geometry)
+        need_mu = any(o.material.mu != 1.0 for o in self.geometry)
+        need_sd = any(o.material.sigma_D != 0.0 for o in self.geometry)
+        need_sb = any(o.material.sigma_B != 0.0 for o in self.geometry)
+        shape = tuple(g.N)
+
+        def paint(comp0, attr, inverse):
+            out = []
+            for d in range(3):
+                xs, ys, zs = self._coords(comp0 + d)
+                X, Y, Z = np.meshgrid(xs, ys, zs, indexing="ij", sparse=True)
+                a = np.full(shape, 1.0 if inverse else 0.0, dtype=np.float64)
+                for obj in reversed(self.geometry):  # earlier objects take priority (Geometry.jl:241)
+                    m = obj.shape.contains(X, Y, Z)
+                    v = getattr(obj.material, attr)
+                    a[np.broadcast_to(m, shape)] = (1.0 / v) if inverse else v
+                out.append(a.astype(T))
+            return out
+
+        if need_eps:
+            arrays["eps_inv"] = paint(EX, "epsilon", True)
+        if need_mu:
+            arrays["mu_inv"] = paint(HX, "mu", True)
+        if need_sd:
+            arrays["sigma_D"] = paint(EX, "sigma_D", False)
+        if need_sb:
+            arrays["sigma_B"] = paint(HX, "sigma_B", False)
+        # dispersive poles: sigma rasterised on the Ex grid, shared by x/y/z (Geometry.jl:1146-1177)
+        uniq = []
+        for obj in self.geometry:
+            for s in obj.material.susceptibilities:
+                key = (s.omega_0, s.gamma)
+                if key not in uniq:
+                    uniq.append(key)
+        xs, ys, zs = self._coords(EX)
+        X, Y, Z = np.meshgrid(xs, ys, zs, indexing="ij", sparse=True)
+        for key in uniq:
+            sg = np.zeros(shape, dtype=np.float64)
+            for obj in reversed(self.geometry):
+                m = np.broadcast_to(obj.shape.contains(X, Y, Z), shape)
+                val = 0.0
+                for s in obj.material.susceptibilities:
+                    if (s.omega_0, s.gamma) == key:
+                        val = s.sigma
+                sg[m] = val
+            poles.append((key[0], key[1], sg.astype(T)))
+        return arrays, poles
+
+    def _zero_pole_sigma_in_pml(self, sigma):
+        """Geometry.jl:1180-1232: dispersive sigma is removed inside the PML."""
+        if self.boundaries is None:
+            return sigma
+        g = self.grid
+        xs = self._coords(EX)
+        mask = np.zeros(sigma.shape, dtype=bool)
+        for a in range(3):
+            half = np.asarray(g.cell_size[a] / g.T(2))  # cell_size ./ 2 stays T
+            lo = g.cell_center[a] - float(half)
+            hi = g.cell_center[a] + float(half)
+            pl, pr = g.T(self.boundaries[a][0]), g.T(self.boundaries[a][1])
+            m1 = np.zeros(g.N[a], dtype=bool)
+            if pl > 0:
+                m1 |= xs[a] < lo + float(pl)
+            if pr > 0:
+                m1 |= xs[a] > hi - float(pr)
+            shp = [1, 1, 1]
+            shp[a] = g.N[a]
+            mask |= m1.reshape(shp)
+        out = sigma.copy()
+        out[mask] = 0
+        return out
+
+    def _apply_absorbers(self, arrays):
+        """Geometry.jl:708-789 _apply_absorbers!: additive sigma ramp on the outer layers."""
+        if self.absorbers is None:
+            return arrays
+        g, T = self.grid, self.T
+        any_abs = any(ax is not None and any(s is not None for s in ax) for ax in self.absorbers)
+        if not any_abs:
+            return arrays
+        for key in ("sigma_D", "sigma_B"):
+            if arrays[key] is None:
+                arrays[key] = [np.zeros(tuple(g.N), dtype=T) for _ in range(3)]
+        for axis, ax in enumerate(self.absorbers):
+            if ax is None:
+                continue
+            for side, ab in enumerate(ax):
+                if ab is None:
+                    continue
+                L = T(ab.num_layers) * g.dl[axis]
+                if ab.sigma_max > 0:
+                    smax = T(ab.sigma_max)
+                else:
+                    smax = T(-(ab.sigma_order + 1) * math.log(1e-6) / (2.0 * float(L)))
+                for key, comp0 in (("sigma_D", EX), ("sigma_B", HX)):
+                    for c in range(3):
+                        st = component_stagger(comp0 + c)
+                        n_axis = g.N[axis] + st[axis]
+                        for layer in range(1, min(ab.num_layers, n_axis) + 1):
+                            dn = (ab.num_layers - layer + 1) / ab.num_layers
+                            val = T(float(smax) * dn ** ab.sigma_order)
+                            idx = (n_axis - layer + 1) if side == 1 else layer
+                            if idx > g.N[axis]:
+                                continue  # staggered extra cell: never read by the kernels
+                            sl = [slice(None)] * 3
+                            sl[axis] = idx - 1
+                            arrays[key][c][tuple(sl)] += val
+        return arrays
+
+    # ------------------------------------------------------------ prepare
+    def prepare_simulation(self, comm_id=None):
+        """Simulation.jl:92-283 prepare_simulation! (the parts the hot path needs)."""
+        if self.is_prepared:
+            return
+        L = _lib.lib()
+        g, T = self.grid, self.T
+        slabs = chunking.z_slab_partition(g, self.boundaries, self.nranks)
+        self.slabs = slabs
+        z_start, nzl = slabs[self.rank]
+        self.z_start, self.nz_local = z_start, nzl
+        desc = _lib.GridDesc()
+        desc.dtype = _lib.KHR_F32 if T is np.float32 else _lib.KHR_F64
+        for a in range(3):
+            desc.n[a] = g.N[a]
+            desc.dl[a] = float(g.dl[a])
+        desc.dt = float(g.dt)
+        desc.z_start, desc.nz_local, desc.rank, desc.nranks = z_start, nzl, self.rank, self.nranks
+        ctx = C.c_void_p()
+        _lib.check(L.khr_ctx_create(self.device, C.byref(desc), C.byref(ctx)))
+        self.ctx = ctx
+        zsl = slice(z_start - 1, z_start - 1 + nzl)
+
+        # boundaries (Boundaries.jl:99-164): sigma_B and sigma_D profiles are identical
+        self.sigma = None
+        if self.boundaries is not None:
+            self.sigma = [g.compute_sigma(a, self.boundaries[a][0], self.boundaries[a][1]) for a in range(3)]
+            for grp in (_lib.GROUP_H, _lib.GROUP_E):
+                for a in range(3):
+                    s = np.ascontiguousarray(self.sigma[a])
+                    _lib.check(L.khr_set_pml_sigma(ctx, grp, a, s.ctypes.data, s.size))
+
+        # geometry (Geometry.jl:450-663) + absorbers + poles
+        arrays, poles = self._rasterize()
+        for k, v in self.user_arrays.items():
+            if v is not None:
+                arrays[k] = [np.asarray(x, dtype=T) for x in v]
+        arrays = self._apply_absorbers(arrays)
+        poles = poles + [(w, gam, np.asarray(s, dtype=T)) for (w, gam, s) in self.user_poles]
+        poles = [(w, gam, self._zero_pole_sigma_in_pml(s)) for (w, gam, s) in poles]
+        if poles:
+            # chi1 semi-implicit correction folded into eps_inv (Geometry.jl:1236-1353)
+            chi1 = np.zeros(tuple(g.N), dtype=T)
+            for (w0, gam, s) in poles:
+                dtd = float(g.dt)
+                g1i = 1.0 / (1.0 + gam * math.pi * dtd)
+                if w0 == 0.0:
+                    c = T(g1i * (gam * (2 * math.pi) * dtd * dtd) / 2)
+                else:
+                    ww = (2 * math.pi) * w0 * dtd
+                    c = T(g1i * (ww * ww) / 2)
+                chi1 = chi1 + s * c
+            if np.max(np.abs(chi1)) > 0:
+                if arrays["eps_inv"] is None:
+                    arrays["eps_inv"] = [np.full(tuple(g.N), T(1), dtype=T) for _ in range(3)]
+                nz = chi1 != 0
+                for d in range(3):
+                    e = arrays["eps_inv"][d].copy()
+                    e[nz] = e[nz] / (T(1) + e[nz] * chi1[nz])
+                    arrays["eps_inv"][d] = e
+        self.material_arrays = arrays
+        kinds = {"eps_inv": _lib.MAT_EPS_INV, "mu_inv": _lib.MAT_MU_INV, "sigma_D": _lib.MAT_SIGMA_D,
+                 "sigma_B": _lib.MAT_SIGMA_B}
+        for k, kind in kinds.items():
+            if arrays[k] is None:
+                continue
+            for d in range(3):
+                a = np.asfortranarray(arrays[k][d][:, :, zsl])
+                _lib.check(L.khr_set_material_array(ctx, kind, d, a.ctypes.data))
+        self.poles = poles
+        for (w0, gam, s) in poles:
+            a = np.asfortranarray(s[:, :, zsl])
+            pid = C.c_int32()
+            _lib.check(L.khr_pole_register(ctx, w0, gam, a.ctypes.data, C.byref(pid)))
+
+        # sources (Sources.jl:40-135 assemble_sources)
+        self.source_ids = []
+        i3 = C.c_int32 * 3
+        for src in self.sources:
+            for comp in src.components:
+                start, end = g.grid_volume(src.center, src.size, comp)
+                dims = [end[a] - start[a] + 1 for a in range(3)]
+                amp = self._source_amplitude(src, comp, start, dims)
+                ampT = np.empty(amp.shape + (2,), dtype=T)
+                ampT[..., 0] = amp.real.astype(T)
+                ampT[..., 1] = amp.imag.astype(T)
+                buf = np.ascontiguousarray(np.transpose(ampT, (2, 1, 0, 3)))  # x fastest, (re,im) innermost
+                tp = (C.c_double * 4)(*src.time_profile.params(T))
+                sid = C.c_int32()
+                _lib.check(L.khr_source_register(ctx, comp, i3(*start), i3(*dims), buf.ctypes.data,
+                                                 src.time_profile.kind, tp, C.byref(sid)))
+                self.source_ids.append((sid.value, src, comp, start, dims))
+
+        # monitors: auto-decimation (Monitors.jl:33-78) then registration (:202-272)
+        self.dft_monitors = []
+        for m in self.monitors:
+            if isinstance(m, FluxMonitor):
+                self.dft_monitors.extend(m.monitors)
+            else:
+                self.dft_monitors.append(m)
+        self._auto_decimate()
+        for m in self.dft_monitors:
+            m.start, m.end = g.grid_volume(m.center, m.size, m.component)
+            fr = (C.c_double * len(m.frequencies))(*[float(T(f)) for f in m.frequencies])
+            mid = C.c_int32()
+            _lib.check(L.khr_monitor_register(ctx, m.component, i3(*m.start), i3(*m.end), len(m.frequencies), fr,
+                                              m.decimation, C.byref(mid)))
+            m.id = mid.value
+        _lib.check(L.khr_finalize_plan(ctx))
+        if self.nranks > 1:
+            if comm_id is None:
+                raise _lib.KhronosError("nranks > 1 needs the 128-byte NCCL unique id (see distributed.py)")
+            buf = (C.c_char * 128).from_buffer_copy(bytes(comm_id))
+            _lib.check(L.khr_comm_init(ctx, buf, self.nranks, self.rank))
+        self.is_prepared = True
+
+    def _source_amplitude(self, src, comp, start, dims):
+        """Sources.jl:107-135 _fill_amplitude_data!: weight * amplitude * profile (Complex{Float64})."""
+        g = self.grid
+        origin = g.component_origin(comp)
+        d = [float(v) for v in g.dl]
+        lo = [c - s / 2 for c, s in zip(src.center, src.size)]
+        hi = [c + s / 2 for c, s in zip(src.center, src.size)]
+        amp = np.zeros(tuple(dims), dtype=np.complex128)
+        # the weight is separable per axis (product over dims in utils.jl:494)
+        w = []
+        for a in range(3):
+            wa = np.zeros(dims[a])
+            for i in range(1, dims[a] + 1):
+                p = origin[a] + (i + start[a] - 2) * d[a]
+                wa[i - 1] = interpolation_weight([p], [lo[a]], [hi[a]], [src.size[a]], 1, [d[a]])
+            w.append(wa)
+        for ix in range(dims[0]):
+            for iy in range(dims[1]):
+                wxy = 1.0 * w[0][ix] * w[1][iy]
+                for iz in range(dims[2]):
+                    weight = wxy * w[2][iz]
+                    prof = 1.0
+                    if src.profile is not None:
+                        pt = [origin[a] + (i + start[a] - 1) * d[a] for a, i in enumerate((ix, iy, iz))]
+                        prof = src.profile(pt, comp)
+                    amp[ix, iy, iz] = weight * src.amplitude * prof
+        return amp
+
+    def _auto_decimate(self):
+        """Monitors.jl:33-78 auto_decimate!."""
+        f_max = 0.0
+        for s in self.sources:
+            f_max = max(f_max, s.time_profile.f_max())
+        if f_max <= 0:
+            return
+        d_max = max(1, int(math.floor(1.0 / (2.0 * f_max * float(self.grid.dt)))))
+        if d_max <= 1:
+            return
+        for m in self.dft_monitors:
+            if m.decimation == 1:
+                m.decimation = d_max
+
+    # --------------------------------------------------------------- step
+    def _push_host_amplitudes(self):
+        L = _lib.lib()
+        T = self.T
+        for sid, src, comp, _, _ in self.source_ids:
+            if src.time_profile.kind == _lib.TIME_HOST:
+                t = float(T(self.timestep) * self.grid.dt)
+                if comp < 3:
+                    t = t + float(self.grid.dt / T(2))
+                a = complex(src.time_profile.src_func(T(t)))
+                _lib.check(L.khr_source_set_amplitude(self.ctx, sid, a.real, a.imag))
+
+    def step(self, n=1):
+        """Kernels.jl:20-88 step! (n of them, the loop runs inside the library)."""
+        if not self.is_prepared:
+            self.prepare_simulation()
+        L = _lib.lib()
+        if any(s.time_profile.kind == _lib.TIME_HOST for s in self.sources):
+            for _ in range(n):
+                self._push_host_amplitudes()
+                _lib.check(L.khr_step(self.ctx, 1))
+                self.timestep += 1
+        else:
+            _lib.check(L.khr_step(self.ctx, int(n)))
+            self.timestep += int(n)
+
+    def round_time(self):
+        """Simulation.jl:22."""
+        return float(self.T(self.timestep) * self.grid.dt)
+
+    def run(self, until=None, until_after_sources=None):
+        """Simulation.jl:295-382 run(sim; until | until_after_sources).
+
+        `until` is an absolute simulation time: stepping stops at the first step with
+        round_time(sim) > until (run_until, Simulation.jl:384-387).  With
+        `until_after_sources` the loop first runs while round_time <= last_source_time
+        and then applies the same predicate to the given number (reference behaviour).
+        Either argument may be a callable `f(sim) -> bool` (stop predicate).
+        """
+        if until is None and until_after_sources is None:
+            raise ValueError("Must specify a terminating conditon in the run functions.")
+        if until is not None and until_after_sources is not None:
+            raise ValueError("Must specify a single terminating conditon in the run functions.")
+        if not self.is_prepared:
+            self.prepare_simulation()
+        T, dt = self.T, self.grid.dt
+        start = self.timestep
+
+        def steps_while(cond, n0):
+            n = n0
+            while cond(float(T(n) * dt)):
+                n += 1
+            return n
+
+        n = self.timestep
+        if until_after_sources is not None:
+            cut = [s.time_profile.cutoff() for s in self.sources]
+            if any(c is None for c in cut):
+                raise ValueError("Cutoff not possible with CW source...")
+            last = float(max(T(c) for c in cut))
+            n = steps_while(lambda t: t <= last, n)
+            self.step(n - self.timestep)
+        stop = until if until is not None else until_after_sources
+        if callable(stop):
+            while not stop(self):
+                self.step(1)
+        else:
+            n = steps_while(lambda t: not (t > float(stop)), self.timestep)
+            self.step(n - self.timestep)
+        self.sync()
+        return self.timestep - start
+
+    def run_benchmark(self, n=110):
+        """Simulation.jl:492-527: n steps, clock restarted after 10, Mcells/s returned."""
+        if not self.is_prepared:
+            self.prepare_simulation()
+        self.step(10)
+        self.sync()
+        self.step(n - 10)
+        ms = self.last_step_ms()
+        return self.Nx * self.Ny * self.Nz * (n - 10) / (ms * 1e-3) / 1e6
+
+    def sync(self):
+        _lib.check(_lib.lib().khr_sync(self.ctx))
+
+    def last_step_ms(self):
+        ms = C.c_double()
+        nl = C.c_int64()
+        _lib.check(_lib.lib().khr_last_step_timing(self.ctx, C.byref(ms), C.byref(nl)))
+        self.last_launches = nl.value
+        return ms.value
+
+    def reset_fields(self):
+        """Simulation.jl:571-637 reset_fields!."""
+        _lib.check(_lib.lib().khr_reset_fields(self.ctx))
+        self.timestep = 0
+
+    # -------------------------------------------------------------- access
+    def get_field(self, comp):
+        """Local slab of a field component, dense (Nx,Ny,Nz_local) (Visualization.jl:294-333)."""
+        out = np.empty((self.Nx, self.Ny, self.nz_local), dtype=self.T, order="F")
+        _lib.check(_lib.lib().khr_field_read(self.ctx, comp, out.ctypes.data))
+        return out
+
+    def set_field(self, comp, arr):
+        a = np.asfortranarray(np.asarray(arr, dtype=self.T))
+        if a.shape != (self.Nx, self.Ny, self.nz_local):
+            raise ValueError("field shape must be (Nx,Ny,Nz_local)")
+        _lib.check(_lib.lib().khr_field_write(self.ctx, comp, a.ctypes.data))
+
+    def get_dft(self, monitor):
+        """Array(md.fields): complex (nx,ny,nz,nf) (FluxMonitor.jl:99-102)."""
+        n = [monitor.end[a] - monitor.start[a] + 1 for a in range(3)] + [len(monitor.frequencies)]
+        raw = np.empty(tuple(n[::-1]) + (2,), dtype=self.T)
+        _lib.check(_lib.lib().khr_monitor_read(self.ctx, monitor.id, raw.ctypes.data))
+        cplx = raw[..., 0] + 1j * raw[..., 1]
+        return np.transpose(cplx, (3, 2, 1, 0))
+
+    def get_flux(self, fm, dft=None):
+        """FluxMonitor.jl:92-156 get_flux: Σ Re(E1·conj(H2) − E2·conj(H1))·dA per frequency.
+
+        `dft` may carry the four (already rank-reduced) DFT arrays; default reads this rank's.
+        """
+        T = self.T
+        ct = np.complex64 if T is np.float32 else np.complex128
+        arrs = dft if dft is not None else [self.get_dft(m) for m in fm.monitors]
+        arrs = [np.asarray(a).astype(ct) for a in arrs]
+        nrm, (t1, t2) = fm.normal, fm.tangential
+
+        def avg(a):  # _avg_dim: mean of the two planes when the box is 2 cells thick
+            if a.shape[nrm] >= 2:
+                idx0 = [slice(None)] * 4
+                idx1 = [slice(None)] * 4
+                idx0[nrm], idx1[nrm] = 0, 1
+                return (a[tuple(idx0)] + a[tuple(idx1)]) / T(2)
+            return np.take(a, 0, axis=nrm)
+
+        e1, e2, h1, h2 = [avg(a) for a in arrs]  # each (n_t1, n_t2, nf)
+        n1 = min(a.shape[0] for a in (e1, e2, h1, h2))
+        n2 = min(a.shape[1] for a in (e1, e2, h1, h2))
+        e1, e2, h1, h2 = [a[:n1, :n2, :] for a in (e1, e2, h1, h2)]
+        dA = float(self.grid.dl[t1]) * float(self.grid.dl[t2])
+        re1 = e1.real * h2.real + e1.imag * h2.imag
+        re2 = e2.real * h1.real + e2.imag * h1.imag
+        s = (re1 - re2).astype(np.float64) * dA
+        return s.sum(axis=(0, 1))
+
+    def voxel_census(self):
+        c = (C.c_int64 * 4)()
+        _lib.check(_lib.lib().khr_voxel_census(self.ctx, c))
+        return list(c)
+
+    def device_bytes(self):
+        b = C.c_int64()
+        _lib.check(_lib.lib().khr_device_bytes(self.ctx, C.byref(b)))
+        return b.value
+
+    def close(self):
+        if self.ctx is not None:
+            _lib.lib().khr_ctx_destroy(self.ctx)
+            self.ctx = None
+            self.is_prepared = False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def run(sim, until=None, until_after_sources=None):
+    """Khronos.run(sim; until=..., until_after_sources=...)."""
+    return sim.run(until=until, until_after_sources=until_after_sources)
+
+
+def step(sim):
+    """Khronos.step!(sim)."""
+    sim.step(1)
+
+
+def run_benchmark(sim, n=110):
+    return sim.run_benchmark(n)

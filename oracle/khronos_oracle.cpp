@@ -1140,7 +1140,7 @@ void ko_get_field(void* hv, int which, int comp, double* out) {
   });
 }
 
-// Set E/H (and the consistent D = E/eps_inv, B = H/mu_inv) over cells 1..N.
+// Set E/H (and the consistent D = E/eps_inv, B = H/mu_inv, W = m_inv*D|B) over cells 1..N.
 void ko_set_field(void* hv, int comp, const double* in) {
   Handle* h = (Handle*)hv;
   DISPATCH(h, {
@@ -1158,6 +1158,10 @@ void ko_set_field(void* hv, int comp, const double* in) {
             TT m = comp < 3 ? S.mat(S.eps_is_array, S.eps_inv, S.eps_inv_a, d, c, ix, iy, iz)
                             : S.mat(S.mu_is_array, S.mu_inv, S.mu_inv_a, d, c, ix, iy, iz);
             Tf.at(ix, iy, iz) = v / m;
+            // keep the W history consistent with the state just written: the
+            // reference stores W = m_inv * net (Helpers.jl:340), i.e. W == A here
+            auto& Wf = comp < 3 ? c.WD[d] : c.WB[d];
+            if (Wf.ok()) Wf.at(ix, iy, iz) = m * Tf.at(ix, iy, iz);
           }
     }
     if (S.chunks.size() > 1) S.exchange_halos(comp < 3 ? 1 : 0);
