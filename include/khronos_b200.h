@@ -145,6 +145,19 @@ int32_t khr_get_stream(khr_ctx* ctx, void** cuda_stream);
 int32_t khr_last_step_timing(khr_ctx* ctx, double* ms, int64_t* kernel_launches);
 /* voxel-class census used by the bytes model: counts of cells with 0,1,2,3 PML axes */
 int32_t khr_voxel_census(khr_ctx* ctx, int64_t counts[4]);
+/* per-kernel live timing: mode 1 = record CUDA events around every step-kernel launch
+ * on the ctx stream, 0 = stop, 2 = start and reset the accumulators */
+typedef struct khr_kernel_stat {
+  char name[96];
+  int64_t launches;             /* launches timed since the last reset */
+  double total_ms;              /* summed CUDA-event time of those launches */
+  int64_t cells_per_launch;     /* voxels one launch updates */
+  double alg_bytes_per_launch;  /* SURVEY.md §8(d) bytes model for those voxels (one half-step) */
+  int64_t ctas;                 /* thread blocks per launch */
+} khr_kernel_stat;
+int32_t khr_set_profiling(khr_ctx* ctx, int32_t mode);
+/* index in [0, count); pass out = NULL to query only the count */
+int32_t khr_kernel_stat_get(khr_ctx* ctx, int32_t index, khr_kernel_stat* out, int32_t* count);
 /* bytes of device memory held by the context */
 int32_t khr_device_bytes(khr_ctx* ctx, int64_t* bytes);
 

@@ -12,10 +12,11 @@ from .simulation import (Absorber, Ball, ContinuousWaveSource, Cuboid, CustomSou
                          FluxMonitor, GaussianPulseSource, LorentzianSusceptibility, Material, Object, Simulation,
                          UniformSource, run, run_benchmark, step)
 from ._lib import KhronosError, build
+from . import workloads
 
 __all__ = [
     "Absorber", "Ball", "ContinuousWaveSource", "Cuboid", "CustomSource", "DFTMonitor", "DrudeSusceptibility",
     "FluxMonitor", "GaussianPulseSource", "LorentzianSusceptibility", "Material", "Object", "Simulation",
     "UniformSource", "run", "run_benchmark", "step", "Grid", "interpolation_weight", "KhronosError", "build",
-    "EX", "EY", "EZ", "HX", "HY", "HZ", "chunking", "grid",
+    "EX", "EY", "EZ", "HX", "HY", "HZ", "chunking", "grid", "workloads",
 ]

@@ -30,6 +30,17 @@ class GridDesc(C.Structure):
     ]
 
 
+class KernelStat(C.Structure):
+    _fields_ = [
+        ("name", C.c_char * 96),
+        ("launches", C.c_int64),
+        ("total_ms", C.c_double),
+        ("cells_per_launch", C.c_int64),
+        ("alg_bytes_per_launch", C.c_double),
+        ("ctas", C.c_int64),
+    ]
+
+
 # every exported symbol of include/khronos_b200.h with its signature
 _P = C.c_void_p
 _I = C.c_int32
@@ -68,6 +79,8 @@ _SIGNATURES = {
     "khr_last_step_timing": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "khr_voxel_census": (_I, [_P, C.POINTER(C.c_int64)]),
     "khr_device_bytes": (_I, [_P, C.POINTER(C.c_int64)]),
+    "khr_set_profiling": (_I, [_P, _I]),
+    "khr_kernel_stat_get": (_I, [_P, _I, C.POINTER(KernelStat), C.POINTER(_I)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

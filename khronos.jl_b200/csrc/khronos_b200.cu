@@ -108,6 +108,8 @@ struct Base {
   virtual double monitor_norm(int id) = 0;
   virtual void sync() = 0;
   virtual void census(int64_t* c) = 0;
+  virtual void set_profiling(int on) = 0;
+  virtual int kernel_stat(int idx, khr_kernel_stat* out) = 0;
   int64_t timestep = 0;
   int sources_mode = -1;
   bool sources_active = true;
@@ -217,7 +219,17 @@ struct Impl : Base {
   struct Table {
     std::vector<WorkItem> items;
     WorkItem* d = nullptr;
+    // bytes model and live CUDA-event timing of this table's launches
+    int64_t cells = 0;
+    double alg_bytes = 0;
+    std::vector<cudaEvent_t> ev;  // pairs
+    size_t ev_used = 0;
+    double total_ms = 0;
+    int64_t nlaunch = 0;
   };
+  bool profiling = false;
+  std::vector<std::vector<uint8_t>> pole_mask;  // host non-zero masks (bytes model only)
+  std::vector<uint8_t> sd_mask[2];
   // phase 0 = boundary planes that feed the halo exchange, phase 1 = the rest
   Table tab[2][2][3][3];
   bool finalized = false;
@@ -293,8 +305,9 @@ struct Impl : Base {
     else throw std::string("scalar material must be eps_inv or mu_inv");
   }
   // dense (Nx,Ny,Nzl) host -> material layout device
-  T* upload_material(const void* dense, int* box6) {
+  T* upload_material(const void* dense, int* box6, std::vector<uint8_t>* mask = nullptr) {
     const T* src = (const T*)dense;
+    if (mask) mask->resize((size_t)N[0] * N[1] * N[2], 0);
     std::vector<T> h(msize + 64, T(0));
     int b[6] = {1 << 30, 1 << 30, 1 << 30, 0, 0, 0};
     for (int z = 1; z <= N[2]; ++z)
@@ -305,7 +318,10 @@ struct Impl : Base {
         int xl = 1 << 30, xh = 0;
         for (int x = 0; x < N[0]; ++x) {
           dst[x] = row[x];
-          if (row[x] != T(0)) { nz = true; xl = std::min(xl, x + 1); xh = std::max(xh, x + 1); }
+          if (row[x] != T(0)) {
+            nz = true; xl = std::min(xl, x + 1); xh = std::max(xh, x + 1);
+            if (mask) (*mask)[(size_t)x + (size_t)N[0] * ((size_t)(y - 1) + (size_t)N[1] * (z - 1))] = 1;
+          }
         }
         if (nz) {
           b[0] = std::min(b[0], xl); b[3] = std::max(b[3], xh);
@@ -328,7 +344,10 @@ struct Impl : Base {
     if (finalized) throw std::string("khr_set_material_array after khr_finalize_plan");
     if (comp < 0 || comp > 2) throw std::string("component must be 0..2");
     int box[6];
-    T* d = upload_material(dense, box);
+    std::vector<uint8_t>* mk = nullptr;
+    if (kind == KHR_MAT_SIGMA_D) mk = &sd_mask[1];
+    if (kind == KHR_MAT_SIGMA_B) mk = &sd_mask[0];
+    T* d = upload_material(dense, box, mk);
     if (kind == KHR_MAT_EPS_INV) m_arr[1][comp] = d;
     else if (kind == KHR_MAT_MU_INV) m_arr[0][comp] = d;
     else if (kind == KHR_MAT_SIGMA_D) { sigM[1][comp] = d; has_sd[1] = true; box_union(sd_box[1], box); }
@@ -350,7 +369,8 @@ struct Impl : Base {
     p.g1 = (T)g1; p.g1i = (T)g1i;
     if (omega0 == 0.0) { p.cp = T(2); p.cd = (T)drude; }
     else { p.cp = T(2) - (T)w2; p.cd = (T)w2; }
-    p.sigma = upload_material(sigma, p.box);
+    pole_mask.emplace_back();
+    p.sigma = upload_material(sigma, p.box, &pole_mask.back());
     for (int q = 0; q < 2; ++q)
       for (int d = 0; d < 3; ++d) p.P[q][d] = dalloc(msize);
     poles.push_back(p);
@@ -518,6 +538,94 @@ struct Impl : Base {
     return r;
   }
 
+  // Algorithmic bytes of one work item for one half-step, SURVEY.md §8(d):
+  //   interior 9w (+3w when the constitutive factor is a per-voxel array),
+  //   +10w / 14w / 18w on voxels inside 1 / 2 / 3 PML axes (T, U, W of the reference),
+  //   +1w per component where a material conductivity array is non-zero,
+  //   ADE voxels: 10w per pole + fPD write 3w + D r/w 6w + fPD read 3w.
+  double item_alg_bytes(int gq, const std::vector<int>* pmlc, int x0, int xw, int y0, int yh, int z0, int zn) const {
+    const double w = sizeof(T);
+    int64_t p1[3], p0[3];
+    int lo[3] = {x0, y0, z0}, n[3] = {xw, yh, zn};
+    for (int a = 0; a < 3; ++a) {
+      p1[a] = pmlc[a][lo[a] + n[a] - 1] - pmlc[a][lo[a] - 1];
+      p0[a] = n[a] - p1[a];
+    }
+    int64_t c0 = p0[0] * p0[1] * p0[2];
+    int64_t c1 = p1[0] * p0[1] * p0[2] + p0[0] * p1[1] * p0[2] + p0[0] * p0[1] * p1[2];
+    int64_t c2 = p1[0] * p1[1] * p0[2] + p1[0] * p0[1] * p1[2] + p0[0] * p1[1] * p1[2];
+    int64_t c3 = p1[0] * p1[1] * p1[2];
+    double base = (m_arr[gq][0] ? 12.0 : 9.0) * w;
+    double b = (double)(c0 + c1 + c2 + c3) * base + (double)c1 * 10 * w + (double)c2 * 14 * w + (double)c3 * 18 * w;
+    auto count_mask = [&](const std::vector<uint8_t>& mk) {
+      int64_t k = 0;
+      if (mk.empty()) return k;
+      for (int z = z0; z < z0 + zn; ++z)
+        for (int y = y0; y < y0 + yh; ++y) {
+          const uint8_t* r = mk.data() + (size_t)N[0] * ((size_t)(y - 1) + (size_t)N[1] * (z - 1));
+          for (int x = x0; x < x0 + xw; ++x) k += r[x - 1];
+        }
+      return k;
+    };
+    if (has_sd[gq] && boxes_hit(sd_box[gq], x0, x0 + xw - 1, y0, y0 + yh - 1, z0, z0 + zn - 1))
+      b += (double)count_mask(sd_mask[gq]) * 3 * w;
+    if (gq == 1)
+      for (size_t q = 0; q < poles.size(); ++q)
+        if (boxes_hit(poles[q].box, x0, x0 + xw - 1, y0, y0 + yh - 1, z0, z0 + zn - 1))
+          b += (double)count_mask(pole_mask[q]) * (10 + (q == 0 ? 12 : 0)) * w;
+    return b;
+  }
+
+  void collect_profile() {
+    for (int gq = 0; gq < 2; ++gq)
+      for (int ph = 0; ph < 2; ++ph)
+        for (int m = 0; m < 3; ++m)
+          for (int l = 0; l < 3; ++l) {
+            Table& t = tab[gq][ph][m][l];
+            for (size_t q = 0; q + 1 < t.ev_used; q += 2) {
+              float ms = 0;
+              if (cudaEventElapsedTime(&ms, t.ev[q], t.ev[q + 1]) == cudaSuccess) { t.total_ms += ms; t.nlaunch += 1; }
+              else cudaGetLastError();
+            }
+            t.ev_used = 0;
+          }
+  }
+  void set_profiling(int on) override {
+    CUDA_OK(cudaStreamSynchronize(stream));
+    collect_profile();
+    profiling = on != 0;
+    if (on == 2)  // reset accumulators
+      for (int gq = 0; gq < 2; ++gq)
+        for (int ph = 0; ph < 2; ++ph)
+          for (int m = 0; m < 3; ++m)
+            for (int l = 0; l < 3; ++l) { tab[gq][ph][m][l].total_ms = 0; tab[gq][ph][m][l].nlaunch = 0; }
+  }
+  int kernel_stat(int idx, khr_kernel_stat* out) override {
+    CUDA_OK(cudaStreamSynchronize(stream));
+    collect_profile();
+    int k = 0;
+    for (int gq = 0; gq < 2; ++gq)
+      for (int ph = 0; ph < 2; ++ph)
+        for (int m = 0; m < 3; ++m)
+          for (int l = 0; l < 3; ++l) {
+            Table& t = tab[gq][ph][m][l];
+            if (t.items.empty()) continue;
+            if (k == idx && out) {
+              memset(out, 0, sizeof(*out));
+              static const char* mn[3] = {"interior", "pml", "full"};
+              snprintf(out->name, sizeof(out->name), "step_kernel<%s,%s,LX%d,%s,%s>%s", sizeof(T) == 4 ? "f32" : "f64",
+                       gq == 0 ? "H" : "E", 8 << l, mn[m], m_arr[gq][0] ? "marr" : "mscalar", ph == 0 ? "[boundary]" : "");
+              out->launches = t.nlaunch;
+              out->total_ms = t.total_ms;
+              out->cells_per_launch = t.cells;
+              out->alg_bytes_per_launch = t.alg_bytes;
+              out->ctas = (int64_t)t.items.size();
+            }
+            ++k;
+          }
+    return k;
+  }
+
   void build_tables() {
     const int ZSEG = 32;
     std::vector<Range> xr = axis_ranges(0, 32), yr = axis_ranges(1, 1), zr = axis_ranges(2, 1);
@@ -531,6 +639,17 @@ struct Impl : Base {
         if (e == N[2] && g.rank < g.nranks - 1 && e > s) { zr2.push_back({s, e - 1, r.pml}); zr2.push_back({e, e, r.pml}); }
         else zr2.push_back({s, e, r.pml});
       } else zr2.push_back(r);
+    }
+    // prefix counts of PML cells per axis (for the bytes model)
+    std::vector<int> pmlc[3];
+    for (int a = 0; a < 3; ++a) {
+      pmlc[a].assign((size_t)N[a] + 1, 0);
+      for (int i = 1; i <= N[a]; ++i) {
+        bool on = false;
+        for (int gg = 0; gg < 2; ++gg)
+          if (have_sigma[gg][a] && h_sig[gg][a][i - 1] != T(0)) on = true;
+        pmlc[a][i] = pmlc[a][i - 1] + (on ? 1 : 0);
+      }
     }
     for (int gq = 0; gq < 2; ++gq) {
       int pole_box[6] = {1, 1, 1, 0, 0, 0};
@@ -562,7 +681,10 @@ struct Impl : Base {
                     if (gq == 0 && g.rank < g.nranks - 1 && z0 + zn - 1 == N[2]) phase = 0;
                     if (gq == 1 && g.rank > 0 && z0 == 1) phase = 0;
                   }
-                  tab[gq][phase][mode][lxi].items.push_back(it);
+                  Table& tt = tab[gq][phase][mode][lxi];
+                  tt.items.push_back(it);
+                  tt.cells += (int64_t)xw * yh * zn;
+                  tt.alg_bytes += item_alg_bytes(gq, pmlc, x0, xw, y0, yh, z0, zn);
                 }
               }
           }
@@ -596,6 +718,12 @@ struct Impl : Base {
         if (t.items.empty()) continue;
         p.items = t.d;
         int n = (int)t.items.size();
+        if (profiling) {
+          if (t.ev_used + 2 > t.ev.size()) {
+            for (int q = 0; q < 2; ++q) { cudaEvent_t e; CUDA_OK(cudaEventCreate(&e)); t.ev.push_back(e); }
+          }
+          CUDA_OK(cudaEventRecord(t.ev[t.ev_used], stream));
+        }
         if (marr) {
           if (m == 0) launch_lx<GROUP, 0, true>(p, l, n);
           else if (m == 1) launch_lx<GROUP, 1, true>(p, l, n);
@@ -604,6 +732,10 @@ struct Impl : Base {
           if (m == 0) launch_lx<GROUP, 0, false>(p, l, n);
           else if (m == 1) launch_lx<GROUP, 1, false>(p, l, n);
           else launch_lx<GROUP, 2, false>(p, l, n);
+        }
+        if (profiling) {
+          CUDA_OK(cudaEventRecord(t.ev[t.ev_used + 1], stream));
+          t.ev_used += 2;
         }
       }
     CUDA_OK(cudaGetLastError());
@@ -859,13 +991,19 @@ struct Impl : Base {
     *p = m.M;
     dims[0] = m.n[0]; dims[1] = m.n[1]; dims[2] = m.n[2]; dims[3] = (int64_t)m.freqs.size();
   }
+  double* d_norm = nullptr;
   double monitor_norm(int id) override {
     if (id < 0 || id >= (int)monitors.size()) throw std::string("bad monitor id");
-    std::vector<T> h(2 * monitors[id].elems);
-    monitor_read(id, h.data());
-    double s = 0;
-    for (T v : h) s += (double)v * (double)v;
-    return std::sqrt(s);
+    if (!d_norm) d_norm = (double*)dalloc((sizeof(double) * 2 + sizeof(T) - 1) / sizeof(T));
+    CUDA_OK(cudaMemsetAsync(d_norm, 0, sizeof(double), stream));
+    long long n = 2 * (long long)monitors[id].elems;
+    int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+    if (blocks > 0) sumsq_kernel<T><<<blocks, 256, 0, stream>>>(monitors[id].M, n, d_norm);
+    CUDA_OK(cudaGetLastError());
+    double h = 0;
+    CUDA_OK(cudaMemcpyAsync(&h, d_norm, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    return std::sqrt(h);
   }
   void sync() override {
     CUDA_OK(cudaStreamSynchronize(stream));
@@ -1078,6 +1216,14 @@ int32_t khr_last_step_timing(khr_ctx* ctx, double* ms, int64_t* kernel_launches)
 int32_t khr_voxel_census(khr_ctx* ctx, int64_t counts[4]) {
   NEED_CTX
   KHR_TRY(ctx->impl->census(counts))
+}
+int32_t khr_set_profiling(khr_ctx* ctx, int32_t mode) {
+  NEED_CTX
+  KHR_TRY(ctx->impl->set_profiling(mode))
+}
+int32_t khr_kernel_stat_get(khr_ctx* ctx, int32_t index, khr_kernel_stat* out, int32_t* count) {
+  NEED_CTX
+  KHR_TRY({ int n = ctx->impl->kernel_stat(index, out); if (count) *count = n; })
 }
 int32_t khr_device_bytes(khr_ctx* ctx, int64_t* bytes) {
   NEED_CTX

@@ -553,4 +553,23 @@ __global__ void __launch_bounds__(256) dft_kernel(const MonDesc<T>* __restrict__
   }
 }
 
+// sum of squares (Simulation.jl:440-445 stop_when_dft_decayed reduces |M|^2 every step)
+template <class T>
+__global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ a, long long n, double* __restrict__ out) {
+  double s = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double v = (double)a[i];
+    s += v * v;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  __shared__ double ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int q = 0; q < 8; ++q) t += ws[q];
+    atomicAdd(out, t);
+  }
+}
+
 }  // namespace khr

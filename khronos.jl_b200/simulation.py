@@ -359,42 +359,24 @@ class Simulation:
         return arrays
 
     # ------------------------------------------------------------ prepare
-    def prepare_simulation(self, comm_id=None):
-        """Simulation.jl:92-283 prepare_simulation! (the parts the hot path needs)."""
-        if self.is_prepared:
+    def host_prepare(self):
+        """Host half of prepare_simulation! (Simulation.jl:92-283): everything the hot path is
+        handed — sigma profiles, material / pole arrays, source boxes + amplitudes, monitor
+        index boxes — with no device involved.  Idempotent."""
+        if getattr(self, "_host_ready", False):
             return
-        L = _lib.lib()
         g, T = self.grid, self.T
-        slabs = chunking.z_slab_partition(g, self.boundaries, self.nranks)
-        self.slabs = slabs
-        z_start, nzl = slabs[self.rank]
-        self.z_start, self.nz_local = z_start, nzl
-        desc = _lib.GridDesc()
-        desc.dtype = _lib.KHR_F32 if T is np.float32 else _lib.KHR_F64
-        for a in range(3):
-            desc.n[a] = g.N[a]
-            desc.dl[a] = float(g.dl[a])
-        desc.dt = float(g.dt)
-        desc.z_start, desc.nz_local, desc.rank, desc.nranks = z_start, nzl, self.rank, self.nranks
-        ctx = C.c_void_p()
-        _lib.check(L.khr_ctx_create(self.device, C.byref(desc), C.byref(ctx)))
-        self.ctx = ctx
-        zsl = slice(z_start - 1, z_start - 1 + nzl)
-
+        self.slabs = chunking.z_slab_partition(g, self.boundaries, self.nranks)
+        self.z_start, self.nz_local = self.slabs[self.rank]
         # boundaries (Boundaries.jl:99-164): sigma_B and sigma_D profiles are identical
         self.sigma = None
         if self.boundaries is not None:
             self.sigma = [g.compute_sigma(a, self.boundaries[a][0], self.boundaries[a][1]) for a in range(3)]
-            for grp in (_lib.GROUP_H, _lib.GROUP_E):
-                for a in range(3):
-                    s = np.ascontiguousarray(self.sigma[a])
-                    _lib.check(L.khr_set_pml_sigma(ctx, grp, a, s.ctypes.data, s.size))
-
         # geometry (Geometry.jl:450-663) + absorbers + poles
         arrays, poles = self._rasterize()
         for k, v in self.user_arrays.items():
             if v is not None:
-                arrays[k] = [np.asarray(x, dtype=T) for x in v]
+                arrays[k] = [np.array(x, dtype=T) for x in v]
         arrays = self._apply_absorbers(arrays)
         poles = poles + [(w, gam, np.asarray(s, dtype=T)) for (w, gam, s) in self.user_poles]
         poles = [(w, gam, self._zero_pole_sigma_in_pml(s)) for (w, gam, s) in poles]
@@ -419,39 +401,17 @@ class Simulation:
                     e[nz] = e[nz] / (T(1) + e[nz] * chi1[nz])
                     arrays["eps_inv"][d] = e
         self.material_arrays = arrays
-        kinds = {"eps_inv": _lib.MAT_EPS_INV, "mu_inv": _lib.MAT_MU_INV, "sigma_D": _lib.MAT_SIGMA_D,
-                 "sigma_B": _lib.MAT_SIGMA_B}
-        for k, kind in kinds.items():
-            if arrays[k] is None:
-                continue
-            for d in range(3):
-                a = np.asfortranarray(arrays[k][d][:, :, zsl])
-                _lib.check(L.khr_set_material_array(ctx, kind, d, a.ctypes.data))
         self.poles = poles
-        for (w0, gam, s) in poles:
-            a = np.asfortranarray(s[:, :, zsl])
-            pid = C.c_int32()
-            _lib.check(L.khr_pole_register(ctx, w0, gam, a.ctypes.data, C.byref(pid)))
-
         # sources (Sources.jl:40-135 assemble_sources)
-        self.source_ids = []
-        i3 = C.c_int32 * 3
+        ct = np.complex64 if T is np.float32 else np.complex128
+        self.source_data = []
         for src in self.sources:
             for comp in src.components:
                 start, end = g.grid_volume(src.center, src.size, comp)
                 dims = [end[a] - start[a] + 1 for a in range(3)]
-                amp = self._source_amplitude(src, comp, start, dims)
-                ampT = np.empty(amp.shape + (2,), dtype=T)
-                ampT[..., 0] = amp.real.astype(T)
-                ampT[..., 1] = amp.imag.astype(T)
-                buf = np.ascontiguousarray(np.transpose(ampT, (2, 1, 0, 3)))  # x fastest, (re,im) innermost
-                tp = (C.c_double * 4)(*src.time_profile.params(T))
-                sid = C.c_int32()
-                _lib.check(L.khr_source_register(ctx, comp, i3(*start), i3(*dims), buf.ctypes.data,
-                                                 src.time_profile.kind, tp, C.byref(sid)))
-                self.source_ids.append((sid.value, src, comp, start, dims))
-
-        # monitors: auto-decimation (Monitors.jl:33-78) then registration (:202-272)
+                amp = self._source_amplitude(src, comp, start, dims).astype(ct)  # complex_backend_number.(...)
+                self.source_data.append(dict(src=src, comp=comp, start=start, dims=dims, amp=amp))
+        # monitors: auto-decimation (Monitors.jl:33-78), index boxes (:202-272)
         self.dft_monitors = []
         for m in self.monitors:
             if isinstance(m, FluxMonitor):
@@ -461,6 +421,60 @@ class Simulation:
         self._auto_decimate()
         for m in self.dft_monitors:
             m.start, m.end = g.grid_volume(m.center, m.size, m.component)
+        self._host_ready = True
+
+    def prepare_simulation(self, comm_id=None):
+        """Simulation.jl:92-283 prepare_simulation!: host plan, then registration with the library."""
+        if self.is_prepared:
+            return
+        self.host_prepare()
+        L = _lib.lib()
+        g, T = self.grid, self.T
+        z_start, nzl = self.z_start, self.nz_local
+        desc = _lib.GridDesc()
+        desc.dtype = _lib.KHR_F32 if T is np.float32 else _lib.KHR_F64
+        for a in range(3):
+            desc.n[a] = g.N[a]
+            desc.dl[a] = float(g.dl[a])
+        desc.dt = float(g.dt)
+        desc.z_start, desc.nz_local, desc.rank, desc.nranks = z_start, nzl, self.rank, self.nranks
+        ctx = C.c_void_p()
+        _lib.check(L.khr_ctx_create(self.device, C.byref(desc), C.byref(ctx)))
+        self.ctx = ctx
+        zsl = slice(z_start - 1, z_start - 1 + nzl)
+        if self.sigma is not None:
+            for grp in (_lib.GROUP_H, _lib.GROUP_E):
+                for a in range(3):
+                    s = np.ascontiguousarray(self.sigma[a])
+                    _lib.check(L.khr_set_pml_sigma(ctx, grp, a, s.ctypes.data, s.size))
+        arrays = self.material_arrays
+        kinds = {"eps_inv": _lib.MAT_EPS_INV, "mu_inv": _lib.MAT_MU_INV, "sigma_D": _lib.MAT_SIGMA_D,
+                 "sigma_B": _lib.MAT_SIGMA_B}
+        for k, kind in kinds.items():
+            if arrays[k] is None:
+                continue
+            for d in range(3):
+                a = np.asfortranarray(arrays[k][d][:, :, zsl])
+                _lib.check(L.khr_set_material_array(ctx, kind, d, a.ctypes.data))
+        for (w0, gam, s) in self.poles:
+            a = np.asfortranarray(s[:, :, zsl])
+            pid = C.c_int32()
+            _lib.check(L.khr_pole_register(ctx, w0, gam, a.ctypes.data, C.byref(pid)))
+        self.source_ids = []
+        i3 = C.c_int32 * 3
+        for sd in self.source_data:
+            amp = sd["amp"]
+            ampT = np.empty(amp.shape + (2,), dtype=T)
+            ampT[..., 0] = amp.real
+            ampT[..., 1] = amp.imag
+            buf = np.ascontiguousarray(np.transpose(ampT, (2, 1, 0, 3)))  # x fastest, (re,im) innermost
+            tpf = sd["src"].time_profile
+            tp = (C.c_double * 4)(*tpf.params(T))
+            sid = C.c_int32()
+            _lib.check(L.khr_source_register(ctx, sd["comp"], i3(*sd["start"]), i3(*sd["dims"]), buf.ctypes.data,
+                                             tpf.kind, tp, C.byref(sid)))
+            self.source_ids.append((sid.value, sd["src"], sd["comp"], sd["start"], sd["dims"]))
+        for m in self.dft_monitors:
             fr = (C.c_double * len(m.frequencies))(*[float(T(f)) for f in m.frequencies])
             mid = C.c_int32()
             _lib.check(L.khr_monitor_register(ctx, m.component, i3(*m.start), i3(*m.end), len(m.frequencies), fr,
@@ -490,16 +504,15 @@ class Simulation:
                 p = origin[a] + (i + start[a] - 2) * d[a]
                 wa[i - 1] = interpolation_weight([p], [lo[a]], [hi[a]], [src.size[a]], 1, [d[a]])
             w.append(wa)
-        for ix in range(dims[0]):
-            for iy in range(dims[1]):
-                wxy = 1.0 * w[0][ix] * w[1][iy]
-                for iz in range(dims[2]):
-                    weight = wxy * w[2][iz]
-                    prof = 1.0
-                    if src.profile is not None:
-                        pt = [origin[a] + (i + start[a] - 1) * d[a] for a, i in enumerate((ix, iy, iz))]
-                        prof = src.profile(pt, comp)
-                    amp[ix, iy, iz] = weight * src.amplitude * prof
+        # weight = ((1.0 * wx) * wy) * wz exactly as the reference's running product
+        wgt = ((1.0 * w[0])[:, None, None] * w[1][None, :, None]) * w[2][None, None, :]
+        if src.profile is None:
+            amp[...] = wgt * src.amplitude * 1.0
+        else:
+            coords = [origin[a] + (np.arange(dims[a]) + start[a] - 1) * d[a] for a in range(3)]
+            X, Y, Z = np.meshgrid(*coords, indexing="ij", sparse=True)
+            prof = src.profile([X, Y, Z], comp)
+            amp[...] = wgt * src.amplitude * prof
         return amp
 
     def _auto_decimate(self):
@@ -662,6 +675,28 @@ class Simulation:
         re2 = e2.real * h1.real + e2.imag * h1.imag
         s = (re1 - re2).astype(np.float64) * dA
         return s.sum(axis=(0, 1))
+
+    def set_profiling(self, mode):
+        _lib.check(_lib.lib().khr_set_profiling(self.ctx, int(mode)))
+
+    def kernel_stats(self):
+        """Per-kernel live CUDA-event timing and bytes model (khr_kernel_stat_get)."""
+        L = _lib.lib()
+        n = C.c_int32()
+        _lib.check(L.khr_kernel_stat_get(self.ctx, -1, None, C.byref(n)))
+        out = []
+        for i in range(n.value):
+            st = _lib.KernelStat()
+            _lib.check(L.khr_kernel_stat_get(self.ctx, i, C.byref(st), None))
+            out.append(dict(name=st.name.decode(), launches=st.launches, total_ms=st.total_ms,
+                            cells_per_launch=st.cells_per_launch, alg_bytes_per_launch=st.alg_bytes_per_launch,
+                            ctas=st.ctas))
+        return out
+
+    def monitor_norm(self, monitor):
+        v = C.c_double()
+        _lib.check(_lib.lib().khr_monitor_norm(self.ctx, monitor.id, C.byref(v)))
+        return v.value
 
     def voxel_census(self):
         c = (C.c_int64 * 4)()

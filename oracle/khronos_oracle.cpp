@@ -34,6 +34,9 @@
 #include <limits>
 #include <string>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace {
 
@@ -273,6 +276,7 @@ struct Sim {
   std::vector<int> adjacency;
   long timestep = 0;
   bool sources_active = true;
+  bool sources_auto = true;
   bool prepared = false;
   int nthreads = 0;
 
@@ -845,6 +849,18 @@ struct Sim {
   void step() {
     double t = (double)((T)timestep * dt);
     double t_half = t + (double)(dt / T(2));
+    // Kernels.jl:27-35: once t > last_source_time (= max get_cutoff, TimeSources.jl:40-47,
+    // 134) the sources are switched off for good; a CW source throws in get_cutoff,
+    // the catch keeps them active forever.
+    if (sources_active && sources_auto && !sources.empty()) {
+      bool any_cw = false;
+      double last = -1e300;
+      for (auto& s : sources) {
+        if (s.ts.kind == 0) any_cw = true;
+        last = std::max(last, (double)s.ts.cutoff);
+      }
+      if (!any_cw && t > last) sources_active = false;
+    }
     if (sources_active) step_sources(0, t);
     for (auto& c : chunks) { step_curl(c, 0); update_field(c, 0); }
     if (chunks.size() > 1) exchange_halos(0);
@@ -1113,7 +1129,15 @@ void ko_step(void* hv, int nsteps) {
 
 void ko_set_sources_active(void* hv, int v) {
   Handle* h = (Handle*)hv;
-  DISPATCH(h, S.sources_active = v != 0);
+  DISPATCH(h, { S.sources_active = v != 0; S.sources_auto = false; });
+}
+
+int ko_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
 }
 
 long ko_timestep(void* hv) {

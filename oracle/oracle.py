@@ -70,6 +70,7 @@ def lib():
         L.ko_step.argtypes = [C.c_void_p, C.c_int]
         L.ko_set_sources_active.argtypes = [C.c_void_p, C.c_int]
         L.ko_timestep.restype = C.c_long
+        L.ko_num_threads.restype = C.c_int
         L.ko_timestep.argtypes = [C.c_void_p]
         L.ko_get_field.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
         L.ko_set_field.argtypes = [C.c_void_p, C.c_int, dp]
@@ -78,6 +79,10 @@ def lib():
         L.ko_flux.argtypes = [C.c_void_p, C.c_int, ip, dp]
         _LIB = L
     return _LIB
+
+
+def num_threads():
+    return int(lib().ko_num_threads())
 
 
 def _d(a):
