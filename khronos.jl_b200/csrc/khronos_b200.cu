@@ -231,7 +231,10 @@ struct Impl : Base {
   std::vector<std::vector<uint8_t>> pole_mask;  // host non-zero masks (bytes model only)
   std::vector<uint8_t> sd_mask[2];
   // phase 0 = boundary planes that feed the halo exchange, phase 1 = the rest
-  Table tab[2][2][3][3];
+  Table tab[2][2][3];
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  bool multi_stream = true;
   bool finalized = false;
   // distributed
   void* comm = nullptr;
@@ -259,6 +262,12 @@ struct Impl : Base {
     CUDA_OK(cudaEventCreateWithFlags(&ev_comm, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreate(&ev_t0));
     CUDA_OK(cudaEventCreate(&ev_t1));
+    for (int q = 0; q < 2; ++q) {
+      CUDA_OK(cudaStreamCreateWithFlags(&side[q], cudaStreamNonBlocking));
+      CUDA_OK(cudaEventCreateWithFlags(&ev_join[q], cudaEventDisableTiming));
+    }
+    CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    if (const char* e = getenv("KHR_MULTI_STREAM")) multi_stream = atoi(e) != 0;
     N[0] = gd.n[0]; N[1] = gd.n[1]; N[2] = gd.nz_local;
     PX = round_up(N[0] + 36, 32);
     PY = N[1] + 2;
@@ -576,70 +585,65 @@ struct Impl : Base {
     return b;
   }
 
-  void collect_profile() {
+  template <class F>
+  void for_tables(F f) {
     for (int gq = 0; gq < 2; ++gq)
       for (int ph = 0; ph < 2; ++ph)
-        for (int m = 0; m < 3; ++m)
-          for (int l = 0; l < 3; ++l) {
-            Table& t = tab[gq][ph][m][l];
-            for (size_t q = 0; q + 1 < t.ev_used; q += 2) {
-              float ms = 0;
-              if (cudaEventElapsedTime(&ms, t.ev[q], t.ev[q + 1]) == cudaSuccess) { t.total_ms += ms; t.nlaunch += 1; }
-              else cudaGetLastError();
-            }
-            t.ev_used = 0;
-          }
+        for (int m = 0; m < 3; ++m) f(tab[gq][ph][m], gq, ph, m);
+  }
+  void collect_profile() {
+    for_tables([&](Table& t, int, int, int) {
+      for (size_t q = 0; q + 1 < t.ev_used; q += 2) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, t.ev[q], t.ev[q + 1]) == cudaSuccess) { t.total_ms += ms; t.nlaunch += 1; }
+        else cudaGetLastError();
+      }
+      t.ev_used = 0;
+    });
   }
   void set_profiling(int on) override {
-    CUDA_OK(cudaStreamSynchronize(stream));
+    sync_all();
     collect_profile();
     profiling = on != 0;
-    if (on == 2)  // reset accumulators
-      for (int gq = 0; gq < 2; ++gq)
-        for (int ph = 0; ph < 2; ++ph)
-          for (int m = 0; m < 3; ++m)
-            for (int l = 0; l < 3; ++l) { tab[gq][ph][m][l].total_ms = 0; tab[gq][ph][m][l].nlaunch = 0; }
+    if (on == 2) for_tables([&](Table& t, int, int, int) { t.total_ms = 0; t.nlaunch = 0; });
   }
   int kernel_stat(int idx, khr_kernel_stat* out) override {
-    CUDA_OK(cudaStreamSynchronize(stream));
+    sync_all();
     collect_profile();
     int k = 0;
-    for (int gq = 0; gq < 2; ++gq)
-      for (int ph = 0; ph < 2; ++ph)
-        for (int m = 0; m < 3; ++m)
-          for (int l = 0; l < 3; ++l) {
-            Table& t = tab[gq][ph][m][l];
-            if (t.items.empty()) continue;
-            if (k == idx && out) {
-              memset(out, 0, sizeof(*out));
-              static const char* mn[3] = {"interior", "pml", "full"};
-              snprintf(out->name, sizeof(out->name), "step_kernel<%s,%s,LX%d,%s,%s>%s", sizeof(T) == 4 ? "f32" : "f64",
-                       gq == 0 ? "H" : "E", 8 << l, mn[m], m_arr[gq][0] ? "marr" : "mscalar", ph == 0 ? "[boundary]" : "");
-              out->launches = t.nlaunch;
-              out->total_ms = t.total_ms;
-              out->cells_per_launch = t.cells;
-              out->alg_bytes_per_launch = t.alg_bytes;
-              out->ctas = (int64_t)t.items.size();
-            }
-            ++k;
-          }
+    for_tables([&](Table& t, int gq, int ph, int m) {
+      if (t.items.empty()) return;
+      if (k == idx && out) {
+        memset(out, 0, sizeof(*out));
+        static const char* mn[3] = {"interior", "pml", "full"};
+        snprintf(out->name, sizeof(out->name), "step_kernel<%s,%s,%s,%s>%s", sizeof(T) == 4 ? "f32" : "f64",
+                 gq == 0 ? "H" : "E", mn[m], m_arr[gq][0] ? "marr" : "mscalar", ph == 0 ? "[boundary]" : "");
+        out->launches = t.nlaunch;
+        out->total_ms = t.total_ms;
+        out->cells_per_launch = t.cells;
+        out->alg_bytes_per_launch = t.alg_bytes;
+        out->ctas = (int64_t)t.items.size();
+      }
+      ++k;
+    });
     return k;
   }
 
-  void build_tables() {
-    const int ZSEG = 32;
-    std::vector<Range> xr = axis_ranges(0, 32), yr = axis_ranges(1, 1), zr = axis_ranges(2, 1);
-    // boundary planes for the halo exchange get their own thin z ranges
-    std::vector<Range> zr2;
-    for (auto r : zr) {
-      if (g.nranks > 1) {
-        // H half-step sends the top plane, E half-step the bottom plane: isolate both
-        int s = r.s, e = r.e;
-        if (s == 1 && g.rank > 0 && e > s) { zr2.push_back({1, 1, r.pml}); s = 2; }
-        if (e == N[2] && g.rank < g.nranks - 1 && e > s) { zr2.push_back({s, e - 1, r.pml}); zr2.push_back({e, e, r.pml}); }
-        else zr2.push_back({s, e, r.pml});
-      } else zr2.push_back(r);
+  // split ranges at extra cut points (cell index where a new range starts)
+  static std::vector<Range> split_ranges(const std::vector<Range>& in, std::vector<int> cuts) {
+    std::sort(cuts.begin(), cuts.end());
+    std::vector<Range> out;
+    for (auto r : in) {
+      int s = r.s;
+      for (int c : cuts)
+        if (c > s && c <= r.e) { out.push_back({s, c - 1, r.pml}); s = c; }
+      out.push_back({s, r.e, r.pml});
     }
+    return out;
+  }
+
+  void build_tables() {
+    std::vector<Range> xr0 = axis_ranges(0, 32), yr0 = axis_ranges(1, 1), zr0 = axis_ranges(2, 1);
     // prefix counts of PML cells per axis (for the bytes model)
     std::vector<int> pmlc[3];
     for (int a = 0; a < 3; ++a) {
@@ -652,93 +656,130 @@ struct Impl : Base {
       }
     }
     for (int gq = 0; gq < 2; ++gq) {
-      int pole_box[6] = {1, 1, 1, 0, 0, 0};
-      if (gq == 1) for (auto& p : poles) box_union(pole_box, p.box);
+      // boxes that need the full kernel (sources, sigma_D/B, poles); the ranges are cut at
+      // their faces so that only the voxels inside them pay for the extras
+      struct Box { int b[6]; bool src; };
+      std::vector<Box> boxes;
+      for (auto& s : sources)
+        if ((s.comp >= 3) == (gq == 0))
+          boxes.push_back({{s.s[0], s.s[1], s.s[2], s.s[0] + s.d[0] - 1, s.s[1] + s.d[1] - 1, s.s[2] + s.d[2] - 1}, true});
+      if (has_sd[gq] && sd_box[gq][0] <= sd_box[gq][3]) {
+        Box b; for (int q = 0; q < 6; ++q) b.b[q] = sd_box[gq][q]; b.src = false; boxes.push_back(b);
+      }
+      if (gq == 1)
+        for (auto& pl : poles)
+          if (pl.box[0] <= pl.box[3]) { Box b; for (int q = 0; q < 6; ++q) b.b[q] = pl.box[q]; b.src = false; boxes.push_back(b); }
+      std::vector<int> cx, cyv, czv;
+      for (auto& bx : boxes) {
+        cx.push_back(1 + 32 * ((std::max(bx.b[0], 1) - 1) / 32));
+        cx.push_back(1 + 32 * ((std::max(bx.b[3], 0) + 31) / 32));
+        cyv.push_back(bx.b[1]); cyv.push_back(bx.b[4] + 1);
+        czv.push_back(bx.b[2]); czv.push_back(bx.b[5] + 1);
+      }
+      if (g.nranks > 1) {
+        // the plane that feeds the halo exchange gets its own thin range (boundary-first launch)
+        if (gq == 0 && g.rank < g.nranks - 1) czv.push_back(N[2]);
+        if (gq == 1 && g.rank > 0) czv.push_back(2);
+      }
+      std::vector<Range> xr = split_ranges(xr0, cx), yr = split_ranges(yr0, cyv), zr = split_ranges(zr0, czv);
+      // z segment length: enough CTAs to fill 148 SMs several times over, but long enough
+      // to amortise the carried plane
+      long long tiles_xy = 0;
       for (auto& X : xr) {
-        int lxi = lx_index(X.e - X.s + 1);
-        int lx = 8 << lxi;
-        int tw = 4 * lx, th = CTA / lx;
-        for (auto& Z : zr2)
-          for (int z0 = Z.s; z0 <= Z.e; z0 += ZSEG) {
-            int zn = std::min(ZSEG, Z.e - z0 + 1);
-            for (auto& Y : yr)
+        int lx = 8 << lx_index(X.e - X.s + 1);
+        for (auto& Y : yr) tiles_xy += (long long)((X.e - X.s) / (4 * lx) + 1) * ((Y.e - Y.s) / (CTA / lx) + 1);
+      }
+      int zseg = (int)std::min<long long>(32, std::max<long long>(4, (tiles_xy * N[2] + 2367) / 2368));
+      if (const char* e = getenv("KHR_ZSEG")) zseg = std::max(1, atoi(e));
+      for (auto& Z : zr)
+        for (int z0 = Z.s; z0 <= Z.e; z0 += zseg) {
+          int zn = std::min(zseg, Z.e - z0 + 1);
+          for (auto& Y : yr)
+            for (auto& X : xr) {
+              int lxi = lx_index(X.e - X.s + 1);
+              int lx = 8 << lxi;
+              int tw = 4 * lx, th = CTA / lx;
               for (int y0 = Y.s; y0 <= Y.e; y0 += th) {
                 int yh = std::min(th, Y.e - y0 + 1);
                 for (int x0 = X.s; x0 <= X.e; x0 += tw) {
                   int xw = std::min(tw, X.e - x0 + 1);
-                  WorkItem it{x0, xw, y0, yh, z0, zn, 0, 0};
+                  WorkItem it{x0, xw, y0, yh, z0, zn, 0, 3 + lxi};
                   bool extras = false;
-                  for (auto& s : sources) {
-                    bool sh = (s.comp >= 3) == (gq == 0);
-                    int b[6] = {s.s[0], s.s[1], s.s[2], s.s[0] + s.d[0] - 1, s.s[1] + s.d[1] - 1, s.s[2] + s.d[2] - 1};
-                    if (sh && boxes_hit(b, x0, x0 + xw - 1, y0, y0 + yh - 1, z0, z0 + zn - 1)) { extras = true; it.flags |= 1; }
-                  }
-                  if (has_sd[gq] && boxes_hit(sd_box[gq], x0, x0 + xw - 1, y0, y0 + yh - 1, z0, z0 + zn - 1)) extras = true;
-                  if (gq == 1 && boxes_hit(pole_box, x0, x0 + xw - 1, y0, y0 + yh - 1, z0, z0 + zn - 1)) extras = true;
+                  for (auto& bx : boxes)
+                    if (boxes_hit(bx.b, x0, x0 + xw - 1, y0, y0 + yh - 1, z0, z0 + zn - 1)) {
+                      extras = true;
+                      if (bx.src) it.flags |= 1;
+                    }
                   int mode = extras ? 2 : ((X.pml || Y.pml || Z.pml) ? 1 : 0);
                   int phase = 1;
                   if (g.nranks > 1) {
                     if (gq == 0 && g.rank < g.nranks - 1 && z0 + zn - 1 == N[2]) phase = 0;
                     if (gq == 1 && g.rank > 0 && z0 == 1) phase = 0;
                   }
-                  Table& tt = tab[gq][phase][mode][lxi];
+                  Table& tt = tab[gq][phase][mode];
                   tt.items.push_back(it);
                   tt.cells += (int64_t)xw * yh * zn;
                   tt.alg_bytes += item_alg_bytes(gq, pmlc, x0, xw, y0, yh, z0, zn);
                 }
               }
-          }
-      }
-      for (int ph = 0; ph < 2; ++ph)
-        for (int m = 0; m < 3; ++m)
-          for (int l = 0; l < 3; ++l) {
-            Table& t = tab[gq][ph][m][l];
-            if (t.items.empty()) continue;
-            size_t bytes = t.items.size() * sizeof(WorkItem);
-            t.d = (WorkItem*)dalloc((bytes + sizeof(T) - 1) / sizeof(T), false);
-            CUDA_OK(cudaMemcpyAsync(t.d, t.items.data(), bytes, cudaMemcpyHostToDevice, stream));
-          }
+            }
+        }
     }
+    for_tables([&](Table& t, int, int, int) {
+      if (t.items.empty()) return;
+      size_t bytes = t.items.size() * sizeof(WorkItem);
+      t.d = (WorkItem*)dalloc((bytes + sizeof(T) - 1) / sizeof(T), false);
+      CUDA_OK(cudaMemcpyAsync(t.d, t.items.data(), bytes, cudaMemcpyHostToDevice, stream));
+    });
     CUDA_OK(cudaStreamSynchronize(stream));
   }
 
   // ---- stepping -------------------------------------------------------------
-  template <int GROUP, int MODE, bool MARR>
-  void launch_lx(const StepParams<T>& p, int lxi, int nitems) {
-    if (lxi == 2) step_kernel<T, GROUP, 32, MODE, MARR><<<nitems, CTA, 0, stream>>>(p);
-    else if (lxi == 1) step_kernel<T, GROUP, 16, MODE, MARR><<<nitems, CTA, 0, stream>>>(p);
-    else step_kernel<T, GROUP, 8, MODE, MARR><<<nitems, CTA, 0, stream>>>(p);
+  template <int GROUP, int MODE>
+  void launch_mode(const StepParams<T>& p, bool marr, int n, cudaStream_t st) {
+    if (marr) step_kernel<T, GROUP, MODE, true><<<n, CTA, 0, st>>>(p);
+    else step_kernel<T, GROUP, MODE, false><<<n, CTA, 0, st>>>(p);
     ++launches;
   }
+  // The (up to) three kernels of a half-step phase are independent: the interior one runs
+  // on the main stream, the PML and the full one on side streams, joined before the next phase.
   template <int GROUP>
   void launch_group(StepParams<T>& p, int phase, bool marr) {
-    for (int m = 0; m < 3; ++m)
-      for (int l = 0; l < 3; ++l) {
-        Table& t = tab[GROUP][phase][m][l];
-        if (t.items.empty()) continue;
-        p.items = t.d;
-        int n = (int)t.items.size();
-        if (profiling) {
-          if (t.ev_used + 2 > t.ev.size()) {
-            for (int q = 0; q < 2; ++q) { cudaEvent_t e; CUDA_OK(cudaEventCreate(&e)); t.ev.push_back(e); }
-          }
-          CUDA_OK(cudaEventRecord(t.ev[t.ev_used], stream));
-        }
-        if (marr) {
-          if (m == 0) launch_lx<GROUP, 0, true>(p, l, n);
-          else if (m == 1) launch_lx<GROUP, 1, true>(p, l, n);
-          else launch_lx<GROUP, 2, true>(p, l, n);
-        } else {
-          if (m == 0) launch_lx<GROUP, 0, false>(p, l, n);
-          else if (m == 1) launch_lx<GROUP, 1, false>(p, l, n);
-          else launch_lx<GROUP, 2, false>(p, l, n);
-        }
-        if (profiling) {
-          CUDA_OK(cudaEventRecord(t.ev[t.ev_used + 1], stream));
-          t.ev_used += 2;
-        }
+    bool forked = false;
+    bool used[3] = {false, false, false};
+    for (int m = 2; m >= 0; --m) {
+      Table& t = tab[GROUP][phase][m];
+      if (t.items.empty()) continue;
+      cudaStream_t st = (m == 0 || !multi_stream) ? stream : side[m - 1];
+      if (st != stream && !forked) {
+        CUDA_OK(cudaEventRecord(ev_fork, stream));
+        forked = true;
       }
+      if (st != stream) CUDA_OK(cudaStreamWaitEvent(st, ev_fork, 0));
+      p.items = t.d;
+      int n = (int)t.items.size();
+      if (profiling) {
+        if (t.ev_used + 2 > t.ev.size()) {
+          for (int q = 0; q < 2; ++q) { cudaEvent_t e; CUDA_OK(cudaEventCreate(&e)); t.ev.push_back(e); }
+        }
+        CUDA_OK(cudaEventRecord(t.ev[t.ev_used], st));
+      }
+      if (m == 0) launch_mode<GROUP, 0>(p, marr, n, st);
+      else if (m == 1) launch_mode<GROUP, 1>(p, marr, n, st);
+      else launch_mode<GROUP, 2>(p, marr, n, st);
+      if (profiling) {
+        CUDA_OK(cudaEventRecord(t.ev[t.ev_used + 1], st));
+        t.ev_used += 2;
+      }
+      if (st != stream) { CUDA_OK(cudaEventRecord(ev_join[m - 1], st)); used[m] = true; }
+    }
+    for (int m = 1; m < 3; ++m)
+      if (used[m]) CUDA_OK(cudaStreamWaitEvent(stream, ev_join[m - 1], 0));
     CUDA_OK(cudaGetLastError());
+  }
+  void sync_all() {
+    CUDA_OK(cudaStreamSynchronize(stream));
+    for (int q = 0; q < 2; ++q) CUDA_OK(cudaStreamSynchronize(side[q]));
   }
 
   double time_now() const { return (double)((T)timestep * dt); }  // Simulation.jl:22 round_time
@@ -1006,7 +1047,7 @@ struct Impl : Base {
     return std::sqrt(h);
   }
   void sync() override {
-    CUDA_OK(cudaStreamSynchronize(stream));
+    sync_all();
     CUDA_OK(cudaStreamSynchronize(comm_stream));
     if (last_ms < 0) {
       float ms = 0;

@@ -43,7 +43,7 @@ struct WorkItem {
   int y0, yh;   // first row and number of rows (<= 256/LX)
   int z0, zn;   // first local plane and number of planes marched
   int flags;    // bit0: tile may contain a source of this group
-  int pad;
+  int lx_log2;  // lanes along x = 1 << lx_log2 (3, 4 or 5); rows per CTA = 256 >> lx_log2
 };
 
 // compact index along a PML axis: cells 1..lo_w map to 0..lo_w-1, cells >= hi_base
@@ -130,20 +130,22 @@ struct Co {  // PML coefficients of one cell along one axis
 };
 
 // ----------------------------------------------------------------------------
-// One component of the general cascade for the 4 cells of a thread.
+// One component of the general cascade for the 4 cells of a thread, on registers
+// only (the caller batches every load before and every store after, so that the
+// memory operations of the three components overlap instead of serialising).
 //   k      : m^-1 * K (scaled curl increment)
 //   cn/cp/co: coefficients along next/prev/own axis (per element)
 //   useU/useW: thread-level "any sigma != 0" on the next/own axis
-//   a      : field values (in: old, out: new)
+//   a      : field values (in: old, out: new); u, w, c: auxiliary values (in/out)
 //   s_old/s_new: m^-1-scaled additive terms riding on the stored field
 //                (source S and polarisation -P) of the previous / this step
-//   sd     : 0.5*dt*sigma_D per element (0 when absent); Cp: C-stage array or null
+//   sd     : 0.5*dt*sigma_D per element (0 when absent)
 // ----------------------------------------------------------------------------
 template <class T, bool EXTRAS>
 __device__ __forceinline__ void cascade(const T (&k)[4], const Co<T> (&cn)[4], const Co<T> (&cp)[4],
-                                        const Co<T> (&co)[4], bool useU, bool useW, T* __restrict__ Up,
-                                        T* __restrict__ Wp, T (&a)[4], const T (&s_old)[4], const T (&s_new)[4],
-                                        bool has_sd, const T (&sd)[4], T* __restrict__ Cp, const bool (&valid)[4]) {
+                                        const Co<T> (&co)[4], bool useU, bool useW, V4<T>& u, V4<T>& w, V4<T>& a,
+                                        const T (&s_old)[4], const T (&s_new)[4], bool has_sd, const T (&sd)[4],
+                                        V4<T>& c, const bool (&valid)[4]) {
   T in[4];
   T omt[4], ipt[4];
 #pragma unroll
@@ -153,11 +155,6 @@ __device__ __forceinline__ void cascade(const T (&k)[4], const Co<T> (&cn)[4], c
     ipt[e] = cp[e].ip;
   }
   if (EXTRAS && has_sd) {
-    bool anyc = false;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) anyc |= (sd[e] != T(0)) && (cn[e].s != T(0) || cp[e].s != T(0));
-    V4<T> c = zero4<T>();
-    if (anyc && Cp) c = ld4(Cp);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       if (sd[e] != T(0)) {
@@ -174,11 +171,9 @@ __device__ __forceinline__ void cascade(const T (&k)[4], const Co<T> (&cn)[4], c
         }
       }
     }
-    if (anyc && Cp) st4(Cp, c);
   }
   if (useU) {
     // U stage (Helpers.jl:55-56): U <- ((1-sn)U + in)/(1+sn); bypassed where sn == 0
-    V4<T> u = ld4(Up);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       T un = (cn[e].om * u.v[e] + in[e]) * cn[e].ip;
@@ -186,28 +181,24 @@ __device__ __forceinline__ void cascade(const T (&k)[4], const Co<T> (&cn)[4], c
       in[e] = on ? (un - u.v[e]) : in[e];
       if (on && valid[e]) u.v[e] = un;
     }
-    st4(Up, u);
   }
-  V4<T> w = zero4<T>();
-  if (useW) w = ld4(Wp);
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     bool won = useW && (co[e].s != T(0));
     // T stage on the stored (scaled) flux: t = m^-1 (T + S - P); the additive
     // S/P parts are not damped by the reference, so peel them off and put the
     // new ones back (Helpers.jl:332-335)
-    T t_old = won ? w.v[e] : a[e];
+    T t_old = won ? w.v[e] : a.v[e];
     T t_new;
     if constexpr (EXTRAS) t_new = (omt[e] * (t_old - s_old[e]) + in[e]) * ipt[e] + s_new[e];
     else t_new = (omt[e] * t_old + in[e]) * ipt[e];
     // W stage (Helpers.jl:336-343)
-    T a_new = won ? ((a[e] + (T(1) + co[e].s) * t_new) - co[e].om * t_old) : t_new;
+    T a_new = won ? ((a.v[e] + (T(1) + co[e].s) * t_new) - co[e].om * t_old) : t_new;
     if (valid[e]) {
-      a[e] = a_new;
+      a.v[e] = a_new;
       if (won) w.v[e] = t_new;
     }
   }
-  if (useW) st4(Wp, w);
 }
 
 // ----------------------------------------------------------------------------
@@ -215,15 +206,24 @@ __device__ __forceinline__ void cascade(const T (&k)[4], const Co<T> (&cn)[4], c
 //   GROUP 0: H from curl E (idx_curl = +1); GROUP 1: E from curl H (idx_curl = -1)
 //   MODE 0: pure interior; 1: + PML cascade; 2: + sigma_D/B, sources, ADE poles
 //   MARR   : per-voxel m^-1 arrays (eps^-1 or mu^-1) instead of a scalar
+// The row width (lanes along x) is a per-item power of two, 8/16/32.
 // ----------------------------------------------------------------------------
-template <class T, int GROUP, int LX, int MODE, bool MARR>
-__global__ void __launch_bounds__(CTA) step_kernel(const __grid_constant__ StepParams<T> p) {
+template <class T, int MODE>
+constexpr int min_ctas() {
+  // registers/thread budget: 64K regs per SM, 256-thread CTAs
+  return sizeof(T) == 4 ? (MODE == 0 ? 3 : (MODE == 1 ? 2 : 1)) : 1;
+}
+
+template <class T, int GROUP, int MODE, bool MARR>
+__global__ void __launch_bounds__(CTA, min_ctas<T, MODE>()) step_kernel(const __grid_constant__ StepParams<T> p) {
   constexpr int IC = (GROUP == 0) ? 1 : -1;
   constexpr bool GENERAL = MODE >= 1;   // PML cascade
   constexpr bool EXTRAS = MODE == 2;    // + sources, sigma_D/B, ADE poles
   const WorkItem it = p.items[blockIdx.x];
-  const int lane_x = threadIdx.x % LX;
-  const int row = threadIdx.x / LX;
+  const int lxl = it.lx_log2;
+  const int LX = 1 << lxl;
+  const int lane_x = threadIdx.x & (LX - 1);
+  const int row = threadIdx.x >> lxl;
   const int gx = it.x0 + 4 * lane_x;
   const int iy = it.y0 + row;
   const int lanes = (it.xw + 3) >> 2;
@@ -284,8 +284,38 @@ __global__ void __launch_bounds__(CTA) step_kernel(const __grid_constant__ StepP
 
   for (int iz = it.z0; iz < it.z0 + it.zn; ++iz) {
     const long long base = p.plane * (long long)iz + fo;
+    const long long mbase = p.mplane * (long long)(iz - 1) + mo;
     V4<T> ax0, ay0, az0, ax_z, ay_z, az_y, ax_y;
+    V4<T> fx, fy, fz, m0, m1, m2;
     T ay_x = T(0), az_x = T(0);
+    T* __restrict__ Fx = p.F[0] + base;
+    T* __restrict__ Fy = p.F[1] + base;
+    T* __restrict__ Fz = p.F[2] + base;
+    // ---- general path: plane coefficients, aux addresses, aux loads (all issued up front) ----
+    Co<T> czc;
+    bool hasz = false;
+    V4<T> ux, uy, uz, wx, wy, wz;
+    T *Uxp = nullptr, *Uyp = nullptr, *Uzp = nullptr, *Wxp = nullptr, *Wyp = nullptr, *Wzp = nullptr;
+    if constexpr (GENERAL) {
+      czc.s = p.sg[2][iz - 1]; czc.om = p.om[2][iz - 1]; czc.ip = p.ip[2][iz - 1];
+      hasz = act && (czc.s != T(0));
+      ux = uy = uz = wx = wy = wz = zero4<T>();
+      if (hasx) {
+        const long long xsl = (long long)p.cxp * p.n[1] * (long long)(iz - 1) + xs_off;
+        Wxp = p.W[0] + xsl; Uzp = p.U[2] + xsl;
+        wx = ld4(Wxp); uz = ld4(Uzp);
+      }
+      if (hasy) {
+        const long long ysl = (long long)p.mpx * p.cy * (long long)(iz - 1) + ys_off;
+        Wyp = p.W[1] + ysl; Uxp = p.U[0] + ysl;
+        wy = ld4(Wyp); ux = ld4(Uxp);
+      }
+      if (hasz) {
+        const long long zsl = p.mplane * (long long)p.slab[2].idx(iz) + mo;
+        Wzp = p.W[2] + zsl; Uyp = p.U[1] + zsl;
+        wz = ld4(Wzp); uy = ld4(Uyp);
+      }
+    }
     if (act) {
       if constexpr (GROUP == 0) {
         ax0 = ax_c; ay0 = ay_c;
@@ -303,9 +333,14 @@ __global__ void __launch_bounds__(CTA) step_kernel(const __grid_constant__ StepP
         ay_x = Ay[base + (GROUP == 0 ? 4 : -1)];
         az_x = Az[base + (GROUP == 0 ? 4 : -1)];
       }
+      fx = ld4(Fx); fy = ld4(Fy); fz = ld4(Fz);
+      if constexpr (MARR) { m0 = ld4(p.m_arr[0] + mbase); m1 = ld4(p.m_arr[1] + mbase); m2 = ld4(p.m_arr[2] + mbase); }
     } else {
       ax0 = ay0 = az0 = ax_z = ay_z = az_y = ax_y = zero4<T>();
     }
+#define KHR_M0(e) (MARR ? m0.v[e] : p.m_inv)
+#define KHR_M1(e) (MARR ? m1.v[e] : p.m_inv)
+#define KHR_M2(e) (MARR ? m2.v[e] : p.m_inv)
     // x neighbour by shuffle inside the LX-lane row
     {
       T sy, sz;
@@ -331,23 +366,10 @@ __global__ void __launch_bounds__(CTA) step_kernel(const __grid_constant__ StepP
           azx = (e > 0) ? az0.v[(e + 3) & 3] : az_x;
         }
         // K = dt * curl (Helpers.jl:286-298), same operation order as the reference
-        kx[e] = dt * (idz_ * (ay_z.v[e] - ay0.v[e]) - idy_ * (az_y.v[e] - az0.v[e]));
-        ky[e] = dt * (idx_ * (azx - az0.v[e]) - idz_ * (ax_z.v[e] - ax0.v[e]));
-        kz[e] = dt * (idy_ * (ax_y.v[e] - ax0.v[e]) - idx_ * (ayx - ay0.v[e]));
+        kx[e] = KHR_M0(e) * (dt * (idz_ * (ay_z.v[e] - ay0.v[e]) - idy_ * (az_y.v[e] - az0.v[e])));
+        ky[e] = KHR_M1(e) * (dt * (idx_ * (azx - az0.v[e]) - idz_ * (ax_z.v[e] - ax0.v[e])));
+        kz[e] = KHR_M2(e) * (dt * (idy_ * (ax_y.v[e] - ax0.v[e]) - idx_ * (ayx - ay0.v[e])));
       }
-      const long long mbase = p.mplane * (long long)(iz - 1) + mo;
-      if constexpr (MARR) {
-        V4<T> m0 = ld4(p.m_arr[0] + mbase), m1 = ld4(p.m_arr[1] + mbase), m2 = ld4(p.m_arr[2] + mbase);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { kx[e] = m0.v[e] * kx[e]; ky[e] = m1.v[e] * ky[e]; kz[e] = m2.v[e] * kz[e]; }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { kx[e] = p.m_inv * kx[e]; ky[e] = p.m_inv * ky[e]; kz[e] = p.m_inv * kz[e]; }
-      }
-      T* __restrict__ Fx = p.F[0] + base;
-      T* __restrict__ Fy = p.F[1] + base;
-      T* __restrict__ Fz = p.F[2] + base;
-      V4<T> fx = ld4(Fx), fy = ld4(Fy), fz = ld4(Fz);
 
       if constexpr (!GENERAL) {
 #pragma unroll
@@ -356,122 +378,107 @@ __global__ void __launch_bounds__(CTA) step_kernel(const __grid_constant__ StepP
         }
       } else {
         // ---- general path ----
-        Co<T> czc;
-        czc.s = p.sg[2][iz - 1]; czc.om = p.om[2][iz - 1]; czc.ip = p.ip[2][iz - 1];
-        const bool hasz = czc.s != T(0);
         Co<T> cyv[4], czv[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) { cyv[e] = cyc; czv[e] = czc; }
-        T so[3][4], sn[3][4];
+        T so[3][4], sn[3][4], sd[3][4];
 #pragma unroll
         for (int d = 0; d < 3; ++d)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) { so[d][e] = T(0); sn[d][e] = T(0); }
-        // m^-1 per component/element (needed to scale S and P)
-        T mi[3][4];
-        if (EXTRAS && (srcmask != 0 || (GROUP == 1 && p.npole > 0))) {
-          if constexpr (MARR) {
-            V4<T> m0 = ld4(p.m_arr[0] + mbase), m1 = ld4(p.m_arr[1] + mbase), m2 = ld4(p.m_arr[2] + mbase);
+          for (int e = 0; e < 4; ++e) { so[d][e] = T(0); sn[d][e] = T(0); sd[d][e] = T(0); }
+        V4<T> c0 = zero4<T>(), c1 = zero4<T>(), c2 = zero4<T>();
+        bool has_sd = false, use_c = false;
+        bool pol_on[MAXPOLE];
+        if constexpr (EXTRAS) {
+          // sources (Sources.jl:355-356): S = real(a(t) * A[x])
+          if (srcmask != 0) {
+            for (int q = 0; q < p.nsrc; ++q) {
+              if (!((srcmask >> q) & 1u)) continue;
+              const SrcDesc<T>& s = p.src[q];
+              const int ly = iy - s.s[1], lz = iz - s.s[2];
+              if (ly < 0 || ly >= s.d[1] || lz < 0 || lz >= s.d[2]) continue;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { mi[0][e] = m0.v[e]; mi[1][e] = m1.v[e]; mi[2][e] = m2.v[e]; }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { mi[0][e] = mi[1][e] = mi[2][e] = p.m_inv; }
-          }
-        }
-        // sources (Sources.jl:355-356): S = real(a(t) * A[x])
-        if (EXTRAS && srcmask != 0) {
-          for (int q = 0; q < p.nsrc; ++q) {
-            if (!((srcmask >> q) & 1u)) continue;
-            const SrcDesc<T>& s = p.src[q];
-            const int ly = iy - s.s[1], lz = iz - s.s[2];
-            if (ly < 0 || ly >= s.d[1] || lz < 0 || lz >= s.d[2]) continue;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int lx = gx + e - s.s[0];
-              if (lx >= 0 && lx < s.d[0]) {
-                const size_t ai = 2 * ((size_t)lx + (size_t)s.d[0] * ((size_t)ly + (size_t)s.d[1] * (size_t)lz));
-                const T are = s.amp[ai], aim = s.amp[ai + 1];
-                const T vn = s.an_re * are - s.an_im * aim;
-                const T vo = s.ao_re * are - s.ao_im * aim;
-#pragma unroll
-                for (int d = 0; d < 3; ++d)
-                  if (d == s.comp) { sn[d][e] += mi[d][e] * vn; so[d][e] += mi[d][e] * vo; }
+              for (int e = 0; e < 4; ++e) {
+                const int lx = gx + e - s.s[0];
+                if (lx >= 0 && lx < s.d[0]) {
+                  const size_t ai = 2 * ((size_t)lx + (size_t)s.d[0] * ((size_t)ly + (size_t)s.d[1] * (size_t)lz));
+                  const T are = s.amp[ai], aim = s.amp[ai + 1];
+                  const T vn = s.an_re * are - s.an_im * aim;
+                  const T vo = s.ao_re * are - s.ao_im * aim;
+                  if (s.comp == 0) { sn[0][e] += KHR_M0(e) * vn; so[0][e] += KHR_M0(e) * vo; }
+                  else if (s.comp == 1) { sn[1][e] += KHR_M1(e) * vn; so[1][e] += KHR_M1(e) * vo; }
+                  else { sn[2][e] += KHR_M2(e) * vn; so[2][e] += KHR_M2(e) * vo; }
+                }
               }
             }
           }
-        }
-        // polarisation: the stored E carries -eps^-1 P^{n-1}; this step puts -eps^-1 P^n
-        bool pol_on[MAXPOLE];
-        if constexpr (GROUP == 1 && EXTRAS) {
+          // polarisation: the stored E carries -eps^-1 P^{n-1}; this step puts -eps^-1 P^n
+          if constexpr (GROUP == 1) {
 #pragma unroll
-          for (int q = 0; q < MAXPOLE; ++q) {
-            pol_on[q] = false;
-            if (q < p.npole) {
-              V4<T> sg = ld4(p.pole[q].sigma + mbase);
-              pol_on[q] = (sg.v[0] != T(0)) || (sg.v[1] != T(0)) || (sg.v[2] != T(0)) || (sg.v[3] != T(0));
-              if (pol_on[q]) {
+            for (int q = 0; q < MAXPOLE; ++q) {
+              pol_on[q] = false;
+              if (q < p.npole) {
+                V4<T> sg = ld4(p.pole[q].sigma + mbase);
+                pol_on[q] = (sg.v[0] != T(0)) || (sg.v[1] != T(0)) || (sg.v[2] != T(0)) || (sg.v[3] != T(0));
+                if (pol_on[q]) {
+#pragma unroll
+                  for (int d = 0; d < 3; ++d) {
+                    V4<T> pc = ld4(p.pole[q].Pc[d] + mbase), pp = ld4(p.pole[q].Pp[d] + mbase);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const T mm = (d == 0) ? KHR_M0(e) : (d == 1) ? KHR_M1(e) : KHR_M2(e);
+                      sn[d][e] -= mm * pc.v[e];
+                      so[d][e] -= mm * pp.v[e];
+                    }
+                  }
+                }
+              }
+            }
+          }
+          // material conductivity
+          has_sd = p.sigD[0] != nullptr;
+          if (has_sd) {
+            bool anysd = false;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              V4<T> s4 = ld4(p.sigD[d] + mbase);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { sd[d][e] = T(0.5) * (dt * s4.v[e]); anysd |= (s4.v[e] != T(0)); }
+            }
+            use_c = anysd && (p.C[0] != nullptr) && (hasx || hasy || hasz);
+            if (use_c) { c0 = ld4(p.C[0] + mbase); c1 = ld4(p.C[1] + mbase); c2 = ld4(p.C[2] + mbase); }
+          }
+        }
+        // x: next = y, prev = z, own = x
+        cascade<T, EXTRAS>(kx, cyv, czv, cx, hasy, hasx, ux, wx, fx, so[0], sn[0], has_sd, sd[0], c0, valid);
+        // y: next = z, prev = x, own = y
+        cascade<T, EXTRAS>(ky, czv, cx, cyv, hasz, hasy, uy, wy, fy, so[1], sn[1], has_sd, sd[1], c1, valid);
+        // z: next = x, prev = y, own = z
+        cascade<T, EXTRAS>(kz, cx, cyv, czv, hasx, hasz, uz, wz, fz, so[2], sn[2], has_sd, sd[2], c2, valid);
+        if (hasx) { st4(Wxp, wx); st4(Uzp, uz); }
+        if (hasy) { st4(Wyp, wy); st4(Uxp, ux); }
+        if (hasz) { st4(Wzp, wz); st4(Uyp, uy); }
+        if constexpr (EXTRAS) {
+          if (use_c) { st4(p.C[0] + mbase, c0); st4(p.C[1] + mbase, c1); st4(p.C[2] + mbase, c2); }
+          // ADE (Dispersive.jl:25-88): P^{n+1} from P^n, P^{n-1} and the new E; written over P^{n-1}
+          if constexpr (GROUP == 1) {
+#pragma unroll
+            for (int q = 0; q < MAXPOLE; ++q) {
+              if (q < p.npole && pol_on[q]) {
+                const PoleDesc<T>& pl = p.pole[q];
+                V4<T> sg = ld4(pl.sigma + mbase);
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
-                  V4<T> pc = ld4(p.pole[q].Pc[d] + mbase), pp = ld4(p.pole[q].Pp[d] + mbase);
+                  V4<T> pc = ld4(pl.Pc[d] + mbase), pp = ld4(pl.Pp[d] + mbase);
+                  const V4<T>& en = (d == 0) ? fx : (d == 1) ? fy : fz;
+                  V4<T> pn;
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) { sn[d][e] -= mi[d][e] * pc.v[e]; so[d][e] -= mi[d][e] * pp.v[e]; }
+                  for (int e = 0; e < 4; ++e) {
+                    T v = pl.g1i * ((pl.cp * pc.v[e] - pl.g1 * pp.v[e]) + pl.cd * sg.v[e] * en.v[e]);
+                    pn.v[e] = (sg.v[e] != T(0) && valid[e]) ? v : pc.v[e];
+                  }
+                  st4(pl.Pp[d] + mbase, pn);
                 }
-              }
-            }
-          }
-        }
-        // material conductivity
-        const bool has_sd = EXTRAS && (p.sigD[0] != nullptr);
-        T sd[3][4];
-#pragma unroll
-        for (int d = 0; d < 3; ++d)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) sd[d][e] = T(0);
-        if (has_sd) {
-#pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            V4<T> s4 = ld4(p.sigD[d] + mbase);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) sd[d][e] = T(0.5) * (dt * s4.v[e]);
-          }
-        }
-        // aux slab addresses for this plane
-        const long long xsl = hasx ? ((long long)p.cxp * p.n[1] * (long long)(iz - 1) + xs_off) : 0;
-        const long long ysl = hasy ? ((long long)p.mpx * p.cy * (long long)(iz - 1) + ys_off) : 0;
-        const long long zsl = hasz ? (p.mplane * (long long)p.slab[2].idx(iz) + mo) : 0;
-        T ax_[4], ay_[4], az_[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { ax_[e] = fx.v[e]; ay_[e] = fy.v[e]; az_[e] = fz.v[e]; }
-        // x: next = y, prev = z, own = x
-        cascade<T, EXTRAS>(kx, cyv, czv, cx, hasy, hasx, p.U[0] + ysl, p.W[0] + xsl, ax_, so[0], sn[0], has_sd, sd[0],
-                   p.C[0] ? p.C[0] + mbase : nullptr, valid);
-        // y: next = z, prev = x, own = y
-        cascade<T, EXTRAS>(ky, czv, cx, cyv, hasz, hasy, p.U[1] + zsl, p.W[1] + ysl, ay_, so[1], sn[1], has_sd, sd[1],
-                   p.C[1] ? p.C[1] + mbase : nullptr, valid);
-        // z: next = x, prev = y, own = z
-        cascade<T, EXTRAS>(kz, cx, cyv, czv, hasx, hasz, p.U[2] + xsl, p.W[2] + zsl, az_, so[2], sn[2], has_sd, sd[2],
-                   p.C[2] ? p.C[2] + mbase : nullptr, valid);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { fx.v[e] = ax_[e]; fy.v[e] = ay_[e]; fz.v[e] = az_[e]; }
-        // ADE (Dispersive.jl:25-88): P^{n+1} from P^n, P^{n-1} and the new E; written over P^{n-1}
-        if constexpr (GROUP == 1 && EXTRAS) {
-#pragma unroll
-          for (int q = 0; q < MAXPOLE; ++q) {
-            if (q < p.npole && pol_on[q]) {
-              const PoleDesc<T>& pl = p.pole[q];
-              V4<T> sg = ld4(pl.sigma + mbase);
-#pragma unroll
-              for (int d = 0; d < 3; ++d) {
-                V4<T> pc = ld4(pl.Pc[d] + mbase), pp = ld4(pl.Pp[d] + mbase);
-                const V4<T>& en = (d == 0) ? fx : (d == 1) ? fy : fz;
-                V4<T> pn;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  T v = pl.g1i * ((pl.cp * pc.v[e] - pl.g1 * pp.v[e]) + pl.cd * sg.v[e] * en.v[e]);
-                  pn.v[e] = (sg.v[e] != T(0) && valid[e]) ? v : pc.v[e];
-                }
-                st4(pl.Pp[d] + mbase, pn);
               }
             }
           }
