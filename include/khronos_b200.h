@@ -135,6 +135,8 @@ int32_t khr_monitor_read(khr_ctx* ctx, int32_t monitor_id, void* complex_out);
 int32_t khr_monitor_view(khr_ctx* ctx, int32_t monitor_id, void** dev_ptr, int64_t dims[4]);
 /* Simulation.jl:440-445 stop_when_dft_decayed: sqrt(sum |M|^2) of one monitor */
 int32_t khr_monitor_norm(khr_ctx* ctx, int32_t monitor_id, double* norm);
+/* all monitors at once (count = number registered); values are cached between DFT updates */
+int32_t khr_monitor_norms(khr_ctx* ctx, double* norms, int32_t count);
 
 int32_t khr_sync(khr_ctx* ctx);
 int32_t khr_get_stream(khr_ctx* ctx, void** cuda_stream);

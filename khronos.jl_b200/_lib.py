@@ -74,6 +74,7 @@ _SIGNATURES = {
     "khr_monitor_read": (_I, [_P, _I, _P]),
     "khr_monitor_view": (_I, [_P, _I, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "khr_monitor_norm": (_I, [_P, _I, C.POINTER(C.c_double)]),
+    "khr_monitor_norms": (_I, [_P, C.POINTER(C.c_double), _I]),
     "khr_sync": (_I, [_P]),
     "khr_get_stream": (_I, [_P, C.POINTER(_P)]),
     "khr_last_step_timing": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

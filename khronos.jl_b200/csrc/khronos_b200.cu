@@ -106,6 +106,7 @@ struct Base {
   virtual void monitor_read(int id, void* out) = 0;
   virtual void monitor_view(int id, void** p, int64_t* dims) = 0;
   virtual double monitor_norm(int id) = 0;
+  virtual void monitor_norms(double* out, int count) = 0;
   virtual void sync() = 0;
   virtual void census(int64_t* c) = 0;
   virtual void set_profiling(int on) = 0;
@@ -285,6 +286,7 @@ struct Impl : Base {
     cudaDeviceSynchronize();
     for (void* p : allocs) cudaFree(p);
     if (h_due) cudaFreeHost(h_due);
+    if (h_norms) cudaFreeHost(h_norms);
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     cudaEventDestroy(ev_boundary); cudaEventDestroy(ev_comm); cudaEventDestroy(ev_t0); cudaEventDestroy(ev_t1);
     cudaStreamDestroy(stream); cudaStreamDestroy(comm_stream);
@@ -913,6 +915,7 @@ struct Impl : Base {
       if (!m.local) continue;
       if (m.decimation > 1 && (timestep % m.decimation) != 0) continue;  // Kernels.jl:465-497
       h_due[group * monitors.size() + nd++] = (int)q;
+      if (!norm_stale.empty()) norm_stale[q] = 1;
       maxcells = std::max(maxcells, (long long)m.n[0] * m.n[1] * m.n[2]);
     }
     if (nd == 0) return;
@@ -962,6 +965,7 @@ struct Impl : Base {
       for (int q = 0; q < 2; ++q)
         for (int d = 0; d < 3; ++d) CUDA_OK(cudaMemsetAsync(p.P[q][d], 0, msize * sizeof(T), stream));
     for (auto& m : monitors) CUDA_OK(cudaMemsetAsync(m.M, 0, 2 * m.elems * sizeof(T), stream));
+    for (auto& c : norm_stale) c = 1;
     for (auto& s : sources) { s.ao_re = 0; s.ao_im = 0; }
     timestep = 0;
     sources_active = true;
@@ -1031,6 +1035,41 @@ struct Impl : Base {
     Monitor& m = monitors[id];
     *p = m.M;
     dims[0] = m.n[0]; dims[1] = m.n[1]; dims[2] = m.n[2]; dims[3] = (int64_t)m.freqs.size();
+  }
+  // Simulation.jl:440-445 stop_when_dft_decayed evaluates every monitor's norm on every step;
+  // the accumulators only change on a DFT update, so the values are cached in between and
+  // all stale ones are reduced by one launch + one small device->host copy.
+  std::vector<double> norm_cache;
+  std::vector<char> norm_stale;
+  double* d_norms = nullptr;
+  double* h_norms = nullptr;
+  void monitor_norms(double* out, int count) override {
+    int n = (int)monitors.size();
+    if (count != n) throw std::string("khr_monitor_norms: count must equal the number of monitors");
+    if (n == 0) return;
+    if (!d_norms) {
+      d_norms = (double*)dalloc((sizeof(double) * (n + 1) + sizeof(T) - 1) / sizeof(T));
+      CUDA_OK(cudaMallocHost((void**)&h_norms, sizeof(double) * n));
+      norm_cache.assign(n, 0.0);
+      norm_stale.assign(n, 1);
+    }
+    bool any = false;
+    for (int q = 0; q < n; ++q) any |= norm_stale[q] != 0;
+    if (any) {
+      CUDA_OK(cudaMemsetAsync(d_norms, 0, sizeof(double) * n, stream));
+      for (int q = 0; q < n; ++q) {
+        if (!norm_stale[q]) continue;
+        long long ne = 2 * (long long)monitors[q].elems;
+        int blocks = (int)std::min<long long>((ne + 255) / 256, 148 * 4);
+        if (blocks > 0) { sumsq_kernel<T><<<blocks, 256, 0, stream>>>(monitors[q].M, ne, d_norms + q); ++launches; }
+      }
+      CUDA_OK(cudaGetLastError());
+      CUDA_OK(cudaMemcpyAsync(h_norms, d_norms, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
+      CUDA_OK(cudaStreamSynchronize(stream));
+      for (int q = 0; q < n; ++q)
+        if (norm_stale[q]) { norm_cache[q] = std::sqrt(h_norms[q]); norm_stale[q] = 0; }
+    }
+    for (int q = 0; q < n; ++q) out[q] = norm_cache[q];
   }
   double* d_norm = nullptr;
   double monitor_norm(int id) override {
@@ -1240,6 +1279,10 @@ int32_t khr_monitor_view(khr_ctx* ctx, int32_t monitor_id, void** dev_ptr, int64
 int32_t khr_monitor_norm(khr_ctx* ctx, int32_t monitor_id, double* norm) {
   NEED_CTX
   KHR_TRY(*norm = ctx->impl->monitor_norm(monitor_id))
+}
+int32_t khr_monitor_norms(khr_ctx* ctx, double* norms, int32_t count) {
+  NEED_CTX
+  KHR_TRY(ctx->impl->monitor_norms(norms, count))
 }
 int32_t khr_sync(khr_ctx* ctx) {
   NEED_CTX

@@ -640,12 +640,13 @@ class Simulation:
         _lib.check(_lib.lib().khr_field_write(self.ctx, comp, a.ctypes.data))
 
     def get_dft(self, monitor):
-        """Array(md.fields): complex (nx,ny,nz,nf) (FluxMonitor.jl:99-102)."""
+        """Array(md.fields): complex (nx,ny,nz,nf) (FluxMonitor.jl:99-102), Complex{T}, zero-copy view
+        of the buffer the device->host copy filled."""
         n = [monitor.end[a] - monitor.start[a] + 1 for a in range(3)] + [len(monitor.frequencies)]
-        raw = np.empty(tuple(n[::-1]) + (2,), dtype=self.T)
+        ct = np.complex64 if self.T is np.float32 else np.complex128
+        raw = np.empty(tuple(n[::-1]), dtype=ct)  # memory order: (re,im) pairs, x fastest, f slowest
         _lib.check(_lib.lib().khr_monitor_read(self.ctx, monitor.id, raw.ctypes.data))
-        cplx = raw[..., 0] + 1j * raw[..., 1]
-        return np.transpose(cplx, (3, 2, 1, 0))
+        return raw.transpose(3, 2, 1, 0)
 
     def get_flux(self, fm, dft=None):
         """FluxMonitor.jl:92-156 get_flux: Σ Re(E1·conj(H2) − E2·conj(H1))·dA per frequency.
@@ -697,6 +698,13 @@ class Simulation:
         v = C.c_double()
         _lib.check(_lib.lib().khr_monitor_norm(self.ctx, monitor.id, C.byref(v)))
         return v.value
+
+    def monitor_norms(self):
+        """dft_fields_norm of every DFT monitor (Simulation.jl:528-539), one call."""
+        n = len(self.dft_monitors)
+        out = (C.c_double * n)()
+        _lib.check(_lib.lib().khr_monitor_norms(self.ctx, out, n))
+        return list(out)
 
     def voxel_census(self):
         c = (C.c_int64 * 4)()
