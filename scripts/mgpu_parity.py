@@ -1,0 +1,61 @@
+"""Multi-GPU parity: N ranks (torchrun, one per GPU, z slabs + NCCL halo exchange) against the
+single-domain CPU oracle on rank 0.   torchrun --nproc-per-node N scripts/mgpu_parity.py"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import khronos_b200 as kb
+from khronos_b200 import distributed as kd
+
+
+def main():
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    cid = kd.broadcast_unique_id(rank)
+    rng = np.random.default_rng(1234)
+    N = (44, 40, 96)
+    eps = [(1.0 / rng.uniform(1.0, 4.0, N)).astype(np.float32) for _ in range(3)]
+    sg = np.zeros(N, dtype=np.float32)
+    sg[:, :, 40:56] = 1.5          # a Drude slab that straddles the rank boundary for 2 ranks
+    srcs = [kb.UniformSource(kb.ContinuousWaveSource(1.0), kb.EZ, [0, 0, 0.05], [0, 0, 0]),
+            kb.UniformSource(kb.ContinuousWaveSource(1.2), kb.HY, [0.3, 0, -1.0], [1.0, 1.0, 0])]
+    mons = [kb.DFTMonitor(kb.EX, [0, 0, 0], [0, 3, 9.6], [1.0, 1.2], 2), kb.DFTMonitor(kb.HZ, [0, 0.2, 1.0], [3, 0, 6.0], [1.0], 1)]
+    kw = dict(boundaries=[[1.0, 1.0]] * 3, monitors=mons, eps_inv=eps, poles=[(0.0, 0.3, sg)])
+    sim = kb.Simulation([4.4, 4.0, 9.6], [0, 0, 0], 10, srcs, rank=rank, nranks=world, device=lr, **kw)
+    sim.prepare_simulation(comm_id=cid)
+    nsteps = 120
+    sim.step(nsteps)
+    sim.sync()
+    fields = [kd.gather_fields(sim, c) for c in range(6)]
+    dfts = [kd.reduce_dft(sim, m) for m in sim.dft_monitors]
+    ok = True
+    if rank == 0:
+        from bridge import oracle_from_simulation
+        whole = kb.Simulation([4.4, 4.0, 9.6], [0, 0, 0], 10, srcs, **kw)
+        o, mids = oracle_from_simulation(whole)
+        o.step(nsteps)
+        num = den = 0.0
+        for c in range(6):
+            b = o.get_field(c)
+            num += ((fields[c].astype(np.float64) - b) ** 2).sum()
+            den += (b ** 2).sum()
+        err = (num / den) ** 0.5
+        derr = [float(np.linalg.norm(a - o.get_dft(m)) / np.linalg.norm(o.get_dft(m))) for a, m in zip(dfts, mids)]
+        print("mgpu parity world=%d slabs=%s: field rel-L2 %.3e, DFT rel-L2 %s" % (world, sim.slabs, err, derr))
+        ok = err < 1e-5 and max(derr) < 1e-5
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.barrier()
+    dist.destroy_process_group()
+    if not flag.item():
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()
