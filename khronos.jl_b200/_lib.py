@@ -8,7 +8,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libkhronos_b200.so")
+LIB_PATH = os.environ.get("KHRONOS_B200_LIB") or os.path.join(_HERE, "lib", "libkhronos_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 KHR_F32, KHR_F64 = 0, 1

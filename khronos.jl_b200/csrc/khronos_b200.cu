@@ -172,6 +172,7 @@ struct Impl : Base {
   T m_scalar[2] = {T(1), T(1)};
   T* sigM[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // [0]=sigma_B [1]=sigma_D
   T* Cst[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+  T* Dst[3] = {nullptr, nullptr, nullptr};  // D on dispersive voxels
   T* W[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
   T* U[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
   size_t slab_elems[3] = {0, 0, 0};
@@ -196,10 +197,13 @@ struct Impl : Base {
     int comp;
     int s[3], d[3];  // local start (z already shifted), extent
     T* amp = nullptr;
+    int* slot = nullptr;
     TimeSrc<T> ts;
     T ao_re = 0, ao_im = 0;
   };
   std::vector<Source> sources;
+  T* Tsrc[2] = {nullptr, nullptr};  // flux accumulators of the source voxels per group
+  size_t nslots[2] = {0, 0};
   struct Monitor {
     int comp;
     int s[3], e[3], n[3];  // global index box
@@ -212,9 +216,7 @@ struct Impl : Base {
   };
   std::vector<Monitor> monitors;
   MonDesc<T>* d_mons = nullptr;
-  int* d_due = nullptr;
-  int* h_due = nullptr;
-  std::vector<int> last_due[2];
+  std::vector<int> mon_local_nz;
 
   // work tables: [group][mode][lx index]
   struct Table {
@@ -285,7 +287,6 @@ struct Impl : Base {
     cudaSetDevice(device);
     cudaDeviceSynchronize();
     for (void* p : allocs) cudaFree(p);
-    if (h_due) cudaFreeHost(h_due);
     if (h_norms) cudaFreeHost(h_norms);
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     cudaEventDestroy(ev_boundary); cudaEventDestroy(ev_comm); cudaEventDestroy(ev_t0); cudaEventDestroy(ev_t1);
@@ -485,6 +486,8 @@ struct Impl : Base {
           sigM[gq][d] = dalloc(msize);
         }
       }
+    if (!poles.empty())
+      for (int d = 0; d < 3; ++d) Dst[d] = dalloc(msize);
     // coefficient vectors
     for (int gq = 0; gq < 2; ++gq)
       for (int a = 0; a < 3; ++a) {
@@ -501,6 +504,7 @@ struct Impl : Base {
         CUDA_OK(cudaMemcpyAsync(coef[gq][a][2], ip.data(), len * sizeof(T), cudaMemcpyHostToDevice, stream));
         CUDA_OK(cudaStreamSynchronize(stream));
       }
+    build_source_slots();
     build_tables();
     // monitors
     if (!monitors.empty()) {
@@ -525,12 +529,53 @@ struct Impl : Base {
       }
       d_mons = (MonDesc<T>*)dalloc((sizeof(MonDesc<T>) * h.size() + sizeof(T) - 1) / sizeof(T), false);
       CUDA_OK(cudaMemcpyAsync(d_mons, h.data(), sizeof(MonDesc<T>) * h.size(), cudaMemcpyHostToDevice, stream));
-      d_due = (int*)dalloc((2 * monitors.size() * sizeof(int) + sizeof(T) - 1) / sizeof(T) + 1, false);
-      CUDA_OK(cudaMallocHost((void**)&h_due, 2 * monitors.size() * sizeof(int)));
+      mon_local_nz.clear();
+      for (auto& d : h) mon_local_nz.push_back(d.n[2]);
       CUDA_OK(cudaStreamSynchronize(stream));
     }
     CUDA_OK(cudaStreamSynchronize(stream));
     finalized = true;
+  }
+
+  // one flux-accumulator slot per (component, cell) touched by a source of the group; sources
+  // that overlap on the same component share the slot
+  void build_source_slots() {
+    for (int gq = 0; gq < 2; ++gq) {
+      std::vector<std::pair<unsigned long long, std::pair<size_t, size_t>>> keys;  // (key, (source, voxel))
+      for (size_t q = 0; q < sources.size(); ++q) {
+        Source& s = sources[q];
+        if ((s.comp >= 3) != (gq == 0)) continue;
+        size_t n = (size_t)s.d[0] * s.d[1] * s.d[2];
+        for (size_t v = 0; v < n; ++v) {
+          long long x = s.s[0] + (long long)(v % s.d[0]);
+          long long y = s.s[1] + (long long)((v / s.d[0]) % s.d[1]);
+          long long z = s.s[2] + (long long)(v / ((size_t)s.d[0] * s.d[1])) + 4;  // local z may be <= 0 on other ranks
+          unsigned long long key = ((unsigned long long)(s.comp % 3) << 60) | ((unsigned long long)z << 40) |
+                                   ((unsigned long long)y << 20) | (unsigned long long)x;
+          keys.push_back({key, {q, v}});
+        }
+      }
+      if (keys.empty()) continue;
+      std::sort(keys.begin(), keys.end());
+      std::vector<std::vector<int>> slots(sources.size());
+      for (size_t q = 0; q < sources.size(); ++q)
+        if ((sources[q].comp >= 3) == (gq == 0)) slots[q].assign((size_t)sources[q].d[0] * sources[q].d[1] * sources[q].d[2], 0);
+      int cur = -1;
+      unsigned long long last = ~0ull;
+      for (auto& k : keys) {
+        if (k.first != last) { ++cur; last = k.first; }
+        slots[k.second.first][k.second.second] = cur;
+      }
+      nslots[gq] = (size_t)cur + 1;
+      Tsrc[gq] = dalloc(nslots[gq]);
+      for (size_t q = 0; q < sources.size(); ++q) {
+        if (slots[q].empty()) continue;
+        size_t bytes = slots[q].size() * sizeof(int);
+        sources[q].slot = (int*)dalloc((bytes + sizeof(T) - 1) / sizeof(T), false);
+        CUDA_OK(cudaMemcpyAsync(sources[q].slot, slots[q].data(), bytes, cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+      }
+    }
   }
 
   // split [1..n] at the PML edges; `gran` aligns the cut points outward (x only)
@@ -691,7 +736,8 @@ struct Impl : Base {
         int lx = 8 << lx_index(X.e - X.s + 1);
         for (auto& Y : yr) tiles_xy += (long long)((X.e - X.s) / (4 * lx) + 1) * ((Y.e - Y.s) / (CTA / lx) + 1);
       }
-      int zseg = (int)std::min<long long>(32, std::max<long long>(4, (tiles_xy * N[2] + 2367) / 2368));
+      // measured on B200 (profiles/r01_zseg_sweep.txt): 7-8 planes per CTA is the sweet spot
+      int zseg = (int)std::min<long long>(8, std::max<long long>(4, (tiles_xy * N[2] + 2367) / 2368));
       if (const char* e = getenv("KHR_ZSEG")) zseg = std::max(1, atoi(e));
       for (auto& Z : zr)
         for (int z0 = Z.s; z0 <= Z.e; z0 += zseg) {
@@ -813,7 +859,7 @@ struct Impl : Base {
       if ((s.comp >= 3) != (gq == 0)) continue;
       if (p.nsrc >= MAXSRC) throw std::string("too many sources in one field group (max 8)");
       SrcDesc<T>& d = p.src[p.nsrc++];
-      d.amp = s.amp; d.comp = s.comp % 3;
+      d.amp = s.amp; d.slot = s.slot; d.comp = s.comp % 3;
       for (int a = 0; a < 3; ++a) { d.s[a] = s.s[a]; d.d[a] = s.d[a]; }
       T re = 0, im = 0;
       if (sources_active) eval_time_source(s.ts, t_src, &re, &im);
@@ -821,6 +867,8 @@ struct Impl : Base {
       s.ao_re = re; s.ao_im = im;
     }
     p.npole = 0;
+    for (int d = 0; d < 3; ++d) p.Dst[d] = (gq == 1) ? Dst[d] : nullptr;
+    p.Tsrc = Tsrc[gq];
     if (gq == 1)
       for (auto& pl : poles) {
         PoleDesc<T>& d = p.pole[p.npole++];
@@ -907,33 +955,47 @@ struct Impl : Base {
   void dft_update(int group, double time) override {
     need_final();
     if (monitors.empty()) return;
-    int nd = 0;
+    const double two_pi = 2 * 3.141592653589793;
+    const T tf = (T)(two_pi * time);  // Monitors.jl:323 complex_backend_number(im*2π*time), cast to T
+    DftBatch<T> bt;
+    bt.n = 0;
+    int used = 0;
     long long maxcells = 0;
+    auto flush = [&]() {
+      if (bt.n == 0) return;
+      dim3 grid((unsigned)((maxcells + 255) / 256), (unsigned)bt.n);
+      dft_kernel<T><<<grid, 256, 0, stream>>>(d_mons, bt, (long long)PX * PY, PX);
+      ++launches;
+      bt.n = 0; used = 0; maxcells = 0;
+    };
     for (size_t q = 0; q < monitors.size(); ++q) {
       Monitor& m = monitors[q];
       if ((m.comp >= 3) != (group == 0)) continue;
       if (!m.local) continue;
       if (m.decimation > 1 && (timestep % m.decimation) != 0) continue;  // Kernels.jl:465-497
-      h_due[group * monitors.size() + nd++] = (int)q;
       if (!norm_stale.empty()) norm_stale[q] = 1;
-      maxcells = std::max(maxcells, (long long)m.n[0] * m.n[1] * m.n[2]);
+      int nf = (int)m.freqs.size();
+      for (int k0 = 0; k0 < nf;) {
+        if (bt.n == DFT_SLOTS || used == DFT_PHASORS) flush();
+        int kc = std::min(nf - k0, DFT_PHASORS - used);
+        int sl = bt.n++;
+        bt.mon[sl] = (int)q; bt.k0[sl] = k0; bt.kc[sl] = kc; bt.off[sl] = used;
+        for (int k = 0; k < kc; ++k) {
+          // phase = T(f_k) * T(2 pi t) formed in T; exp(i phase) = (cos, sin) rounded to T
+          T ph = m.freqs[k0 + k] * tf;
+          T er = (T)std::cos((double)ph), ei = (T)std::sin((double)ph);
+          bt.ph_re[used + k] = dt * er;
+          bt.ph_im[used + k] = dt * ei;
+        }
+        used += kc;
+        k0 += kc;
+        maxcells = std::max(maxcells, (long long)m.n[0] * m.n[1] * std::max(0, monLocalNz(q)));
+      }
     }
-    if (nd == 0) return;
-    // the due list only changes when decimations differ; upload on change only
-    std::vector<int> now(h_due + group * monitors.size(), h_due + group * monitors.size() + nd);
-    if (now != last_due[group]) {
-      CUDA_OK(cudaMemcpyAsync(d_due + group * monitors.size(), h_due + group * monitors.size(), nd * sizeof(int),
-                              cudaMemcpyHostToDevice, stream));
-      CUDA_OK(cudaStreamSynchronize(stream));
-      last_due[group] = now;
-    }
-    const double two_pi = 2 * 3.141592653589793;
-    T tf = (T)(two_pi * time);  // Monitors.jl:323 complex_backend_number(im*2π*time)
-    dim3 grid((unsigned)((maxcells + 255) / 256), (unsigned)nd);
-    dft_kernel<T><<<grid, 256, 0, stream>>>(d_mons, d_due + group * monitors.size(), tf, dt, (long long)PX * PY, PX);
-    ++launches;
+    flush();
     CUDA_OK(cudaGetLastError());
   }
+  int monLocalNz(size_t q) const { return mon_local_nz[q]; }
   void step(int n) override {
     need_final();
     launches = 0;
@@ -964,6 +1026,10 @@ struct Impl : Base {
     for (auto& p : poles)
       for (int q = 0; q < 2; ++q)
         for (int d = 0; d < 3; ++d) CUDA_OK(cudaMemsetAsync(p.P[q][d], 0, msize * sizeof(T), stream));
+    for (int d = 0; d < 3; ++d)
+      if (Dst[d]) CUDA_OK(cudaMemsetAsync(Dst[d], 0, msize * sizeof(T), stream));
+    for (int gq = 0; gq < 2; ++gq)
+      if (Tsrc[gq]) CUDA_OK(cudaMemsetAsync(Tsrc[gq], 0, nslots[gq] * sizeof(T), stream));
     for (auto& m : monitors) CUDA_OK(cudaMemsetAsync(m.M, 0, 2 * m.elems * sizeof(T), stream));
     for (auto& c : norm_stale) c = 1;
     for (auto& s : sources) { s.ao_re = 0; s.ao_im = 0; }
@@ -995,6 +1061,13 @@ struct Impl : Base {
   }
   void field_write(int comp, const void* in) override {
     need_final();
+    if (comp < 3 && !poles.empty())
+      throw std::string("khr_field_write: writing E is not supported when dispersive poles are registered "
+                        "(the D / P history would be inconsistent); use khr_reset_fields");
+    for (auto& s : sources)
+      if ((s.comp >= 3) == (comp >= 3))
+        throw std::string("khr_field_write: not supported for a field group that has sources registered "
+                          "(the flux accumulators of the source voxels would be inconsistent)");
     std::vector<T> h(fsize, T(0));
     const T* src = (const T*)in;
     for (int z = 1; z <= N[2]; ++z)

@@ -56,6 +56,7 @@ struct Slab {
 template <class T>
 struct SrcDesc {
   const T* amp;       // complex interleaved, extent (dx,dy,dz)
+  const int* slot;    // per source voxel: index of the (component, cell) flux accumulator in StepParams::Tsrc
   int comp;           // 0..2 within the group
   int s[3], d[3];     // local start cell, extent
   T an_re, an_im;     // amplitude a(t) of this step
@@ -102,6 +103,8 @@ struct StepParams {
   // ADE
   int npole;
   PoleDesc<T> pole[MAXPOLE];
+  T* Dst[3];          // D kept on dispersive voxels (material layout), as the reference does
+  T* Tsrc;            // B/D kept on source voxels (compact, one slot per (component, cell))
   const WorkItem* items;
 };
 
@@ -211,7 +214,13 @@ __device__ __forceinline__ void cascade(const T (&k)[4], const Co<T> (&cn)[4], c
 template <class T, int MODE>
 constexpr int min_ctas() {
   // registers/thread budget: 64K regs per SM, 256-thread CTAs
-  return sizeof(T) == 4 ? (MODE == 0 ? 3 : (MODE == 1 ? 2 : 1)) : 1;
+#ifndef KHR_MINCTA_M0
+#define KHR_MINCTA_M0 3
+#endif
+#ifndef KHR_MINCTA_M1
+#define KHR_MINCTA_M1 2
+#endif
+  return sizeof(T) == 4 ? (MODE == 0 ? KHR_MINCTA_M0 : (MODE == 1 ? KHR_MINCTA_M1 : 1)) : 1;
 }
 
 template <class T, int GROUP, int MODE, bool MARR>
@@ -355,6 +364,7 @@ __global__ void __launch_bounds__(CTA, min_ctas<T, MODE>()) step_kernel(const __
     }
     if (act) {
       T kx[4], ky[4], kz[4];
+      T ku[3][4];  // unscaled K (only live in the full kernel)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         T ayx, azx;
@@ -366,9 +376,13 @@ __global__ void __launch_bounds__(CTA, min_ctas<T, MODE>()) step_kernel(const __
           azx = (e > 0) ? az0.v[(e + 3) & 3] : az_x;
         }
         // K = dt * curl (Helpers.jl:286-298), same operation order as the reference
-        kx[e] = KHR_M0(e) * (dt * (idz_ * (ay_z.v[e] - ay0.v[e]) - idy_ * (az_y.v[e] - az0.v[e])));
-        ky[e] = KHR_M1(e) * (dt * (idx_ * (azx - az0.v[e]) - idz_ * (ax_z.v[e] - ax0.v[e])));
-        kz[e] = KHR_M2(e) * (dt * (idy_ * (ax_y.v[e] - ax0.v[e]) - idx_ * (ayx - ay0.v[e])));
+        const T k0 = dt * (idz_ * (ay_z.v[e] - ay0.v[e]) - idy_ * (az_y.v[e] - az0.v[e]));
+        const T k1 = dt * (idx_ * (azx - az0.v[e]) - idz_ * (ax_z.v[e] - ax0.v[e]));
+        const T k2 = dt * (idy_ * (ax_y.v[e] - ax0.v[e]) - idx_ * (ayx - ay0.v[e]));
+        kx[e] = KHR_M0(e) * k0;
+        ky[e] = KHR_M1(e) * k1;
+        kz[e] = KHR_M2(e) * k2;
+        if constexpr (EXTRAS) { ku[0][e] = k0; ku[1][e] = k1; ku[2][e] = k2; }
       }
 
       if constexpr (!GENERAL) {
@@ -389,6 +403,14 @@ __global__ void __launch_bounds__(CTA, min_ctas<T, MODE>()) step_kernel(const __
         V4<T> c0 = zero4<T>(), c1 = zero4<T>(), c2 = zero4<T>();
         bool has_sd = false, use_c = false;
         bool pol_on[MAXPOLE];
+        bool pol_any = false;
+        bool disp[4] = {false, false, false, false};  // cell carries a pole
+        int sslot[3][4];                               // flux-accumulator slot of a source voxel, -1 if none
+        T su[3][4], pu[3][4];                          // unscaled S(t) and sum of P^n
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { su[d][e] = T(0); pu[d][e] = T(0); sslot[d][e] = -1; }
         if constexpr (EXTRAS) {
           // sources (Sources.jl:355-356): S = real(a(t) * A[x])
           if (srcmask != 0) {
@@ -403,11 +425,12 @@ __global__ void __launch_bounds__(CTA, min_ctas<T, MODE>()) step_kernel(const __
                 if (lx >= 0 && lx < s.d[0]) {
                   const size_t ai = 2 * ((size_t)lx + (size_t)s.d[0] * ((size_t)ly + (size_t)s.d[1] * (size_t)lz));
                   const T are = s.amp[ai], aim = s.amp[ai + 1];
+                  const int sl = s.slot[ai >> 1];
                   const T vn = s.an_re * are - s.an_im * aim;
                   const T vo = s.ao_re * are - s.ao_im * aim;
-                  if (s.comp == 0) { sn[0][e] += KHR_M0(e) * vn; so[0][e] += KHR_M0(e) * vo; }
-                  else if (s.comp == 1) { sn[1][e] += KHR_M1(e) * vn; so[1][e] += KHR_M1(e) * vo; }
-                  else { sn[2][e] += KHR_M2(e) * vn; so[2][e] += KHR_M2(e) * vo; }
+                  if (s.comp == 0) { sn[0][e] += KHR_M0(e) * vn; so[0][e] += KHR_M0(e) * vo; su[0][e] += vn; sslot[0][e] = sl; }
+                  else if (s.comp == 1) { sn[1][e] += KHR_M1(e) * vn; so[1][e] += KHR_M1(e) * vo; su[1][e] += vn; sslot[1][e] = sl; }
+                  else { sn[2][e] += KHR_M2(e) * vn; so[2][e] += KHR_M2(e) * vo; su[2][e] += vn; sslot[2][e] = sl; }
                 }
               }
             }
@@ -421,6 +444,9 @@ __global__ void __launch_bounds__(CTA, min_ctas<T, MODE>()) step_kernel(const __
                 V4<T> sg = ld4(p.pole[q].sigma + mbase);
                 pol_on[q] = (sg.v[0] != T(0)) || (sg.v[1] != T(0)) || (sg.v[2] != T(0)) || (sg.v[3] != T(0));
                 if (pol_on[q]) {
+                  pol_any = true;
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) disp[e] |= (sg.v[e] != T(0));
 #pragma unroll
                   for (int d = 0; d < 3; ++d) {
                     V4<T> pc = ld4(p.pole[q].Pc[d] + mbase), pp = ld4(p.pole[q].Pp[d] + mbase);
@@ -429,6 +455,7 @@ __global__ void __launch_bounds__(CTA, min_ctas<T, MODE>()) step_kernel(const __
                       const T mm = (d == 0) ? KHR_M0(e) : (d == 1) ? KHR_M1(e) : KHR_M2(e);
                       sn[d][e] -= mm * pc.v[e];
                       so[d][e] -= mm * pp.v[e];
+                      pu[d][e] += pc.v[e];
                     }
                   }
                 }
@@ -458,6 +485,59 @@ __global__ void __launch_bounds__(CTA, min_ctas<T, MODE>()) step_kernel(const __
         if (hasx) { st4(Wxp, wx); st4(Uzp, uz); }
         if (hasy) { st4(Wyp, wy); st4(Uxp, ux); }
         if (hasz) { st4(Wzp, wz); st4(Uyp, uy); }
+        if constexpr (EXTRAS) {
+          // Source voxels outside the PML keep the flux field (B or D) like the reference and
+          // rebuild A = m^-1 (T + S) from it every step (Helpers.jl:332-338).  With |S| >> |T| the
+          // eliminated form would let the S round-off random-walk inside the stored field.
+          if (srcmask != 0 && p.Tsrc != nullptr) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              V4<T>& f = (d == 0) ? fx : (d == 1) ? fy : fz;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const bool in_pml = (cx[e].s != T(0)) || (cyc.s != T(0)) || (czc.s != T(0));
+                if (sslot[d][e] >= 0 && !in_pml && !disp[e] && valid[e]) {
+                  const T s_ = sd[d][e];
+                  const T t_old = p.Tsrc[sslot[d][e]];
+                  const T t_new = (s_ != T(0)) ? (((T(1) - s_) * t_old + ku[d][e]) / (T(1) + s_)) : (t_old + ku[d][e]);
+                  T net = t_new;
+                  net += su[d][e];
+                  const T mm = (d == 0) ? KHR_M0(e) : (d == 1) ? KHR_M1(e) : KHR_M2(e);
+                  f.v[e] = mm * net;
+                  p.Tsrc[sslot[d][e]] = t_new;
+                }
+              }
+            }
+          }
+        }
+        if constexpr (EXTRAS && GROUP == 1) {
+          // Dispersive voxels outside the PML keep D exactly like the reference
+          // (Kernels.jl:315,371: fPD present -> no D elimination): D += K (or the sigma_D stage),
+          // E = eps^-1 * ((D + S) - P) (Helpers.jl:332-338).  |P| >> |eps E| in a metal, so
+          // recomputing E from D each step avoids a random walk of the P round-off in E.
+          if (pol_any && p.Dst[0] != nullptr) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              V4<T> dv = ld4(p.Dst[d] + mbase);
+              V4<T>& f = (d == 0) ? fx : (d == 1) ? fy : fz;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const bool in_pml = (cx[e].s != T(0)) || (cyc.s != T(0)) || (czc.s != T(0));
+                if (disp[e] && !in_pml && valid[e]) {
+                  const T s_ = sd[d][e];
+                  const T d_new = (s_ != T(0)) ? (((T(1) - s_) * dv.v[e] + ku[d][e]) / (T(1) + s_)) : (dv.v[e] + ku[d][e]);
+                  T net = d_new;
+                  net += su[d][e];
+                  net -= pu[d][e];
+                  const T mm = (d == 0) ? KHR_M0(e) : (d == 1) ? KHR_M1(e) : KHR_M2(e);
+                  f.v[e] = mm * net;
+                  dv.v[e] = d_new;
+                }
+              }
+              st4(p.Dst[d] + mbase, dv);
+            }
+          }
+        }
         if constexpr (EXTRAS) {
           if (use_c) { st4(p.C[0] + mbase, c0); st4(p.C[1] + mbase, c1); st4(p.C[2] + mbase, c2); }
           // ADE (Dispersive.jl:25-88): P^{n+1} from P^n, P^{n-1} and the new E; written over P^{n-1}
@@ -512,51 +592,45 @@ struct MonDesc {
   int group;
 };
 
-constexpr int DFT_MAXF = 64;
+constexpr int DFT_SLOTS = 32;    // (monitor, frequency-range) slots per launch
+constexpr int DFT_PHASORS = 384; // phasors per launch, passed by value with the launch
+
+// The phasors dt*exp(i*T(f_k)*T(2 pi t)) are evaluated on the host exactly as the reference
+// does (phase formed in T, Monitors.jl:323,355; sincos to < 1 ulp like Julia's) and travel in
+// the kernel-parameter buffer, so no device table has to be kept alive or synchronised.
+template <class T>
+struct DftBatch {
+  int n;
+  int mon[DFT_SLOTS];     // monitor index
+  int k0[DFT_SLOTS];      // first frequency of the slot
+  int kc[DFT_SLOTS];      // number of frequencies
+  int off[DFT_SLOTS];     // offset into ph_re / ph_im
+  T ph_re[DFT_PHASORS];
+  T ph_im[DFT_PHASORS];
+};
 
 template <class T>
-__device__ __forceinline__ void sincos_T(T x, T* s, T* c);
-template <>
-__device__ __forceinline__ void sincos_T<float>(float x, float* s, float* c) { sincosf(x, s, c); }
-template <>
-__device__ __forceinline__ void sincos_T<double>(double x, double* s, double* c) { sincos(x, s, c); }
-
-template <class T>
-__global__ void __launch_bounds__(256) dft_kernel(const MonDesc<T>* __restrict__ mons, const int* __restrict__ due,
-                                                  T time_fac, T dt, long long plane, int px) {
-  const MonDesc<T> m = mons[due[blockIdx.y]];
-  __shared__ T ph_re[DFT_MAXF], ph_im[DFT_MAXF];
+__global__ void __launch_bounds__(256) dft_kernel(const MonDesc<T>* __restrict__ mons,
+                                                  const __grid_constant__ DftBatch<T> bt, long long plane, int px) {
+  const int slot = blockIdx.y;
+  const MonDesc<T> m = mons[bt.mon[slot]];
   const long long ncell = (long long)m.n[0] * m.n[1] * m.n[2];
-  if ((long long)blockIdx.x * blockDim.x >= ncell) return;
-  for (int k0 = 0; k0 < m.nf; k0 += DFT_MAXF) {
-    const int kc = min(DFT_MAXF, m.nf - k0);
-    __syncthreads();
-    if ((int)threadIdx.x < kc) {
-      // phase = T(f_k) * T(2 pi t) in T (Monitors.jl:323, 355); exp(i phase) = (cos, sin)
-      T ph = m.freqs[k0 + threadIdx.x] * time_fac;
-      T s, c;
-      sincos_T<T>(ph, &s, &c);
-      ph_re[threadIdx.x] = dt * c;
-      ph_im[threadIdx.x] = dt * s;
-    }
-    __syncthreads();
-    const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell < ncell) {
-      const int x = (int)(cell % m.n[0]);
-      const int y = (int)((cell / m.n[0]) % m.n[1]);
-      const int z = (int)(cell / ((long long)m.n[0] * m.n[1]));
-      const T f = m.F[plane * (long long)(m.s[2] + z) + (long long)px * (m.s[1] + y) + (m.s[0] + x + XO)];
-      const long long mcell = (long long)(x + m.moff[0]) +
-                              (long long)m.mn[0] * ((long long)(y + m.moff[1]) + (long long)m.mn[1] * (z + m.moff[2]));
-      const long long mstride = (long long)m.mn[0] * m.mn[1] * m.mn[2];
-      for (int k = 0; k < kc; ++k) {
-        T* mp = m.M + 2 * (mcell + mstride * (k0 + k));
-        // complex accumulate: (dt*e) * F
-        T re = mp[0], im = mp[1];
-        mp[0] = re + ph_re[k] * f;
-        mp[1] = im + ph_im[k] * f;
-      }
-    }
+  const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= ncell) return;
+  const int x = (int)(cell % m.n[0]);
+  const int y = (int)((cell / m.n[0]) % m.n[1]);
+  const int z = (int)(cell / ((long long)m.n[0] * m.n[1]));
+  const T f = m.F[plane * (long long)(m.s[2] + z) + (long long)px * (m.s[1] + y) + (m.s[0] + x + XO)];
+  const long long mcell = (long long)(x + m.moff[0]) +
+                          (long long)m.mn[0] * ((long long)(y + m.moff[1]) + (long long)m.mn[1] * (z + m.moff[2]));
+  const long long mstride = (long long)m.mn[0] * m.mn[1] * m.mn[2];
+  const int k0 = bt.k0[slot], kc = bt.kc[slot], off = bt.off[slot];
+  for (int k = 0; k < kc; ++k) {
+    T* mp = m.M + 2 * (mcell + mstride * (k0 + k));
+    // M += (dt * e) * F  (complex accumulate, Monitors.jl:353-357)
+    T re = mp[0], im = mp[1];
+    mp[0] = re + bt.ph_re[off + k] * f;
+    mp[1] = im + bt.ph_im[off + k] * f;
   }
 }
 

@@ -1,0 +1,139 @@
+"""The named benchmark configurations (SURVEY.md §8d / BASELINE.json configs) on the GPU:
+(a) at reduced resolution against the CPU oracle, (b) at full size through size-independent
+properties (exact linearity in the source amplitude, mirror symmetry, zero-in/zero-out)."""
+import numpy as np
+import pytest
+
+import khronos_b200 as kb
+from khronos_b200 import workloads as w
+from bridge import oracle_from_simulation
+from common import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _against_oracle(desc, nsteps, dtype=np.float32, tol=1e-5):
+    sim = w.build_simulation(desc, dtype)
+    o, mids = oracle_from_simulation(sim)
+    sim.prepare_simulation()
+    sim.step(nsteps)
+    sim.sync()
+    o.step(nsteps)
+    num = den = 0.0
+    for c in range(6):
+        a, b = sim.get_field(c).astype(np.float64), o.get_field(c)
+        num += ((a - b) ** 2).sum()
+        den += (b ** 2).sum()
+    assert den > 0
+    err = (num / den) ** 0.5
+    assert err < tol, err
+    # DFT parity: jointly over the monitors of each field group, and per monitor for every
+    # monitor that carries signal (components that vanish by symmetry hold only round-off
+    # in both implementations, so their own norm is not a meaningful denominator)
+    stats = []
+    for m, mid in zip(sim.dft_monitors, mids):
+        a, b = sim.get_dft(m), o.get_dft(mid)
+        stats.append((m.component >= 3, float(np.sum(np.abs(a - b) ** 2)), float(np.sum(np.abs(b) ** 2)), b.size))
+    for grp in (False, True):
+        sel = [s for s in stats if s[0] == grp]
+        if not sel or sum(s[2] for s in sel) == 0:
+            continue
+        joint = (sum(s[1] for s in sel) / sum(s[2] for s in sel)) ** 0.5
+        assert joint < tol, (grp, joint)
+        ref_density = max(s[2] / s[3] for s in sel)
+        for s in sel:
+            # single monitors in weak-field regions sit closer to the round-off floor
+            if s[2] / s[3] > 1e-4 * ref_density:
+                assert (s[1] / s[2]) ** 0.5 < 3 * tol, (grp, (s[1] / s[2]) ** 0.5, s)
+    return sim, o, mids
+
+
+def test_waveguide_mode_reduced():
+    """configs[1] at res 10 (120x60x33): per-voxel eps, 4-component plane source, 12 DFT monitors."""
+    sim, o, mids = _against_oracle(w.waveguide_mode(res=10), 130)
+    fm = sim.monitors[0]
+    ids = [mids[sim.dft_monitors.index(m)] for m in fm.monitors]
+    f_gpu, f_cpu = sim.get_flux(fm), o.flux(fm.normal, ids)
+    assert rel_l2(f_gpu, f_cpu) < 1e-5, (f_gpu, f_cpu)
+
+
+def test_sphere_reduced():
+    """sphere.jl at res 8 (64^3): eps=3 ball, two infinite plane sources, 24 DFT planes x 5 freqs."""
+    _against_oracle(w.sphere(res=8, nfreq=5), 100)
+
+
+def test_uled_reduced_drude_lorentz():
+    """uled.jl at res 12 (84x84x30): layered stack, Ag Drude + Lorentz poles, 20 DFT planes."""
+    _against_oracle(w.uled(res=12), 100)
+
+
+def test_uled_float64_long():
+    """Same stack in Float64 over 150 steps at the 1e-12 bound.  (In Float32 the weak far-field
+    monitors of this configuration sit on the round-off floor: the oracle's own two evaluation
+    orders — single chunk vs chunked cascade — differ by up to 4e-5 there after 150 steps, see
+    DESIGN.md §2; the Float32 case above therefore stops at 100 steps.)"""
+    _against_oracle(w.uled(res=12), 150, dtype=np.float64, tol=1e-12)
+
+
+def test_metalens_reduced():
+    """metalens.jl shape at 96x96x64: substrate + pillars, 4 plane sources, Courant 0.55."""
+    _against_oracle(w.metalens(nx=96, ny=96, nz=64, res=16, pml_cells=10, pillars=3), 120)
+
+
+def test_dipole_float64_reduced():
+    _against_oracle(w.dipole(40), 60, dtype=np.float64, tol=1e-12)
+
+
+# ------------------------------------------------------------------ full-size properties
+def _run(desc, nsteps, amp=1.0):
+    for s in desc["sources"]:
+        s.amplitude = s.amplitude * amp
+    sim = w.build_simulation(desc, np.float32)
+    sim.prepare_simulation()
+    sim.step(nsteps)
+    sim.sync()
+    return sim
+
+
+def test_waveguide_full_size_linearity_exact():
+    """480x240x132: doubling the source amplitude doubles every field value *bit-exactly*
+    (power-of-two scaling commutes with every IEEE operation of the update)."""
+    s1 = _run(w.waveguide_mode(), 40, 1.0)
+    f1 = [s1.get_field(c) for c in range(6)]
+    d1 = s1.get_dft(s1.dft_monitors[0])
+    s1.close()
+    s2 = _run(w.waveguide_mode(), 40, 2.0)
+    for c in range(6):
+        f2 = s2.get_field(c)
+        assert np.abs(f1[c]).max() > 0
+        # exact, except at the leading wave front where intermediates are sub-normal (sub-normal
+        # rounding is not scale invariant and can flip the last bit of a ~1e-28 value)
+        assert np.max(np.abs(f2 - 2.0 * f1[c])) < 1e-30, c
+        big = np.abs(f1[c]) > 1e-20
+        assert big.sum() > 1000
+        assert np.array_equal(f2[big], 2.0 * f1[c][big]), c
+    d2 = s2.get_dft(s2.dft_monitors[0])
+    assert np.max(np.abs(d2 - 2.0 * d1)) < 1e-30
+
+
+def test_dipole_320_mirror_symmetry_and_zero():
+    """320^3 vacuum dipole: Ez is mirror symmetric about the source planes; without a source
+    every field stays exactly zero."""
+    s = _run(w.dipole(320), 60)
+    ez = s.get_field(kb.EZ)
+    assert np.abs(ez).max() > 0
+    st, en = s.grid.grid_volume([0, 0, 0], [0, 0, 0], kb.EZ)
+    # the Ez point source sits on cells (st..en) = 2 cells along z, 1 along x,y (f32 index maps give 2x2x2)
+    # in Float32 the point lands 6e-7 of a cell below grid line `en`, so the weight sits on en (0-based en-1)
+    c0 = en[0] - 1
+    a = ez[c0 - 60:c0 + 61, :, :]
+    assert np.allclose(a, a[::-1, :, :], rtol=0, atol=2e-5 * np.abs(ez).max())
+    c1 = en[1] - 1
+    b = ez[:, c1 - 60:c1 + 61, :]
+    assert np.allclose(b, b[:, ::-1, :], rtol=0, atol=2e-5 * np.abs(ez).max())
+    s.close()
+    d = w.dipole(160)
+    for src in d["sources"]:
+        src.amplitude = 0.0
+    z = _run(d, 20)
+    assert all(not np.any(z.get_field(c)) for c in range(6))
