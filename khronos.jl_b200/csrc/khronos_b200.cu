@@ -739,6 +739,8 @@ struct Impl : Base {
       // measured on B200 (profiles/r01_zseg_sweep.txt): 7-8 planes per CTA is the sweet spot
       int zseg = (int)std::min<long long>(8, std::max<long long>(4, (tiles_xy * N[2] + 2367) / 2368));
       if (const char* e = getenv("KHR_ZSEG")) zseg = std::max(1, atoi(e));
+      int zseg_full = 2;
+      if (const char* e = getenv("KHR_ZSEG_FULL")) zseg_full = std::max(1, atoi(e));
       for (auto& Z : zr)
         for (int z0 = Z.s; z0 <= Z.e; z0 += zseg) {
           int zn = std::min(zseg, Z.e - z0 + 1);
@@ -751,23 +753,34 @@ struct Impl : Base {
                 int yh = std::min(th, Y.e - y0 + 1);
                 for (int x0 = X.s; x0 <= X.e; x0 += tw) {
                   int xw = std::min(tw, X.e - x0 + 1);
-                  WorkItem it{x0, xw, y0, yh, z0, zn, 0, 3 + lxi};
-                  bool extras = false;
-                  for (auto& bx : boxes)
-                    if (boxes_hit(bx.b, x0, x0 + xw - 1, y0, y0 + yh - 1, z0, z0 + zn - 1)) {
-                      extras = true;
-                      if (bx.src) it.flags |= 1;
+                  // Tiles that touch a source / conductivity / pole box run the heavy MODE 2 kernel
+                  // (1 CTA per SM): they are cut into short z pieces so that a thin box still
+                  // spreads over all SMs and does not become the critical path of the half-step.
+                  auto emit = [&](int zs, int zc) {
+                    WorkItem it{x0, xw, y0, yh, zs, zc, 0, 3 + lxi};
+                    bool extras = false;
+                    for (auto& bx : boxes)
+                      if (boxes_hit(bx.b, x0, x0 + xw - 1, y0, y0 + yh - 1, zs, zs + zc - 1)) {
+                        extras = true;
+                        if (bx.src) it.flags |= 1;
+                      }
+                    int mode = extras ? 2 : ((X.pml || Y.pml || Z.pml) ? 1 : 0);
+                    int phase = 1;
+                    if (g.nranks > 1) {
+                      if (gq == 0 && g.rank < g.nranks - 1 && zs + zc - 1 == N[2]) phase = 0;
+                      if (gq == 1 && g.rank > 0 && zs == 1) phase = 0;
                     }
-                  int mode = extras ? 2 : ((X.pml || Y.pml || Z.pml) ? 1 : 0);
-                  int phase = 1;
-                  if (g.nranks > 1) {
-                    if (gq == 0 && g.rank < g.nranks - 1 && z0 + zn - 1 == N[2]) phase = 0;
-                    if (gq == 1 && g.rank > 0 && z0 == 1) phase = 0;
-                  }
-                  Table& tt = tab[gq][phase][mode];
-                  tt.items.push_back(it);
-                  tt.cells += (int64_t)xw * yh * zn;
-                  tt.alg_bytes += item_alg_bytes(gq, pmlc, x0, xw, y0, yh, z0, zn);
+                    Table& tt = tab[gq][phase][mode];
+                    tt.items.push_back(it);
+                    tt.cells += (int64_t)xw * yh * zc;
+                    tt.alg_bytes += item_alg_bytes(gq, pmlc, x0, xw, y0, yh, zs, zc);
+                  };
+                  bool any_box = false;
+                  for (auto& bx : boxes)
+                    if (boxes_hit(bx.b, x0, x0 + xw - 1, y0, y0 + yh - 1, z0, z0 + zn - 1)) any_box = true;
+                  if (!any_box) emit(z0, zn);
+                  else
+                    for (int zs = z0; zs < z0 + zn; zs += zseg_full) emit(zs, std::min(zseg_full, z0 + zn - zs));
                 }
               }
             }

@@ -127,6 +127,18 @@ __device__ __forceinline__ V4<T> zero4() {
   return a;
 }
 
+// L2 prefetch of the line(s) a later 128-bit load will touch: the CTA asks for plane
+// iz+1 while it works on plane iz, so the marching loop waits for an L2 hit instead of a
+// DRAM round trip (the loads themselves stay where they are; no registers are held).
+#ifndef KHR_PREFETCH
+#define KHR_PREFETCH 1
+#endif
+__device__ __forceinline__ void pf_l2(const void* p) {
+#if KHR_PREFETCH
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+
 template <class T>
 struct Co {  // PML coefficients of one cell along one axis
   T s, om, ip;
@@ -291,9 +303,32 @@ __global__ void __launch_bounds__(CTA, min_ctas<T, MODE>()) step_kernel(const __
     if (act) { ax_c = ld4(Ax + b0); ay_c = ld4(Ay + b0); }
   }
 
-  for (int iz = it.z0; iz < it.z0 + it.zn; ++iz) {
+  // z coefficients are fetched one plane ahead (they gate the z-slab loads)
+  Co<T> czn;
+  czn.s = T(0); czn.om = T(1); czn.ip = T(1);
+  if constexpr (GENERAL) { czn.s = p.sg[2][it.z0 - 1]; czn.om = p.om[2][it.z0 - 1]; czn.ip = p.ip[2][it.z0 - 1]; }
+  const int z_end = it.z0 + it.zn;
+  const bool yedge = (GROUP == 0) ? (row == it.yh - 1) : (row == 0);  // row whose y neighbour belongs to another CTA
+
+  for (int iz = it.z0; iz < z_end; ++iz) {
     const long long base = p.plane * (long long)iz + fo;
     const long long mbase = p.mplane * (long long)(iz - 1) + mo;
+    const bool more = iz + 1 < z_end;
+#if KHR_PREFETCH
+    if (act && more) {
+      const long long nb = base + p.plane;  // plane iz+1
+      pf_l2(Ax + nb + (GROUP == 0 ? p.plane : 0));
+      pf_l2(Ay + nb + (GROUP == 0 ? p.plane : 0));
+      pf_l2(Az + nb);
+      if (yedge) { pf_l2(Az + nb + IC * p.px); pf_l2(Ax + nb + IC * p.px); }
+      if (edge) { pf_l2(Ay + nb + (GROUP == 0 ? 4 : -1)); pf_l2(Az + nb + (GROUP == 0 ? 4 : -1)); }
+      pf_l2(p.F[0] + nb); pf_l2(p.F[1] + nb); pf_l2(p.F[2] + nb);
+      if constexpr (MARR) {
+        const long long nm = mbase + p.mplane;
+        pf_l2(p.m_arr[0] + nm); pf_l2(p.m_arr[1] + nm); pf_l2(p.m_arr[2] + nm);
+      }
+    }
+#endif
     V4<T> ax0, ay0, az0, ax_z, ay_z, az_y, ax_y;
     V4<T> fx, fy, fz, m0, m1, m2;
     T ay_x = T(0), az_x = T(0);
@@ -306,23 +341,32 @@ __global__ void __launch_bounds__(CTA, min_ctas<T, MODE>()) step_kernel(const __
     V4<T> ux, uy, uz, wx, wy, wz;
     T *Uxp = nullptr, *Uyp = nullptr, *Uzp = nullptr, *Wxp = nullptr, *Wyp = nullptr, *Wzp = nullptr;
     if constexpr (GENERAL) {
-      czc.s = p.sg[2][iz - 1]; czc.om = p.om[2][iz - 1]; czc.ip = p.ip[2][iz - 1];
+      czc = czn;
+      if (more) { czn.s = p.sg[2][iz]; czn.om = p.om[2][iz]; czn.ip = p.ip[2][iz]; }
       hasz = act && (czc.s != T(0));
       ux = uy = uz = wx = wy = wz = zero4<T>();
       if (hasx) {
-        const long long xsl = (long long)p.cxp * p.n[1] * (long long)(iz - 1) + xs_off;
+        const long long xst = (long long)p.cxp * p.n[1];
+        const long long xsl = xst * (long long)(iz - 1) + xs_off;
         Wxp = p.W[0] + xsl; Uzp = p.U[2] + xsl;
         wx = ld4(Wxp); uz = ld4(Uzp);
+        if (more) { pf_l2(Wxp + xst); pf_l2(Uzp + xst); }
       }
       if (hasy) {
-        const long long ysl = (long long)p.mpx * p.cy * (long long)(iz - 1) + ys_off;
+        const long long yst = (long long)p.mpx * p.cy;
+        const long long ysl = yst * (long long)(iz - 1) + ys_off;
         Wyp = p.W[1] + ysl; Uxp = p.U[0] + ysl;
         wy = ld4(Wyp); ux = ld4(Uxp);
+        if (more) { pf_l2(Wyp + yst); pf_l2(Uxp + yst); }
       }
       if (hasz) {
         const long long zsl = p.mplane * (long long)p.slab[2].idx(iz) + mo;
         Wzp = p.W[2] + zsl; Uyp = p.U[1] + zsl;
         wz = ld4(Wzp); uy = ld4(Uyp);
+      }
+      if (act && more && czn.s != T(0)) {
+        const long long zsn = p.mplane * (long long)p.slab[2].idx(iz + 1) + mo;
+        pf_l2(p.W[2] + zsn); pf_l2(p.U[1] + zsn);
       }
     }
     if (act) {
