@@ -234,9 +234,16 @@ struct Impl : Base {
   std::vector<std::vector<uint8_t>> pole_mask;  // host non-zero masks (bytes model only)
   std::vector<uint8_t> sd_mask[2];
   // phase 0 = boundary planes that feed the halo exchange, phase 1 = the rest
-  Table tab[2][2][3];
-  cudaStream_t side[2] = {nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  // table index: 0 interior; 1 / 2 / 4 PML on x / y / z only; 7 PML on several axes;
+  // 8 "full" (sources, conductivity, poles); 3, 5, 6 unused (folded into 7)
+  static constexpr int NTAB = 9, NSIDE = 6;
+  Table tab[2][2][NTAB];
+  cudaStream_t side[NSIDE] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {};
+  bool axis_spec = false;  // measured slower on B200 (profiles/r01_axis_spec_pdl_ab.txt): more launches, more tails
+  static int side_of(int m) { return m == 1 ? 0 : m == 2 ? 1 : m == 4 ? 2 : m == 7 ? 3 : m == 8 ? 4 : 5; }
+  bool main_heaviest = false;
+  bool pdl = false;
   bool multi_stream = true;
   bool finalized = false;
   // distributed
@@ -265,10 +272,13 @@ struct Impl : Base {
     CUDA_OK(cudaEventCreateWithFlags(&ev_comm, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreate(&ev_t0));
     CUDA_OK(cudaEventCreate(&ev_t1));
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < NSIDE; ++q) {
       CUDA_OK(cudaStreamCreateWithFlags(&side[q], cudaStreamNonBlocking));
       CUDA_OK(cudaEventCreateWithFlags(&ev_join[q], cudaEventDisableTiming));
     }
+    if (const char* e = getenv("KHR_AXIS_SPEC")) axis_spec = atoi(e) != 0;
+    if (const char* e = getenv("KHR_MAIN_HEAVIEST")) main_heaviest = atoi(e) != 0;
+    if (const char* e = getenv("KHR_PDL")) { pdl = atoi(e) != 0; if (pdl) multi_stream = false; }
     CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     if (const char* e = getenv("KHR_MULTI_STREAM")) multi_stream = atoi(e) != 0;
     N[0] = gd.n[0]; N[1] = gd.n[1]; N[2] = gd.nz_local;
@@ -636,7 +646,7 @@ struct Impl : Base {
   void for_tables(F f) {
     for (int gq = 0; gq < 2; ++gq)
       for (int ph = 0; ph < 2; ++ph)
-        for (int m = 0; m < 3; ++m) f(tab[gq][ph][m], gq, ph, m);
+        for (int m = 0; m < NTAB; ++m) f(tab[gq][ph][m], gq, ph, m);
   }
   void collect_profile() {
     for_tables([&](Table& t, int, int, int) {
@@ -662,7 +672,7 @@ struct Impl : Base {
       if (t.items.empty()) return;
       if (k == idx && out) {
         memset(out, 0, sizeof(*out));
-        static const char* mn[3] = {"interior", "pml", "full"};
+        static const char* mn[NTAB] = {"interior", "pml-x", "pml-y", "", "pml-z", "", "", "pml", "full"};
         snprintf(out->name, sizeof(out->name), "step_kernel<%s,%s,%s,%s>%s", sizeof(T) == 4 ? "f32" : "f64",
                  gq == 0 ? "H" : "E", mn[m], m_arr[gq][0] ? "marr" : "mscalar", ph == 0 ? "[boundary]" : "");
         out->launches = t.nlaunch;
@@ -764,7 +774,9 @@ struct Impl : Base {
                         extras = true;
                         if (bx.src) it.flags |= 1;
                       }
-                    int mode = extras ? 2 : ((X.pml || Y.pml || Z.pml) ? 1 : 0);
+                    int axm = (X.pml ? 1 : 0) | (Y.pml ? 2 : 0) | (Z.pml ? 4 : 0);
+                    if (!(axm == 1 || axm == 2 || axm == 4) || !axis_spec) axm = axm ? 7 : 0;
+                    int mode = extras ? 8 : axm;
                     int phase = 1;
                     if (g.nranks > 1) {
                       if (gq == 0 && g.rank < g.nranks - 1 && zs + zc - 1 == N[2]) phase = 0;
@@ -796,22 +808,44 @@ struct Impl : Base {
   }
 
   // ---- stepping -------------------------------------------------------------
-  template <int GROUP, int MODE>
+  template <int GROUP, int MODE, int AXM>
   void launch_mode(const StepParams<T>& p, bool marr, int n, cudaStream_t st) {
-    if (marr) step_kernel<T, GROUP, MODE, true><<<n, CTA, 0, st>>>(p);
-    else step_kernel<T, GROUP, MODE, false><<<n, CTA, 0, st>>>(p);
+    if (pdl) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)n); cfg.blockDim = dim3(CTA); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      if (marr) CUDA_OK(cudaLaunchKernelEx(&cfg, step_kernel<T, GROUP, MODE, true, AXM>, p));
+      else CUDA_OK(cudaLaunchKernelEx(&cfg, step_kernel<T, GROUP, MODE, false, AXM>, p));
+    } else {
+      if (marr) step_kernel<T, GROUP, MODE, true, AXM><<<n, CTA, 0, st>>>(p);
+      else step_kernel<T, GROUP, MODE, false, AXM><<<n, CTA, 0, st>>>(p);
+    }
     ++launches;
   }
-  // The (up to) three kernels of a half-step phase are independent: the interior one runs
-  // on the main stream, the PML and the full one on side streams, joined before the next phase.
+  // The kernels of a half-step phase are independent: the interior one runs on the main
+  // stream, every PML class and the full one on side streams, joined before the next phase.
   template <int GROUP>
   void launch_group(StepParams<T>& p, int phase, bool marr) {
     bool forked = false;
-    bool used[3] = {false, false, false};
-    for (int m = 2; m >= 0; --m) {
+    bool used[NTAB] = {};
+    // the heaviest table stays on the main stream, so the critical path of consecutive
+    // half-steps is plain stream order with no cross-stream hop; it is launched last
+    int mmain = 0;
+    double best = -1;
+    for (int m = 0; m < NTAB; ++m)
+      if (!tab[GROUP][phase][m].items.empty() && tab[GROUP][phase][m].alg_bytes > best) { best = tab[GROUP][phase][m].alg_bytes; mmain = m; }
+    if (!main_heaviest) mmain = 0;
+    int order[NTAB], no = 0;
+    for (int m = NTAB - 1; m >= 0; --m) if (m != mmain) order[no++] = m;
+    order[no++] = mmain;
+    for (int oi = 0; oi < no; ++oi) {
+      const int m = order[oi];
       Table& t = tab[GROUP][phase][m];
       if (t.items.empty()) continue;
-      cudaStream_t st = (m == 0 || !multi_stream) ? stream : side[m - 1];
+      cudaStream_t st = (m == mmain || !multi_stream) ? stream : side[side_of(m)];
       if (st != stream && !forked) {
         CUDA_OK(cudaEventRecord(ev_fork, stream));
         forked = true;
@@ -825,22 +859,27 @@ struct Impl : Base {
         }
         CUDA_OK(cudaEventRecord(t.ev[t.ev_used], st));
       }
-      if (m == 0) launch_mode<GROUP, 0>(p, marr, n, st);
-      else if (m == 1) launch_mode<GROUP, 1>(p, marr, n, st);
-      else launch_mode<GROUP, 2>(p, marr, n, st);
+      switch (m) {
+        case 0: launch_mode<GROUP, 0, 7>(p, marr, n, st); break;
+        case 1: launch_mode<GROUP, 1, 1>(p, marr, n, st); break;
+        case 2: launch_mode<GROUP, 1, 2>(p, marr, n, st); break;
+        case 4: launch_mode<GROUP, 1, 4>(p, marr, n, st); break;
+        case 8: launch_mode<GROUP, 2, 7>(p, marr, n, st); break;
+        default: launch_mode<GROUP, 1, 7>(p, marr, n, st); break;
+      }
       if (profiling) {
         CUDA_OK(cudaEventRecord(t.ev[t.ev_used + 1], st));
         t.ev_used += 2;
       }
-      if (st != stream) { CUDA_OK(cudaEventRecord(ev_join[m - 1], st)); used[m] = true; }
+      if (st != stream) { CUDA_OK(cudaEventRecord(ev_join[side_of(m)], st)); used[m] = true; }
     }
-    for (int m = 1; m < 3; ++m)
-      if (used[m]) CUDA_OK(cudaStreamWaitEvent(stream, ev_join[m - 1], 0));
+    for (int m = 0; m < NTAB; ++m)
+      if (used[m]) CUDA_OK(cudaStreamWaitEvent(stream, ev_join[side_of(m)], 0));
     CUDA_OK(cudaGetLastError());
   }
   void sync_all() {
     CUDA_OK(cudaStreamSynchronize(stream));
-    for (int q = 0; q < 2; ++q) CUDA_OK(cudaStreamSynchronize(side[q]));
+    for (int q = 0; q < NSIDE; ++q) CUDA_OK(cudaStreamSynchronize(side[q]));
   }
 
   double time_now() const { return (double)((T)timestep * dt); }  // Simulation.jl:22 round_time

@@ -133,6 +133,9 @@ __device__ __forceinline__ V4<T> zero4() {
 #ifndef KHR_PREFETCH
 #define KHR_PREFETCH 1
 #endif
+#ifndef KHR_PF_DIST
+#define KHR_PF_DIST 1   // planes ahead
+#endif
 __device__ __forceinline__ void pf_l2(const void* p) {
 #if KHR_PREFETCH
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -223,7 +226,7 @@ __device__ __forceinline__ void cascade(const T (&k)[4], const Co<T> (&cn)[4], c
 //   MARR   : per-voxel m^-1 arrays (eps^-1 or mu^-1) instead of a scalar
 // The row width (lanes along x) is a per-item power of two, 8/16/32.
 // ----------------------------------------------------------------------------
-template <class T, int MODE>
+template <class T, int MODE, int AXM>
 constexpr int min_ctas() {
   // registers/thread budget: 64K regs per SM, 256-thread CTAs
 #ifndef KHR_MINCTA_M0
@@ -232,14 +235,26 @@ constexpr int min_ctas() {
 #ifndef KHR_MINCTA_M1
 #define KHR_MINCTA_M1 2
 #endif
-  return sizeof(T) == 4 ? (MODE == 0 ? KHR_MINCTA_M0 : (MODE == 1 ? KHR_MINCTA_M1 : 1)) : 1;
+#ifndef KHR_MINCTA_M1S
+#define KHR_MINCTA_M1S 3   // single-axis PML tiles
+#endif
+  constexpr bool single = (AXM == 1 || AXM == 2 || AXM == 4);
+  return sizeof(T) == 4 ? (MODE == 0 ? KHR_MINCTA_M0 : (MODE == 1 ? (single ? KHR_MINCTA_M1S : KHR_MINCTA_M1) : 1)) : 1;
 }
 
-template <class T, int GROUP, int MODE, bool MARR>
-__global__ void __launch_bounds__(CTA, min_ctas<T, MODE>()) step_kernel(const __grid_constant__ StepParams<T> p) {
+//   AXM    : bit mask of the axes whose sigma may be non-zero inside the work item (the planner
+//            cuts the items at the PML faces).  Coefficients of the other axes are the
+//            compile-time constants (0, 1, 1), so their stages fold away exactly (x*1 == x):
+//            a single-axis PML tile carries one W and one U array and nothing else.
+template <class T, int GROUP, int MODE, bool MARR, int AXM = 7>
+__global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(const __grid_constant__ StepParams<T> p) {
   constexpr int IC = (GROUP == 0) ? 1 : -1;
   constexpr bool GENERAL = MODE >= 1;   // PML cascade
   constexpr bool EXTRAS = MODE == 2;    // + sources, sigma_D/B, ADE poles
+  constexpr bool PXA = (AXM & 1) != 0, PYA = (AXM & 2) != 0, PZA = (AXM & 4) != 0;
+#ifdef KHR_PDL_EXPERIMENT
+  asm volatile("griddepcontrol.launch_dependents;");
+#endif
   const WorkItem it = p.items[blockIdx.x];
   const int lxl = it.lx_log2;
   const int LX = 1 << lxl;
@@ -271,16 +286,20 @@ __global__ void __launch_bounds__(CTA, min_ctas<T, MODE>()) step_kernel(const __
     for (int e = 0; e < 4; ++e) { cx[e].s = T(0); cx[e].om = T(1); cx[e].ip = T(1); }
     cyc.s = T(0); cyc.om = T(1); cyc.ip = T(1);
     if (act) {
-      V4<T> s = ld4(p.sg[0] + gx - 1), o = ld4(p.om[0] + gx - 1), i = ld4(p.ip[0] + gx - 1);
+      if constexpr (PXA) {
+        V4<T> s = ld4(p.sg[0] + gx - 1), o = ld4(p.om[0] + gx - 1), i = ld4(p.ip[0] + gx - 1);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        cx[e].s = s.v[e]; cx[e].om = o.v[e]; cx[e].ip = i.v[e];
-        hasx |= (s.v[e] != T(0));
+        for (int e = 0; e < 4; ++e) {
+          cx[e].s = s.v[e]; cx[e].om = o.v[e]; cx[e].ip = i.v[e];
+          hasx |= (s.v[e] != T(0));
+        }
+        if (hasx) xs_off = p.slab[0].idx(gx) + p.cxp * (iy - 1);
       }
-      cyc.s = p.sg[1][iy - 1]; cyc.om = p.om[1][iy - 1]; cyc.ip = p.ip[1][iy - 1];
-      hasy = cyc.s != T(0);
-      if (hasx) xs_off = p.slab[0].idx(gx) + p.cxp * (iy - 1);
-      if (hasy) ys_off = (gx - 1) + p.mpx * p.slab[1].idx(iy);
+      if constexpr (PYA) {
+        cyc.s = p.sg[1][iy - 1]; cyc.om = p.om[1][iy - 1]; cyc.ip = p.ip[1][iy - 1];
+        hasy = cyc.s != T(0);
+        if (hasy) ys_off = (gx - 1) + p.mpx * p.slab[1].idx(iy);
+      }
     }
   }
   // sources: which table entries can touch this tile (block-uniform mask)
@@ -306,27 +325,47 @@ __global__ void __launch_bounds__(CTA, min_ctas<T, MODE>()) step_kernel(const __
   // z coefficients are fetched one plane ahead (they gate the z-slab loads)
   Co<T> czn;
   czn.s = T(0); czn.om = T(1); czn.ip = T(1);
-  if constexpr (GENERAL) { czn.s = p.sg[2][it.z0 - 1]; czn.om = p.om[2][it.z0 - 1]; czn.ip = p.ip[2][it.z0 - 1]; }
+  if constexpr (GENERAL && PZA) { czn.s = p.sg[2][it.z0 - 1]; czn.om = p.om[2][it.z0 - 1]; czn.ip = p.ip[2][it.z0 - 1]; }
   const int z_end = it.z0 + it.zn;
   const bool yedge = (GROUP == 0) ? (row == it.yh - 1) : (row == 0);  // row whose y neighbour belongs to another CTA
+
+  // everything plane zp will load from HBM, requested into L2 ahead of time
+  auto prefetch_plane = [&](int zp) {
+    const long long nb = p.plane * (long long)zp + fo;
+    pf_l2(Ax + nb + (GROUP == 0 ? p.plane : 0));
+    pf_l2(Ay + nb + (GROUP == 0 ? p.plane : 0));
+    pf_l2(Az + nb);
+    if (yedge) { pf_l2(Az + nb + IC * p.px); pf_l2(Ax + nb + IC * p.px); }
+    if (edge) { pf_l2(Ay + nb + (GROUP == 0 ? 4 : -1)); pf_l2(Az + nb + (GROUP == 0 ? 4 : -1)); }
+    pf_l2(p.F[0] + nb); pf_l2(p.F[1] + nb); pf_l2(p.F[2] + nb);
+    const long long nm = p.mplane * (long long)(zp - 1) + mo;
+    if constexpr (MARR) { pf_l2(p.m_arr[0] + nm); pf_l2(p.m_arr[1] + nm); pf_l2(p.m_arr[2] + nm); }
+    if constexpr (GENERAL) {
+      if (hasx) {
+        const long long xsl = (long long)p.cxp * p.n[1] * (long long)(zp - 1) + xs_off;
+        pf_l2(p.W[0] + xsl); pf_l2(p.U[2] + xsl);
+      }
+      if (hasy) {
+        const long long ysl = (long long)p.mpx * p.cy * (long long)(zp - 1) + ys_off;
+        pf_l2(p.W[1] + ysl); pf_l2(p.U[0] + ysl);
+      }
+      if (PZA && p.sg[2][zp - 1] != T(0)) {
+        const long long zsn = p.mplane * (long long)p.slab[2].idx(zp) + mo;
+        pf_l2(p.W[2] + zsn); pf_l2(p.U[1] + zsn);
+      }
+    }
+  };
 
   for (int iz = it.z0; iz < z_end; ++iz) {
     const long long base = p.plane * (long long)iz + fo;
     const long long mbase = p.mplane * (long long)(iz - 1) + mo;
     const bool more = iz + 1 < z_end;
 #if KHR_PREFETCH
-    if (act && more) {
-      const long long nb = base + p.plane;  // plane iz+1
-      pf_l2(Ax + nb + (GROUP == 0 ? p.plane : 0));
-      pf_l2(Ay + nb + (GROUP == 0 ? p.plane : 0));
-      pf_l2(Az + nb);
-      if (yedge) { pf_l2(Az + nb + IC * p.px); pf_l2(Ax + nb + IC * p.px); }
-      if (edge) { pf_l2(Ay + nb + (GROUP == 0 ? 4 : -1)); pf_l2(Az + nb + (GROUP == 0 ? 4 : -1)); }
-      pf_l2(p.F[0] + nb); pf_l2(p.F[1] + nb); pf_l2(p.F[2] + nb);
-      if constexpr (MARR) {
-        const long long nm = mbase + p.mplane;
-        pf_l2(p.m_arr[0] + nm); pf_l2(p.m_arr[1] + nm); pf_l2(p.m_arr[2] + nm);
+    if (act) {
+      if (iz == it.z0) {
+        for (int zp = iz + 1; zp < iz + KHR_PF_DIST && zp < z_end; ++zp) prefetch_plane(zp);
       }
+      if (iz + KHR_PF_DIST < z_end) prefetch_plane(iz + KHR_PF_DIST);
     }
 #endif
     V4<T> ax0, ay0, az0, ax_z, ay_z, az_y, ax_y;
@@ -342,31 +381,27 @@ __global__ void __launch_bounds__(CTA, min_ctas<T, MODE>()) step_kernel(const __
     T *Uxp = nullptr, *Uyp = nullptr, *Uzp = nullptr, *Wxp = nullptr, *Wyp = nullptr, *Wzp = nullptr;
     if constexpr (GENERAL) {
       czc = czn;
-      if (more) { czn.s = p.sg[2][iz]; czn.om = p.om[2][iz]; czn.ip = p.ip[2][iz]; }
-      hasz = act && (czc.s != T(0));
+      if constexpr (PZA) {
+        if (more) { czn.s = p.sg[2][iz]; czn.om = p.om[2][iz]; czn.ip = p.ip[2][iz]; }
+        hasz = act && (czc.s != T(0));
+      }
       ux = uy = uz = wx = wy = wz = zero4<T>();
       if (hasx) {
         const long long xst = (long long)p.cxp * p.n[1];
         const long long xsl = xst * (long long)(iz - 1) + xs_off;
         Wxp = p.W[0] + xsl; Uzp = p.U[2] + xsl;
         wx = ld4(Wxp); uz = ld4(Uzp);
-        if (more) { pf_l2(Wxp + xst); pf_l2(Uzp + xst); }
       }
       if (hasy) {
         const long long yst = (long long)p.mpx * p.cy;
         const long long ysl = yst * (long long)(iz - 1) + ys_off;
         Wyp = p.W[1] + ysl; Uxp = p.U[0] + ysl;
         wy = ld4(Wyp); ux = ld4(Uxp);
-        if (more) { pf_l2(Wyp + yst); pf_l2(Uxp + yst); }
       }
       if (hasz) {
         const long long zsl = p.mplane * (long long)p.slab[2].idx(iz) + mo;
         Wzp = p.W[2] + zsl; Uyp = p.U[1] + zsl;
         wz = ld4(Wzp); uy = ld4(Uyp);
-      }
-      if (act && more && czn.s != T(0)) {
-        const long long zsn = p.mplane * (long long)p.slab[2].idx(iz + 1) + mo;
-        pf_l2(p.W[2] + zsn); pf_l2(p.U[1] + zsn);
       }
     }
     if (act) {

@@ -1140,6 +1140,13 @@ int ko_num_threads(void) {
 #endif
 }
 
+// torchrun exports OMP_NUM_THREADS=1; the CPU baseline arm asks for all host cores explicitly
+void ko_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#endif
+}
+
 long ko_timestep(void* hv) {
   Handle* h = (Handle*)hv;
   long t = 0;

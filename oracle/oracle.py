@@ -71,6 +71,7 @@ def lib():
         L.ko_set_sources_active.argtypes = [C.c_void_p, C.c_int]
         L.ko_timestep.restype = C.c_long
         L.ko_num_threads.restype = C.c_int
+        L.ko_set_num_threads.argtypes = [C.c_int]
         L.ko_timestep.argtypes = [C.c_void_p]
         L.ko_get_field.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
         L.ko_set_field.argtypes = [C.c_void_p, C.c_int, dp]
@@ -83,6 +84,10 @@ def lib():
 
 def num_threads():
     return int(lib().ko_num_threads())
+
+
+def set_num_threads(n):
+    lib().ko_set_num_threads(int(n))
 
 
 def _d(a):
