@@ -20,7 +20,6 @@ import math
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -39,25 +38,37 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region by ONE long-running
+    `nvidia-smi -lms` child (started before, stopped after): nothing forks inside the timed loops."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        super().__init__(daemon=True)
-        self.index, self.stop_flag, self.rows = index, False, []
+        self.index, self.proc, self.rows = index, None, []
 
-    def run(self):
-        while not self.stop_flag:
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return
+        try:
+            self.proc.terminate()
+            out, _ = self.proc.communicate(timeout=5)
+            self.rows = [[x.strip() for x in ln.split(",")] for ln in out.strip().splitlines() if ln.strip()]
+        except Exception:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(",")])
+                self.proc.kill()
             except Exception:
                 pass
-            time.sleep(0.1)
+        self.proc = None
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
@@ -226,7 +237,8 @@ def main_ours(args):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = cells * e2e_steps / e2e_s / 1e6
-    sampler.stop_flag = True
+    if rank == 0:
+        sampler.stop()
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -275,14 +287,14 @@ def main_ours(args):
                     "what": "sim.step(1) through the Python API/C ABI per step + host source amplitudes in + DFT norms out, monitors read at the end"},
             "roofline": roof, "cpu_baseline": cpu, "clocks": sampler.summary(),
             "ms_per_step_with_kernel_events": ms_profiled / args.steps,
-            "kernels": [{k: s[k] for k in ("name", "launches", "total_ms", "ctas")} for s in stats]}
+            "kernels": [{k: s[k] for k in ("name", "launches", "total_ms", "ctas", "uniform_ctas")} for s in stats]}
     print(json.dumps(line))
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="waveguide_mode")

@@ -156,6 +156,7 @@ typedef struct khr_kernel_stat {
   int64_t cells_per_launch;     /* voxels one launch updates */
   double alg_bytes_per_launch;  /* SURVEY.md §8(d) bytes model for those voxels (one half-step) */
   int64_t ctas;                 /* thread blocks per launch */
+  int64_t uniform_ctas;         /* of those, tiles with constant per-voxel material (loads skipped) */
 } khr_kernel_stat;
 int32_t khr_set_profiling(khr_ctx* ctx, int32_t mode);
 /* index in [0, count); pass out = NULL to query only the count */

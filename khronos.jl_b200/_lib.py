@@ -38,6 +38,7 @@ class KernelStat(C.Structure):
         ("cells_per_launch", C.c_int64),
         ("alg_bytes_per_launch", C.c_double),
         ("ctas", C.c_int64),
+        ("uniform_ctas", C.c_int64),
     ]
 
 

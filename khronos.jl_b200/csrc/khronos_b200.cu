@@ -221,9 +221,11 @@ struct Impl : Base {
   // work tables: [group][mode][lx index]
   struct Table {
     std::vector<WorkItem> items;
+    std::vector<double> cost;  // bytes model per item (launch-order heuristic)
     WorkItem* d = nullptr;
     // bytes model and live CUDA-event timing of this table's launches
     int64_t cells = 0;
+    int64_t uniform_items = 0;  // tiles whose per-voxel material arrays are constant
     double alg_bytes = 0;
     std::vector<cudaEvent_t> ev;  // pairs
     size_t ev_used = 0;
@@ -243,7 +245,17 @@ struct Impl : Base {
   bool axis_spec = false;  // measured slower on B200 (profiles/r01_axis_spec_pdl_ab.txt): more launches, more tails
   static int side_of(int m) { return m == 1 ? 0 : m == 2 ? 1 : m == 4 ? 2 : m == 7 ? 3 : m == 8 ? 4 : 5; }
   bool main_heaviest = false;
+  // chain mode: all kernels of a step on one stream, launched with programmatic dependent launch;
+  // H <-> E ordering is enforced per z chunk by device counters (step_kernels.cuh), so the tail of
+  // one half-step overlaps the head of the next
   bool pdl = false;
+  int nchunk = 0;
+  unsigned long long* d_cnt[2] = {nullptr, nullptr};
+  unsigned long long* d_done[2] = {nullptr, nullptr};
+  unsigned long long epochs[2] = {0, 0};
+  int* h_err = nullptr;  // mapped pinned flag, set by a kernel whose dependency wait timed out
+  int* d_err = nullptr;
+  int launch_order = 0;
   bool multi_stream = true;
   bool finalized = false;
   // distributed
@@ -278,7 +290,12 @@ struct Impl : Base {
     }
     if (const char* e = getenv("KHR_AXIS_SPEC")) axis_spec = atoi(e) != 0;
     if (const char* e = getenv("KHR_MAIN_HEAVIEST")) main_heaviest = atoi(e) != 0;
-    if (const char* e = getenv("KHR_PDL")) { pdl = atoi(e) != 0; if (pdl) multi_stream = false; }
+    if (const char* e = getenv("KHR_ORDER")) launch_order = atoi(e);
+    if (const char* e = getenv("KHR_CHAIN")) pdl = atoi(e) != 0;
+    if (pdl) multi_stream = false;
+    CUDA_OK(cudaHostAlloc((void**)&h_err, sizeof(int), cudaHostAllocMapped));
+    *h_err = 0;
+    CUDA_OK(cudaHostGetDevicePointer((void**)&d_err, h_err, 0));
     CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     if (const char* e = getenv("KHR_MULTI_STREAM")) multi_stream = atoi(e) != 0;
     N[0] = gd.n[0]; N[1] = gd.n[1]; N[2] = gd.nz_local;
@@ -298,6 +315,7 @@ struct Impl : Base {
     cudaDeviceSynchronize();
     for (void* p : allocs) cudaFree(p);
     if (h_norms) cudaFreeHost(h_norms);
+    if (h_err) cudaFreeHost(h_err);
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     cudaEventDestroy(ev_boundary); cudaEventDestroy(ev_comm); cudaEventDestroy(ev_t0); cudaEventDestroy(ev_t1);
     cudaStreamDestroy(stream); cudaStreamDestroy(comm_stream);
@@ -680,6 +698,7 @@ struct Impl : Base {
         out->cells_per_launch = t.cells;
         out->alg_bytes_per_launch = t.alg_bytes;
         out->ctas = (int64_t)t.items.size();
+        out->uniform_ctas = t.uniform_items;
       }
       ++k;
     });
@@ -712,11 +731,14 @@ struct Impl : Base {
         pmlc[a][i] = pmlc[a][i - 1] + (on ? 1 : 0);
       }
     }
+    // boxes that need the full kernel (sources, sigma_D/B, poles); the ranges are cut at
+    // their faces so that only the voxels inside them pay for the extras
+    struct Box { int b[6]; bool src; };
+    std::vector<Box> gboxes[2];
+    std::vector<int> czv;  // z cuts are shared by both field groups: the z chunks they define are
+                           // the unit of the H <-> E dependency counters (chain mode)
     for (int gq = 0; gq < 2; ++gq) {
-      // boxes that need the full kernel (sources, sigma_D/B, poles); the ranges are cut at
-      // their faces so that only the voxels inside them pay for the extras
-      struct Box { int b[6]; bool src; };
-      std::vector<Box> boxes;
+      std::vector<Box>& boxes = gboxes[gq];
       for (auto& s : sources)
         if ((s.comp >= 3) == (gq == 0))
           boxes.push_back({{s.s[0], s.s[1], s.s[2], s.s[0] + s.d[0] - 1, s.s[1] + s.d[1] - 1, s.s[2] + s.d[2] - 1}, true});
@@ -726,34 +748,47 @@ struct Impl : Base {
       if (gq == 1)
         for (auto& pl : poles)
           if (pl.box[0] <= pl.box[3]) { Box b; for (int q = 0; q < 6; ++q) b.b[q] = pl.box[q]; b.src = false; boxes.push_back(b); }
-      std::vector<int> cx, cyv, czv;
+      for (auto& bx : boxes) { czv.push_back(bx.b[2]); czv.push_back(bx.b[5] + 1); }
+    }
+    if (g.nranks > 1) {
+      // the plane that feeds the halo exchange gets its own thin range (boundary-first launch)
+      if (g.rank < g.nranks - 1) czv.push_back(N[2]);
+      if (g.rank > 0) czv.push_back(2);
+    }
+    const std::vector<Range> zr = split_ranges(zr0, czv);
+    int zseg;
+    {
+      // z segment length: enough CTAs to fill 148 SMs several times over, but long enough
+      // to amortise the carried plane
+      long long tiles_xy = 0;
+      for (auto& X : xr0) {
+        int lx = 8 << lx_index(X.e - X.s + 1);
+        for (auto& Y : yr0) tiles_xy += (long long)((X.e - X.s) / (4 * lx) + 1) * ((Y.e - Y.s) / (CTA / lx) + 1);
+      }
+      // measured on B200 (profiles/r01_zseg_sweep.txt): 7-8 planes per CTA is the sweet spot
+      zseg = (int)std::min<long long>(8, std::max<long long>(4, (tiles_xy * N[2] + 2367) / 2368));
+      if (const char* e = getenv("KHR_ZSEG")) zseg = std::max(1, atoi(e));
+    }
+    nchunk = 0;
+    for (auto& Z : zr) nchunk += (Z.e - Z.s) / zseg + 1;
+    std::vector<unsigned long long> chunk_cnt[2];
+    for (int gq = 0; gq < 2; ++gq) chunk_cnt[gq].assign((size_t)nchunk, 0ull);
+    for (int gq = 0; gq < 2; ++gq) {
+      std::vector<Box>& boxes = gboxes[gq];
+      std::vector<int> cx, cyv;
       for (auto& bx : boxes) {
         cx.push_back(1 + 32 * ((std::max(bx.b[0], 1) - 1) / 32));
         cx.push_back(1 + 32 * ((std::max(bx.b[3], 0) + 31) / 32));
         cyv.push_back(bx.b[1]); cyv.push_back(bx.b[4] + 1);
-        czv.push_back(bx.b[2]); czv.push_back(bx.b[5] + 1);
       }
-      if (g.nranks > 1) {
-        // the plane that feeds the halo exchange gets its own thin range (boundary-first launch)
-        if (gq == 0 && g.rank < g.nranks - 1) czv.push_back(N[2]);
-        if (gq == 1 && g.rank > 0) czv.push_back(2);
-      }
-      std::vector<Range> xr = split_ranges(xr0, cx), yr = split_ranges(yr0, cyv), zr = split_ranges(zr0, czv);
-      // z segment length: enough CTAs to fill 148 SMs several times over, but long enough
-      // to amortise the carried plane
-      long long tiles_xy = 0;
-      for (auto& X : xr) {
-        int lx = 8 << lx_index(X.e - X.s + 1);
-        for (auto& Y : yr) tiles_xy += (long long)((X.e - X.s) / (4 * lx) + 1) * ((Y.e - Y.s) / (CTA / lx) + 1);
-      }
-      // measured on B200 (profiles/r01_zseg_sweep.txt): 7-8 planes per CTA is the sweet spot
-      int zseg = (int)std::min<long long>(8, std::max<long long>(4, (tiles_xy * N[2] + 2367) / 2368));
-      if (const char* e = getenv("KHR_ZSEG")) zseg = std::max(1, atoi(e));
+      std::vector<Range> xr = split_ranges(xr0, cx), yr = split_ranges(yr0, cyv);
+      int chunk = -1;
       int zseg_full = 2;
       if (const char* e = getenv("KHR_ZSEG_FULL")) zseg_full = std::max(1, atoi(e));
       for (auto& Z : zr)
         for (int z0 = Z.s; z0 <= Z.e; z0 += zseg) {
           int zn = std::min(zseg, Z.e - z0 + 1);
+          ++chunk;
           for (auto& Y : yr)
             for (auto& X : xr) {
               int lxi = lx_index(X.e - X.s + 1);
@@ -768,6 +803,8 @@ struct Impl : Base {
                   // spreads over all SMs and does not become the critical path of the half-step.
                   auto emit = [&](int zs, int zc) {
                     WorkItem it{x0, xw, y0, yh, zs, zc, 0, 3 + lxi};
+                    it.chunk = chunk;
+                    chunk_cnt[gq][(size_t)chunk] += 1;
                     bool extras = false;
                     for (auto& bx : boxes)
                       if (boxes_hit(bx.b, x0, x0 + xw - 1, y0, y0 + yh - 1, zs, zs + zc - 1)) {
@@ -785,7 +822,9 @@ struct Impl : Base {
                     Table& tt = tab[gq][phase][mode];
                     tt.items.push_back(it);
                     tt.cells += (int64_t)xw * yh * zc;
-                    tt.alg_bytes += item_alg_bytes(gq, pmlc, x0, xw, y0, yh, zs, zc);
+                    const double ab = item_alg_bytes(gq, pmlc, x0, xw, y0, yh, zs, zc);
+                    tt.cost.push_back(ab);
+                    tt.alg_bytes += ab;
                   };
                   bool any_box = false;
                   for (auto& bx : boxes)
@@ -798,13 +837,67 @@ struct Impl : Base {
             }
         }
     }
-    for_tables([&](Table& t, int, int, int) {
+    // Launch order: the hardware hands CTAs to free SM slots in table order, so the heaviest
+    // tiles (most PML axes) go first and the last ones are cut into short z pieces: the
+    // tail of a half-step then ends within a few microseconds on every SM.
+    int tail_zn = 0, sort_items = 0;  // both measured: no gain / a loss (sorting breaks L2 locality)
+    if (const char* e = getenv("KHR_TAIL_ZN")) tail_zn = atoi(e);
+    if (const char* e = getenv("KHR_SORT_ITEMS")) sort_items = atoi(e);
+    for_tables([&](Table& t, int, int, int m) {
+      if (t.items.empty() || m == 8) return;
+      const size_t n = t.items.size();
+      std::vector<size_t> idx(n);
+      for (size_t q = 0; q < n; ++q) idx[q] = q;
+      if (sort_items) std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return t.cost[a] > t.cost[b]; });
+      const size_t slots = (size_t)148 * (m == 0 ? 3 : 2);
+      const size_t ntail = tail_zn > 0 ? std::min(n / 3, slots) : 0;
+      std::vector<WorkItem> out;
+      out.reserve(n + 4 * ntail);
+      for (size_t q = 0; q < n; ++q) {
+        const WorkItem& it = t.items[idx[q]];
+        if (q + ntail < n || it.zn <= tail_zn) { out.push_back(it); continue; }
+        for (int zs = it.z0; zs < it.z0 + it.zn; zs += tail_zn) {
+          WorkItem p = it;
+          p.z0 = zs; p.zn = std::min(tail_zn, it.z0 + it.zn - zs);
+          out.push_back(p);
+        }
+      }
+      t.items.swap(out);
+      t.cost.clear();
+    });
+    // items per (group, z chunk) after any splitting: the targets of the dependency counters
+    for (int gq = 0; gq < 2; ++gq) std::fill(chunk_cnt[gq].begin(), chunk_cnt[gq].end(), 0ull);
+    for_tables([&](Table& t, int gq, int, int) {
+      for (auto& it : t.items) chunk_cnt[gq][(size_t)it.chunk] += 1;
+    });
+    for (int gq = 0; gq < 2; ++gq) {
+      size_t words = ((size_t)nchunk * sizeof(unsigned long long) + sizeof(T) - 1) / sizeof(T);
+      d_cnt[gq] = (unsigned long long*)dalloc(words, false);
+      d_done[gq] = (unsigned long long*)dalloc(words, true);
+      CUDA_OK(cudaMemcpyAsync(d_cnt[gq], chunk_cnt[gq].data(), (size_t)nchunk * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+      epochs[gq] = 0;
+    }
+    CUDA_OK(cudaStreamSynchronize(stream));
+    bool uniform_tiles = true;
+    if (const char* e = getenv("KHR_UNIFORM_TILES")) uniform_tiles = atoi(e) != 0;
+    for_tables([&](Table& t, int gq, int, int) {
       if (t.items.empty()) return;
       size_t bytes = t.items.size() * sizeof(WorkItem);
       t.d = (WorkItem*)dalloc((bytes + sizeof(T) - 1) / sizeof(T), false);
       CUDA_OK(cudaMemcpyAsync(t.d, t.items.data(), bytes, cudaMemcpyHostToDevice, stream));
+      if (uniform_tiles && m_arr[gq][0] && m_arr[gq][1] && m_arr[gq][2]) {
+        // tiles with constant material skip the per-voxel loads (bit-identical results)
+        classify_items_kernel<T><<<(unsigned)t.items.size(), 256, 0, stream>>>(t.d, m_arr[gq][0], m_arr[gq][1], m_arr[gq][2], MPX,
+                                                                             (long long)MPX * N[1]);
+        CUDA_OK(cudaGetLastError());
+        CUDA_OK(cudaMemcpyAsync(t.items.data(), t.d, bytes, cudaMemcpyDeviceToHost, stream));
+      }
     });
     CUDA_OK(cudaStreamSynchronize(stream));
+    for_tables([&](Table& t, int, int, int) {
+      t.uniform_items = 0;
+      for (auto& it : t.items) t.uniform_items += (it.flags & 2) ? 1 : 0;
+    });
   }
 
   // ---- stepping -------------------------------------------------------------
@@ -839,8 +932,16 @@ struct Impl : Base {
       if (!tab[GROUP][phase][m].items.empty() && tab[GROUP][phase][m].alg_bytes > best) { best = tab[GROUP][phase][m].alg_bytes; mmain = m; }
     if (!main_heaviest) mmain = 0;
     int order[NTAB], no = 0;
-    for (int m = NTAB - 1; m >= 0; --m) if (m != mmain) order[no++] = m;
-    order[no++] = mmain;
+    if (launch_order == 1) {        // PML classes, interior, full last
+      for (int m = 7; m >= 1; --m) order[no++] = m;
+      order[no++] = 0; order[no++] = 8;
+    } else if (launch_order == 2) { // PML classes, full, interior
+      for (int m = 7; m >= 1; --m) order[no++] = m;
+      order[no++] = 8; order[no++] = 0;
+    } else {                        // full, PML classes, interior
+      for (int m = NTAB - 1; m >= 0; --m) if (m != mmain) order[no++] = m;
+      order[no++] = mmain;
+    }
     for (int oi = 0; oi < no; ++oi) {
       const int m = order[oi];
       Table& t = tab[GROUP][phase][m];
@@ -918,6 +1019,13 @@ struct Impl : Base {
       d.an_re = re; d.an_im = im; d.ao_re = s.ao_re; d.ao_im = s.ao_im;
       s.ao_re = re; s.ao_im = im;
     }
+    p.dep_on = pdl ? 1 : 0;
+    p.nchunk = nchunk;
+    p.done_mine = d_done[gq];
+    p.done_other = d_done[1 - gq];
+    p.cnt_other = d_cnt[1 - gq];
+    p.epoch_other = epochs[1 - gq];   // every launch of the other group enqueued so far must have finished the chunk
+    p.err_flag = d_err;
     p.npole = 0;
     for (int d = 0; d < 3; ++d) p.Dst[d] = (gq == 1) ? Dst[d] : nullptr;
     p.Tsrc = Tsrc[gq];
@@ -991,6 +1099,7 @@ struct Impl : Base {
       if (gq == 0) launch_group<0>(p, 1, marr); else launch_group<1>(p, 1, marr);
     }
     if (gq == 1) for (auto& pl : poles) pl.cur = 1 - pl.cur;
+    epochs[gq] += 1;
   }
 
   void step_h() override {
@@ -1085,6 +1194,10 @@ struct Impl : Base {
     for (auto& m : monitors) CUDA_OK(cudaMemsetAsync(m.M, 0, 2 * m.elems * sizeof(T), stream));
     for (auto& c : norm_stale) c = 1;
     for (auto& s : sources) { s.ao_re = 0; s.ao_im = 0; }
+    for (int gq = 0; gq < 2; ++gq) {
+      if (d_done[gq]) CUDA_OK(cudaMemsetAsync(d_done[gq], 0, (size_t)nchunk * sizeof(unsigned long long), stream));
+      epochs[gq] = 0;
+    }
     timestep = 0;
     sources_active = true;
   }
@@ -1213,6 +1326,7 @@ struct Impl : Base {
   void sync() override {
     sync_all();
     CUDA_OK(cudaStreamSynchronize(comm_stream));
+    if (h_err && *h_err) { *h_err = 0; throw std::string("a step kernel timed out waiting for its H/E dependency counters (chain mode)"); }
     if (last_ms < 0) {
       float ms = 0;
       if (cudaEventElapsedTime(&ms, ev_t0, ev_t1) == cudaSuccess) last_ms = ms;

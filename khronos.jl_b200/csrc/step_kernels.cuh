@@ -43,7 +43,11 @@ struct WorkItem {
   int y0, yh;   // first row and number of rows (<= 256/LX)
   int z0, zn;   // first local plane and number of planes marched
   int flags;    // bit0: tile may contain a source of this group
+                // bit1: the per-voxel constitutive arrays are constant over the tile (values in mu[])
   int lx_log2;  // lanes along x = 1 << lx_log2 (3, 4 or 5); rows per CTA = 256 >> lx_log2
+  double mu[3]; // tile-uniform m^-1 per component (exact: a Float32 value is representable)
+  int chunk;    // z chunk of the item (unit of the H <-> E dependency counters)
+  int pad_;
 };
 
 // compact index along a PML axis: cells 1..lo_w map to 0..lo_w-1, cells >= hi_base
@@ -105,6 +109,14 @@ struct StepParams {
   PoleDesc<T> pole[MAXPOLE];
   T* Dst[3];          // D kept on dispersive voxels (material layout), as the reference does
   T* Tsrc;            // B/D kept on source voxels (compact, one slot per (component, cell))
+  // chain mode (one stream, programmatic dependent launch): per z chunk, done_*[c] counts the
+  // work items of a field group that have finished since the last reset
+  int dep_on, nchunk;
+  unsigned long long* done_mine;
+  const unsigned long long* done_other;
+  const unsigned long long* cnt_other;   // items per chunk of the other group
+  unsigned long long epoch_other;        // launches of the other group this launch depends on
+  int* err_flag;
   const WorkItem* items;
 };
 
@@ -140,6 +152,12 @@ __device__ __forceinline__ void pf_l2(const void* p) {
 #if KHR_PREFETCH
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 #endif
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
 }
 
 template <class T>
@@ -252,9 +270,9 @@ __global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(c
   constexpr bool GENERAL = MODE >= 1;   // PML cascade
   constexpr bool EXTRAS = MODE == 2;    // + sources, sigma_D/B, ADE poles
   constexpr bool PXA = (AXM & 1) != 0, PYA = (AXM & 2) != 0, PZA = (AXM & 4) != 0;
-#ifdef KHR_PDL_EXPERIMENT
+  // chain mode: the next kernel of the stream may start as soon as every CTA of this one is
+  // resident; data dependencies are handled by the chunk counters below (no-op otherwise)
   asm volatile("griddepcontrol.launch_dependents;");
-#endif
   const WorkItem it = p.items[blockIdx.x];
   const int lxl = it.lx_log2;
   const int LX = 1 << lxl;
@@ -315,18 +333,12 @@ __global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(c
     }
   }
 
-  // ---- z-neighbour carry ----
-  V4<T> ax_c = zero4<T>(), ay_c = zero4<T>();  // GROUP 0: current plane; GROUP 1: plane below
-  {
-    const long long b0 = p.plane * (long long)(GROUP == 0 ? it.z0 : it.z0 - 1) + fo;
-    if (act) { ax_c = ld4(Ax + b0); ay_c = ld4(Ay + b0); }
-  }
-
   // z coefficients are fetched one plane ahead (they gate the z-slab loads)
   Co<T> czn;
   czn.s = T(0); czn.om = T(1); czn.ip = T(1);
   if constexpr (GENERAL && PZA) { czn.s = p.sg[2][it.z0 - 1]; czn.om = p.om[2][it.z0 - 1]; czn.ip = p.ip[2][it.z0 - 1]; }
   const int z_end = it.z0 + it.zn;
+  const bool m_uniform = MARR && (it.flags & 2) != 0;  // block-uniform
   const bool yedge = (GROUP == 0) ? (row == it.yh - 1) : (row == 0);  // row whose y neighbour belongs to another CTA
 
   // everything plane zp will load from HBM, requested into L2 ahead of time
@@ -339,7 +351,9 @@ __global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(c
     if (edge) { pf_l2(Ay + nb + (GROUP == 0 ? 4 : -1)); pf_l2(Az + nb + (GROUP == 0 ? 4 : -1)); }
     pf_l2(p.F[0] + nb); pf_l2(p.F[1] + nb); pf_l2(p.F[2] + nb);
     const long long nm = p.mplane * (long long)(zp - 1) + mo;
-    if constexpr (MARR) { pf_l2(p.m_arr[0] + nm); pf_l2(p.m_arr[1] + nm); pf_l2(p.m_arr[2] + nm); }
+    if constexpr (MARR) {
+      if (!m_uniform) { pf_l2(p.m_arr[0] + nm); pf_l2(p.m_arr[1] + nm); pf_l2(p.m_arr[2] + nm); }
+    }
     if constexpr (GENERAL) {
       if (hasx) {
         const long long xsl = (long long)p.cxp * p.n[1] * (long long)(zp - 1) + xs_off;
@@ -355,6 +369,40 @@ __global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(c
       }
     }
   };
+
+  // ---- chain mode: wait until the other field group has finished the z chunks this tile reads
+  // (E reads H[k-1..k]: chunks c-1, c; H reads E[k..k+1]: chunks c, c+1).  The same wait also
+  // covers the write-after-read hazard on the own field (its readers are exactly those items).
+  if (p.dep_on) {
+    // ask L2 for the first planes before blocking on the counters (stale lines cannot result:
+    // L2 is the coherence point, the producers' stores update the prefetched lines)
+    if (act) {
+      const long long cb = p.plane * (long long)(GROUP == 0 ? it.z0 : it.z0 - 1) + fo;
+      pf_l2(Ax + cb); pf_l2(Ay + cb);
+      prefetch_plane(it.z0);
+    }
+    if (threadIdx.x == 0) {
+      const int c_lo = it.chunk + (GROUP == 0 ? 0 : -1), c_hi = it.chunk + (GROUP == 0 ? 1 : 0);
+      for (int c = c_lo; c <= c_hi; ++c) {
+        if (c < 0 || c >= p.nchunk) continue;
+        const unsigned long long target = p.epoch_other * p.cnt_other[c];
+        unsigned spins = 0;
+        while (ld_acquire_u64(p.done_other + c) < target) {
+          __nanosleep(40);
+          // never hang the GPU: give up after ~1 s, or at once when another CTA already gave up
+          if (++spins > (1u << 20) || ((spins & 1023u) == 0 && *(volatile int*)p.err_flag != 0)) { *p.err_flag = 1; break; }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- z-neighbour carry ----
+  V4<T> ax_c = zero4<T>(), ay_c = zero4<T>();  // GROUP 0: current plane; GROUP 1: plane below
+  {
+    const long long b0 = p.plane * (long long)(GROUP == 0 ? it.z0 : it.z0 - 1) + fo;
+    if (act) { ax_c = ld4(Ax + b0); ay_c = ld4(Ay + b0); }
+  }
 
   for (int iz = it.z0; iz < z_end; ++iz) {
     const long long base = p.plane * (long long)iz + fo;
@@ -422,7 +470,14 @@ __global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(c
         az_x = Az[base + (GROUP == 0 ? 4 : -1)];
       }
       fx = ld4(Fx); fy = ld4(Fy); fz = ld4(Fz);
-      if constexpr (MARR) { m0 = ld4(p.m_arr[0] + mbase); m1 = ld4(p.m_arr[1] + mbase); m2 = ld4(p.m_arr[2] + mbase); }
+      if constexpr (MARR) {
+        if (m_uniform) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { m0.v[e] = (T)it.mu[0]; m1.v[e] = (T)it.mu[1]; m2.v[e] = (T)it.mu[2]; }
+        } else {
+          m0 = ld4(p.m_arr[0] + mbase); m1 = ld4(p.m_arr[1] + mbase); m2 = ld4(p.m_arr[2] + mbase);
+        }
+      }
     } else {
       ax0 = ay0 = az0 = ax_z = ay_z = az_y = ax_y = zero4<T>();
     }
@@ -650,6 +705,44 @@ __global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(c
     // carry
     if constexpr (GROUP == 0) { ax_c = ax_z; ay_c = ay_z; }
     else { ax_c = ax0; ay_c = ay0; }
+  }
+  if (p.dep_on) {
+    // release: every store of the CTA is ordered before the counter increment
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(p.done_mine + it.chunk, 1ull);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Planner helper (runs once in khr_finalize_plan): marks the work items over which all three
+// per-voxel constitutive arrays are bit-wise constant, and records the values.  Such tiles
+// (most of a piecewise-homogeneous scene) skip the three material loads per plane; the
+// arithmetic is unchanged, so results are bit-identical to the per-voxel path.
+// ----------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256) classify_items_kernel(WorkItem* items, const T* m0, const T* m1, const T* m2,
+                                                            int mpx, long long mplane) {
+  WorkItem& it = items[blockIdx.x];
+  const T* arr[3] = {m0, m1, m2};
+  const long long first = mplane * (long long)(it.z0 - 1) + (long long)mpx * (it.y0 - 1) + (it.x0 - 1);
+  bool same = true;
+  const int ncell = it.xw * it.yh * it.zn;
+  for (int c = 0; c < 3; ++c) {
+    const T v0 = arr[c][first];
+    for (int q = threadIdx.x; q < ncell; q += blockDim.x) {
+      const int x = q % it.xw, y = (q / it.xw) % it.yh, z = q / (it.xw * it.yh);
+      const T v = arr[c][first + x + (long long)mpx * y + mplane * z];
+      if (sizeof(T) == 4) same &= (__float_as_uint((float)v) == __float_as_uint((float)v0));
+      else same &= (__double_as_longlong((double)v) == __double_as_longlong((double)v0));
+    }
+  }
+  const int all = __syncthreads_and(same ? 1 : 0);
+  if (threadIdx.x == 0 && all) {
+    it.flags |= 2;
+    for (int c = 0; c < 3; ++c) it.mu[c] = (double)arr[c][first];
   }
 }
 

@@ -691,7 +691,7 @@ class Simulation:
             _lib.check(L.khr_kernel_stat_get(self.ctx, i, C.byref(st), None))
             out.append(dict(name=st.name.decode(), launches=st.launches, total_ms=st.total_ms,
                             cells_per_launch=st.cells_per_launch, alg_bytes_per_launch=st.alg_bytes_per_launch,
-                            ctas=st.ctas))
+                            ctas=st.ctas, uniform_ctas=st.uniform_ctas))
         return out
 
     def monitor_norm(self, monitor):
