@@ -148,7 +148,8 @@ int32_t khr_last_step_timing(khr_ctx* ctx, double* ms, int64_t* kernel_launches)
 /* voxel-class census used by the bytes model: counts of cells with 0,1,2,3 PML axes */
 int32_t khr_voxel_census(khr_ctx* ctx, int64_t counts[4]);
 /* per-kernel live timing: mode 1 = record CUDA events around every step-kernel launch
- * on the ctx stream, 0 = stop, 2 = start and reset the accumulators */
+ * on the ctx stream, 0 = stop, 2 = start and reset the accumulators, 3 = like 2 but with the
+ * kernels of a half-step serialised on one stream, so that each event pair times its kernel alone */
 typedef struct khr_kernel_stat {
   char name[96];
   int64_t launches;             /* launches timed since the last reset */

@@ -232,7 +232,7 @@ struct Impl : Base {
     double total_ms = 0;
     int64_t nlaunch = 0;
   };
-  bool profiling = false;
+  bool profiling = false, serial_prof = false;
   std::vector<std::vector<uint8_t>> pole_mask;  // host non-zero masks (bytes model only)
   std::vector<uint8_t> sd_mask[2];
   // phase 0 = boundary planes that feed the halo exchange, phase 1 = the rest
@@ -284,8 +284,14 @@ struct Impl : Base {
     CUDA_OK(cudaEventCreateWithFlags(&ev_comm, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreate(&ev_t0));
     CUDA_OK(cudaEventCreate(&ev_t1));
+    int prio_lo = 0, prio_hi = 0;
+    CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    bool use_prio = true;
+    if (const char* e = getenv("KHR_STREAM_PRIO")) use_prio = atoi(e) != 0;
     for (int q = 0; q < NSIDE; ++q) {
-      CUDA_OK(cudaStreamCreateWithFlags(&side[q], cudaStreamNonBlocking));
+      // the PML / full kernels are the critical path of a half-step: their CTAs get the SM slots
+      // first, the interior kernel (main stream, default priority) fills what is left
+      CUDA_OK(cudaStreamCreateWithPriority(&side[q], cudaStreamNonBlocking, (use_prio && q < 5) ? prio_hi : prio_lo));
       CUDA_OK(cudaEventCreateWithFlags(&ev_join[q], cudaEventDisableTiming));
     }
     if (const char* e = getenv("KHR_AXIS_SPEC")) axis_spec = atoi(e) != 0;
@@ -680,7 +686,8 @@ struct Impl : Base {
     sync_all();
     collect_profile();
     profiling = on != 0;
-    if (on == 2) for_tables([&](Table& t, int, int, int) { t.total_ms = 0; t.nlaunch = 0; });
+    serial_prof = on == 3;   // mode 3: one stream, so that every kernel's event pair times it alone
+    if (on == 2 || on == 3) for_tables([&](Table& t, int, int, int) { t.total_ms = 0; t.nlaunch = 0; });
   }
   int kernel_stat(int idx, khr_kernel_stat* out) override {
     sync_all();
@@ -946,7 +953,7 @@ struct Impl : Base {
       const int m = order[oi];
       Table& t = tab[GROUP][phase][m];
       if (t.items.empty()) continue;
-      cudaStream_t st = (m == mmain || !multi_stream) ? stream : side[side_of(m)];
+      cudaStream_t st = (m == mmain || !multi_stream || serial_prof) ? stream : side[side_of(m)];
       if (st != stream && !forked) {
         CUDA_OK(cudaEventRecord(ev_fork, stream));
         forked = true;

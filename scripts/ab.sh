@@ -1,6 +1,6 @@
 #!/bin/bash
 # usage (GPU box): scripts/ab.sh "<variant list>" "<env settings list, ';'-separated>" -- A/B of library variants
-P='import sys,json; d=json.loads(sys.stdin.read().strip().split(chr(10))[-1]); print("%.0f Mcells/s %.4f ms/step (prof %.4f) e2e %.0f | " % (d["value"], d["ms_per_step"], d.get("ms_per_step_with_kernel_events",0), d["e2e"]["value"]) + " ".join("%s=%.4f" % (k["name"].split("<")[1][:14], k["total_ms"]/max(k["launches"],1)) for k in d["kernels"]))'
+P='import sys,json; d=json.loads(sys.stdin.read().strip().split(chr(10))[-1]); print("%.0f Mcells/s %.4f ms/step (prof %.4f) e2e %.0f | " % (d["value"], d["ms_per_step"], d.get("ms_per_step_serialised_with_kernel_events",0), d["e2e"]["value"]) + " ".join("%s=%.4f" % (k["name"].split("<")[1][:14], k["total_ms"]/max(k["launches"],1)) for k in d["kernels"]))'
 VARS=${1:-default}
 WL=${2:-"waveguide_mode sphere uled"}
 for v in $VARS; do

@@ -1,0 +1,130 @@
+"""GPU: every execution-mode switch of the library computes the same numbers.
+
+The switches only change how the same arithmetic is scheduled (streams vs. programmatic
+dependent launch with per-z-chunk dependency counters, axis-specialised PML kernels, skipping
+the material loads on tiles with constant material, tile/z-segment sizes), so the results must
+be bit-identical to the default mode, and within the north-star tolerance of the CPU oracle.
+"""
+import contextlib
+import os
+
+import numpy as np
+import pytest
+
+import khronos_b200 as kb
+from common import Pair, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+CW = kb.ContinuousWaveSource(fcen=1.0)
+
+
+@contextlib.contextmanager
+def env(**kw):
+    old = {k: os.environ.get(k) for k in kw}
+    os.environ.update({k: str(v) for k, v in kw.items()})
+    try:
+        yield
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _scene(dtype=np.float32):
+    """Piecewise-constant eps with one random block (uniform and non-uniform tiles), PML on all
+    axes, a Drude slab, a plane source and a point source, two DFT monitors."""
+    rng = np.random.default_rng(7)
+    N = (72, 44, 48)
+    eps = [np.full(N, 1.0, dtype=dtype) for _ in range(3)]
+    for e in eps:
+        e[:, :, 24:] = dtype(1.0 / 2.25)
+        e[30:40, 10:20, 10:30] = (1.0 / rng.uniform(1.0, 4.0, (10, 10, 20))).astype(dtype)
+    sg = np.zeros(N, dtype=dtype)
+    sg[20:50, 12:30, 30:34] = 1.2
+    kw = dict(sources=[(kb.EX, [0, 0, -0.9], [3.0, 2.0, 0], CW), (kb.HZ, [0.4, 0.2, 0.5], [0, 0, 0], CW)],
+              monitors=[(kb.EX, [0, 0, 0.3], [5.0, 3.0, 0], [0.9, 1.0], 1), (kb.HY, [0, 0.1, 0], [4.0, 0, 3.0], [1.0], 2)],
+              eps_inv=eps, poles=[(0.0, 0.3, sg)])
+    return ([7.2, 4.4, 4.8], 10, [1.0, 1.0, 1.0], dtype), kw
+
+
+def _run_gpu(nsteps, dtype=np.float32, **envkw):
+    args, kw = _scene(dtype)
+    with env(**envkw):
+        p = Pair(*args, **kw)
+    p.k.step(nsteps)
+    p.k.sync()
+    fields = [p.k.get_field(c).copy() for c in range(6)]
+    dfts = [np.array(p.k.get_dft(m)) for m in p.kmon]
+    p.k.close()
+    return p, fields, dfts
+
+
+MODES = [
+    dict(KHR_CHAIN=1),
+    dict(KHR_CHAIN=1, KHR_ZSEG=3),
+    dict(KHR_AXIS_SPEC=1),
+    dict(KHR_AXIS_SPEC=1, KHR_CHAIN=1),
+    dict(KHR_UNIFORM_TILES=0),
+    dict(KHR_MULTI_STREAM=0),
+    dict(KHR_ZSEG=5, KHR_ZSEG_FULL=1),
+    dict(KHR_TAIL_ZN=2, KHR_SORT_ITEMS=1),
+]
+
+
+@pytest.fixture(scope="module")
+def baseline():
+    return _run_gpu(60)
+
+
+@pytest.mark.parametrize("mode", MODES, ids=lambda m: ",".join("%s=%s" % kv for kv in m.items()))
+def test_mode_is_bit_identical_to_default(baseline, mode):
+    _, f0, d0 = baseline
+    _, f1, d1 = _run_gpu(60, **mode)
+    for c in range(6):
+        assert np.array_equal(f0[c], f1[c]), ("field", c, rel_l2(f1[c], f0[c]))
+    for a, b in zip(d0, d1):
+        assert np.array_equal(a, b), ("dft", rel_l2(b, a))
+
+
+def test_default_mode_matches_oracle(baseline):
+    p, f0, d0 = baseline
+    p.o.step(60)
+    num = den = 0.0
+    for c in range(6):
+        b = p.o.get_field(c).astype(np.float64)
+        num += np.sum((f0[c].astype(np.float64) - b) ** 2)
+        den += np.sum(b ** 2)
+    assert np.sqrt(num / den) < 1e-5
+    for a, om in zip(d0, p.omon):
+        assert rel_l2(a, p.o.get_dft(om)) < 1e-5
+
+
+def test_chain_mode_float64_matches_oracle():
+    args, kw = _scene(np.float64)
+    with env(KHR_CHAIN=1):
+        p = Pair(*args, **kw)
+    p.step(40)
+    assert p.total_field_error() < 1e-12
+    for km, om in zip(p.kmon, p.omon):
+        assert rel_l2(p.k.get_dft(km), p.o.get_dft(om)) < 1e-12
+
+
+def test_uniform_tiles_are_detected():
+    """The planner must mark constant-material tiles (and only those): with a constant eps array
+    every E tile is uniform; the kernel statistics expose the count."""
+    N = (64, 32, 24)
+    eps = [np.full(N, 0.5, dtype=np.float32) for _ in range(3)]
+    p = Pair([6.4, 3.2, 2.4], 10, [0.5, 0.5, 0.5], np.float32, sources=[(kb.EZ, [0, 0, 0], [0, 0, 0], CW)], eps_inv=eps)
+    st = [s for s in p.k.kernel_stats() if ",E," in s["name"]]
+    assert st and all(s["uniform_ctas"] == s["ctas"] for s in st), st
+    sth = [s for s in p.k.kernel_stats() if ",H," in s["name"]]
+    assert all(s["uniform_ctas"] == 0 for s in sth)
+    eps[1][10, 5, 7] = 0.25
+    q = Pair([6.4, 3.2, 2.4], 10, [0.5, 0.5, 0.5], np.float32, sources=[(kb.EZ, [0, 0, 0], [0, 0, 0], CW)], eps_inv=eps)
+    st = [s for s in q.k.kernel_stats() if ",E," in s["name"]]
+    assert sum(s["ctas"] - s["uniform_ctas"] for s in st) == 1, st
+    q.step(30)
+    assert q.total_field_error() < 1e-5
