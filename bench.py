@@ -228,9 +228,16 @@ def main_ours(args):
         h2d += 32 * len(sim.source_ids)
         sim.monitor_norms()  # stop_when_dft_decayed's per-step convergence metric (cached between DFT updates)
         d2h += 8 * len(sim.dft_monitors) / max(1, sim.dft_monitors[0].decimation if sim.dft_monitors else 1)
+    # results the user reads after the run: get_flux of every flux monitor (reduced on the device,
+    # nf doubles each; boxes split across ranks are read as arrays instead), Array(md.fields) of
+    # every other DFT monitor (FluxMonitor.jl:92-102)
     out_bytes = 0
-    for m in sim.dft_monitors:
-        out_bytes += sim.get_dft(m).size * 2 * np.dtype(dtype).itemsize
+    for m in sim.monitors:
+        if isinstance(m, kb.FluxMonitor) and world == 1:
+            out_bytes += sim.get_flux(m).size * 8
+        else:
+            for dm in (m.monitors if isinstance(m, kb.FluxMonitor) else [m]):
+                out_bytes += sim.get_dft(dm).size * 2 * np.dtype(dtype).itemsize
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -285,7 +292,7 @@ def main_ours(args):
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "Mcells/s", "h2d_bytes_per_step": h2d / e2e_steps,
                     "d2h_bytes_per_step": (d2h + out_bytes) / e2e_steps,
-                    "what": "sim.step(1) through the Python API/C ABI per step + host source amplitudes in + DFT norms out, monitors read at the end"},
+                    "what": "sim.step(1) through the Python API/C ABI per step + host source amplitudes in + DFT norms out; get_flux / DFT arrays read at the end"},
             "roofline": roof, "cpu_baseline": cpu, "clocks": sampler.summary(),
             "ms_per_step_serialised_with_kernel_events": ms_profiled / args.steps,
             "kernels": [{k: s[k] for k in ("name", "launches", "total_ms", "ctas", "uniform_ctas")} for s in stats]}

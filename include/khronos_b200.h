@@ -98,6 +98,14 @@ int32_t khr_set_sources_active(khr_ctx* ctx, int32_t mode /* -1 auto, 0 off, 1 o
 int32_t khr_monitor_register(khr_ctx* ctx, int32_t comp, const int32_t start[3], const int32_t end[3], int32_t nfreq,
                              const double* freqs, int32_t decimation, int32_t* monitor_id);
 
+/* Chunking.jl:1725-1770 _add_periodic_connections!: both sides of `axis` are Periodic (or
+ * Bloch with k = 0): after every half-step the last interior layer is copied to the lower
+ * ghost and the first interior layer to the upper ghost, for the three components of the
+ * group (z on several ranks: the wrap closes the halo ring).  The caller passes PML
+ * thickness 0 on such an axis (eff_boundaries, Boundaries.jl:100-110).  Before
+ * khr_finalize_plan.  Bloch k != 0 (complex fields) is not supported. */
+int32_t khr_set_periodic(khr_ctx* ctx, int32_t axis, int32_t on);
+
 /* builds region/work tables, allocates PML auxiliary slabs; call once after all
  * registrations (tail of prepare_simulation!, Simulation.jl:198-280) */
 int32_t khr_finalize_plan(khr_ctx* ctx);
@@ -137,6 +145,13 @@ int32_t khr_monitor_view(khr_ctx* ctx, int32_t monitor_id, void** dev_ptr, int64
 int32_t khr_monitor_norm(khr_ctx* ctx, int32_t monitor_id, double* norm);
 /* all monitors at once (count = number registered); values are cached between DFT updates */
 int32_t khr_monitor_norms(khr_ctx* ctx, double* norms, int32_t count);
+
+/* FluxMonitor.jl:92-156 get_flux(md): Poynting flux through the plane of four DFT monitors
+ * (ids ordered E1, E2, H1, H2 as init_flux_monitor creates them, :18-70) per frequency, reduced
+ * on the device with the reference's per-cell arithmetic (two-plane average and products in
+ * Complex{T}, area factor and sum in Float64); replaces Array(md.fields) x4 + the host loop.
+ * normal_axis 0..2.  Fails if the box is split across ranks. */
+int32_t khr_flux(khr_ctx* ctx, const int32_t monitor_ids[4], int32_t normal_axis, double* flux_out, int32_t nfreq);
 
 int32_t khr_sync(khr_ctx* ctx);
 int32_t khr_get_stream(khr_ctx* ctx, void** cuda_stream);

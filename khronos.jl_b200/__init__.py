@@ -10,7 +10,7 @@ from . import _lib, chunking, grid
 from .grid import EX, EY, EZ, HX, HY, HZ, Grid, interpolation_weight
 from .simulation import (Absorber, Ball, ContinuousWaveSource, Cuboid, CustomSource, DFTMonitor, DrudeSusceptibility,
                          FluxMonitor, GaussianPulseSource, LorentzianSusceptibility, Material, Object, Simulation,
-                         UniformSource, run, run_benchmark, step)
+                         UniformSource, run, run_benchmark, step, PML, Periodic, Bloch, PECBoundary, PMCBoundary)
 from ._lib import KhronosError, build
 from . import workloads
 
@@ -18,5 +18,6 @@ __all__ = [
     "Absorber", "Ball", "ContinuousWaveSource", "Cuboid", "CustomSource", "DFTMonitor", "DrudeSusceptibility",
     "FluxMonitor", "GaussianPulseSource", "LorentzianSusceptibility", "Material", "Object", "Simulation",
     "UniformSource", "run", "run_benchmark", "step", "Grid", "interpolation_weight", "KhronosError", "build",
-    "EX", "EY", "EZ", "HX", "HY", "HZ", "chunking", "grid", "workloads",
+    "EX", "EY", "EZ", "HX", "HY", "HZ", "chunking", "grid", "workloads", "PML", "Periodic", "Bloch", "PECBoundary",
+    "PMCBoundary",
 ]

@@ -59,6 +59,8 @@ _SIGNATURES = {
     "khr_set_sources_active": (_I, [_P, _I]),
     "khr_monitor_register": (_I, [_P, _I, C.POINTER(_I), C.POINTER(_I), _I, C.POINTER(C.c_double), _I, C.POINTER(_I)]),
     "khr_finalize_plan": (_I, [_P]),
+    "khr_set_periodic": (_I, [_P, _I, _I]),
+    "khr_flux": (_I, [_P, C.POINTER(_I), _I, C.POINTER(C.c_double), _I]),
     "khr_step": (_I, [_P, _I]),
     "khr_step_h": (_I, [_P]),
     "khr_step_e": (_I, [_P]),

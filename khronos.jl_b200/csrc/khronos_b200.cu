@@ -107,10 +107,12 @@ struct Base {
   virtual void monitor_view(int id, void** p, int64_t* dims) = 0;
   virtual double monitor_norm(int id) = 0;
   virtual void monitor_norms(double* out, int count) = 0;
+  virtual void flux(const int32_t* ids4, int normal_axis, double* out, int nfreq) = 0;
   virtual void sync() = 0;
   virtual void census(int64_t* c) = 0;
   virtual void set_profiling(int on) = 0;
   virtual int kernel_stat(int idx, khr_kernel_stat* out) = 0;
+  bool periodic[3] = {false, false, false};
   int64_t timestep = 0;
   int sources_mode = -1;
   bool sources_active = true;
@@ -469,6 +471,8 @@ struct Impl : Base {
 
   void finalize() override {
     if (finalized) throw std::string("khr_finalize_plan called twice");
+    // the wrap kernels are plain launches between the chain kernels: keep stream semantics simple
+    if (any_periodic()) pdl = false;
     // per-axis PML cell sets from both groups' profiles
     std::vector<char> pml[3];
     for (int a = 0; a < 3; ++a) {
@@ -759,8 +763,8 @@ struct Impl : Base {
     }
     if (g.nranks > 1) {
       // the plane that feeds the halo exchange gets its own thin range (boundary-first launch)
-      if (g.rank < g.nranks - 1) czv.push_back(N[2]);
-      if (g.rank > 0) czv.push_back(2);
+      if (rank_up() >= 0) czv.push_back(N[2]);
+      if (rank_dn() >= 0) czv.push_back(2);
     }
     const std::vector<Range> zr = split_ranges(zr0, czv);
     int zseg;
@@ -823,8 +827,8 @@ struct Impl : Base {
                     int mode = extras ? 8 : axm;
                     int phase = 1;
                     if (g.nranks > 1) {
-                      if (gq == 0 && g.rank < g.nranks - 1 && zs + zc - 1 == N[2]) phase = 0;
-                      if (gq == 1 && g.rank > 0 && zs == 1) phase = 0;
+                      if (gq == 0 && rank_up() >= 0 && zs + zc - 1 == N[2]) phase = 0;
+                      if (gq == 1 && rank_dn() >= 0 && zs == 1) phase = 0;
                     }
                     Table& tt = tab[gq][phase][mode];
                     tt.items.push_back(it);
@@ -1074,13 +1078,13 @@ struct Impl : Base {
       if (gq == 0) {
         // H: my top interior plane -> +z neighbour's lower ghost (E update reads H[k-1])
         T* f = F[3 + c];
-        if (g.rank < g.nranks - 1) NCCL_OK(g_nccl.Send(f + (size_t)PX * PY * N[2], cnt, /*ncclChar*/ 0, g.rank + 1, comm, comm_stream));
-        if (g.rank > 0) NCCL_OK(g_nccl.Recv(f, cnt, 0, g.rank - 1, comm, comm_stream));
+        if (rank_up() >= 0) NCCL_OK(g_nccl.Send(f + (size_t)PX * PY * N[2], cnt, /*ncclChar*/ 0, rank_up(), comm, comm_stream));
+        if (rank_dn() >= 0) NCCL_OK(g_nccl.Recv(f, cnt, 0, rank_dn(), comm, comm_stream));
       } else {
         // E: my bottom interior plane -> -z neighbour's upper ghost (H update reads E[k+1])
         T* f = F[c];
-        if (g.rank > 0) NCCL_OK(g_nccl.Send(f + (size_t)PX * PY, cnt, 0, g.rank - 1, comm, comm_stream));
-        if (g.rank < g.nranks - 1) NCCL_OK(g_nccl.Recv(f + (size_t)PX * PY * (N[2] + 1), cnt, 0, g.rank + 1, comm, comm_stream));
+        if (rank_dn() >= 0) NCCL_OK(g_nccl.Send(f + (size_t)PX * PY, cnt, 0, rank_dn(), comm, comm_stream));
+        if (rank_up() >= 0) NCCL_OK(g_nccl.Recv(f + (size_t)PX * PY * (N[2] + 1), cnt, 0, rank_up(), comm, comm_stream));
       }
     }
     NCCL_OK(g_nccl.GroupEnd());
@@ -1090,6 +1094,30 @@ struct Impl : Base {
     if (g.nranks <= 1) return;
     CUDA_OK(cudaStreamWaitEvent(stream, ev_comm, 0));
   }
+
+  // periodic axes: wrap the group's three components once its kernels are queued (the
+  // reference calls exchange_halos! at the end of step_H_fused! / step_E_fused!, before the
+  // DFT update).  x and y are always local to the slab; z is local only on a single rank,
+  // otherwise the wrap travels with the halo exchange (ring, post_halo).
+  void wrap_periodic(int gq) {
+    T* f[3];
+    for (int d = 0; d < 3; ++d) f[d] = gq == 0 ? F[3 + d] : F[d];
+    const long long st[3] = {1, (long long)PX, (long long)PX * PY};
+    for (int a = 0; a < 3; ++a) {
+      if (!periodic[a]) continue;
+      if (a == 2 && g.nranks > 1) continue;
+      const int t1 = (a + 1) % 3, t2 = (a + 2) % 3;
+      const long long cells = (long long)N[t1] * N[t2];
+      dim3 grid((unsigned)((cells + 255) / 256), 3);
+      wrap_kernel<T><<<grid, 256, 0, stream>>>(f[0], f[1], f[2], (long long)XO, st[a], st[t1], st[t2], N[a], N[t1], N[t2]);
+      ++launches;
+    }
+    CUDA_OK(cudaGetLastError());
+  }
+  bool any_periodic() const { return periodic[0] || periodic[1] || periodic[2]; }
+  // z neighbours of this rank (ring when z is periodic), -1 if none
+  int rank_up() const { return g.rank < g.nranks - 1 ? g.rank + 1 : (periodic[2] && g.nranks > 1 ? 0 : -1); }
+  int rank_dn() const { return g.rank > 0 ? g.rank - 1 : (periodic[2] && g.nranks > 1 ? g.nranks - 1 : -1); }
 
   void half_step(int gq, double t_src) {
     StepParams<T> p;
@@ -1105,6 +1133,7 @@ struct Impl : Base {
     } else {
       if (gq == 0) launch_group<0>(p, 1, marr); else launch_group<1>(p, 1, marr);
     }
+    if (any_periodic()) wrap_periodic(gq);
     if (gq == 1) for (auto& pl : poles) pl.cur = 1 - pl.cur;
     epochs[gq] += 1;
   }
@@ -1316,6 +1345,48 @@ struct Impl : Base {
     }
     for (int q = 0; q < n; ++q) out[q] = norm_cache[q];
   }
+  // FluxMonitor.jl:92-156 get_flux on the device: only nf doubles cross PCIe instead of the
+  // four DFT arrays (Array(md.fields), FluxMonitor.jl:99-102)
+  double* d_flux = nullptr;
+  size_t d_flux_cap = 0;
+  void flux(const int32_t* ids4, int normal_axis, double* out, int nfreq) override {
+    need_final();
+    if (normal_axis < 0 || normal_axis > 2) throw std::string("khr_flux: normal axis must be 0, 1 or 2");
+    FluxArgs<T> a;
+    a.normal = normal_axis;
+    a.t1 = normal_axis == 0 ? 1 : 0;
+    a.t2 = normal_axis == 2 ? 1 : 2;
+    a.n1 = a.n2 = 1 << 30;
+    for (int q = 0; q < 4; ++q) {
+      if (ids4[q] < 0 || ids4[q] >= (int)monitors.size()) throw std::string("khr_flux: bad monitor id");
+      const Monitor& m = monitors[ids4[q]];
+      if ((int)m.freqs.size() != nfreq) throw std::string("khr_flux: the four monitors must share the frequency list");
+      if ((q < 2) != (m.comp < 3)) throw std::string("khr_flux: monitors must be ordered E1, E2, H1, H2");
+      if (g.nranks > 1 && (m.s[2] < g.z_start || m.e[2] > g.z_start + N[2] - 1 + (g.rank == g.nranks - 1 ? 1 : 0)))
+        throw std::string("khr_flux: the monitor box is split across ranks; reduce the DFT arrays first "
+                          "(distributed.reduce_dft) and use the host formula");
+      a.M[q] = m.M;
+      for (int d = 0; d < 3; ++d) a.n[q][d] = m.n[d];
+      if (m.n[normal_axis] < 1) throw std::string("khr_flux: empty monitor box");
+      a.n1 = std::min(a.n1, m.n[a.t1]);
+      a.n2 = std::min(a.n2, m.n[a.t2]);
+    }
+    a.nf = nfreq;
+    a.dA = (double)dl[a.t1] * (double)dl[a.t2];
+    if (a.n1 < 1 || a.n2 < 1) { for (int k = 0; k < nfreq; ++k) out[k] = 0.0; return; }
+    const int nblocks = (int)std::min<long long>(((long long)a.n1 * a.n2 + 255) / 256, 256);
+    const size_t need = (size_t)nfreq * (nblocks + 1);
+    if (need > d_flux_cap) {
+      d_flux = (double*)dalloc((sizeof(double) * need + sizeof(T) - 1) / sizeof(T), false);
+      d_flux_cap = need;
+    }
+    flux_kernel<T><<<dim3((unsigned)nblocks, (unsigned)nfreq), 256, 0, stream>>>(a, d_flux + nfreq);
+    flux_finish_kernel<<<(nfreq + 63) / 64, 64, 0, stream>>>(d_flux + nfreq, nblocks, nfreq, d_flux);
+    CUDA_OK(cudaGetLastError());
+    launches += 2;
+    CUDA_OK(cudaMemcpyAsync(out, d_flux, sizeof(double) * nfreq, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+  }
   double* d_norm = nullptr;
   double monitor_norm(int id) override {
     if (id < 0 || id >= (int)monitors.size()) throw std::string("bad monitor id");
@@ -1454,6 +1525,12 @@ int32_t khr_monitor_register(khr_ctx* ctx, int32_t comp, const int32_t start[3],
   if (comp < 0 || comp > 5 || !start || !end || nfreq < 1 || !freqs) return khr::fail("bad argument");
   KHR_TRY({ int id = ctx->impl->monitor_register(comp, start, end, nfreq, freqs, decimation); if (monitor_id) *monitor_id = id; })
 }
+int32_t khr_set_periodic(khr_ctx* ctx, int32_t axis, int32_t on) {
+  NEED_CTX
+  if (axis < 0 || axis > 2) return khr::fail("axis must be 0, 1 or 2");
+  ctx->impl->periodic[axis] = on != 0;
+  return 0;
+}
 int32_t khr_finalize_plan(khr_ctx* ctx) {
   NEED_CTX
   KHR_TRY(ctx->impl->finalize())
@@ -1529,6 +1606,11 @@ int32_t khr_monitor_norm(khr_ctx* ctx, int32_t monitor_id, double* norm) {
 int32_t khr_monitor_norms(khr_ctx* ctx, double* norms, int32_t count) {
   NEED_CTX
   KHR_TRY(ctx->impl->monitor_norms(norms, count))
+}
+int32_t khr_flux(khr_ctx* ctx, const int32_t monitor_ids[4], int32_t normal_axis, double* flux_out, int32_t nfreq) {
+  NEED_CTX
+  if (!monitor_ids || !flux_out || nfreq < 1) return khr::fail("bad argument");
+  KHR_TRY(ctx->impl->flux(monitor_ids, normal_axis, flux_out, nfreq))
 }
 int32_t khr_sync(khr_ctx* ctx) {
   NEED_CTX

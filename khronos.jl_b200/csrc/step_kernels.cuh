@@ -368,6 +368,21 @@ __global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(c
         pf_l2(p.W[2] + zsn); pf_l2(p.U[1] + zsn);
       }
     }
+    if constexpr (EXTRAS) {
+      // the pole / conductivity arrays are read through sigma-dependent chains: make them L2 hits
+      if constexpr (GROUP == 1) {
+        for (int q = 0; q < p.npole; ++q) {
+          pf_l2(p.pole[q].sigma + nm);
+#pragma unroll
+          for (int d = 0; d < 3; ++d) { pf_l2(p.pole[q].Pc[d] + nm); pf_l2(p.pole[q].Pp[d] + nm); }
+        }
+        if (p.npole > 0 && p.Dst[0] != nullptr) { pf_l2(p.Dst[0] + nm); pf_l2(p.Dst[1] + nm); pf_l2(p.Dst[2] + nm); }
+      }
+      if (p.sigD[0] != nullptr) {
+        pf_l2(p.sigD[0] + nm); pf_l2(p.sigD[1] + nm); pf_l2(p.sigD[2] + nm);
+        if (p.C[0] != nullptr) { pf_l2(p.C[0] + nm); pf_l2(p.C[1] + nm); pf_l2(p.C[2] + nm); }
+      }
+    }
   };
 
   // ---- chain mode: wait until the other field group has finished the z chunks this tile reads
@@ -804,6 +819,89 @@ __global__ void __launch_bounds__(256) dft_kernel(const MonDesc<T>* __restrict__
     mp[0] = re + bt.ph_re[off + k] * f;
     mp[1] = im + bt.ph_im[off + k] * f;
   }
+}
+
+// ----------------------------------------------------------------------------
+// Periodic wrap-around of one axis (Chunking.jl:1725-1770, single-chunk form): for the three
+// components of the field group just updated, last interior layer N -> ghost 0 and first
+// interior layer 1 -> ghost N+1, over the transverse cells 1..N (send / recv ranges of
+// Chunking.jl:1825-1852).  `sa` is the element stride of the wrapped axis, `s1`, `s2` those
+// of the transverse axes; `base` the offset of cell (0,0,0).
+// ----------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256) wrap_kernel(T* f0, T* f1, T* f2, long long base, long long sa, long long s1,
+                                                   long long s2, int n_axis, int n1, int n2) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (long long)n1 * n2) return;
+  const int a = (int)(q % n1) + 1, b = (int)(q / n1) + 1;
+  const long long o = base + s1 * a + s2 * b;
+  T* f = blockIdx.y == 0 ? f0 : (blockIdx.y == 1 ? f1 : f2);
+  f[o] = f[o + sa * n_axis];              // ghost 0    <- cell N
+  f[o + sa * (n_axis + 1)] = f[o + sa];   // ghost N+1  <- cell 1
+}
+
+// ----------------------------------------------------------------------------
+// Poynting flux through a monitor plane (FluxMonitor.jl:92-156 get_flux), on the device:
+//   S(f) = sum_cells real(E1 conj(H2) - E2 conj(H1)) * dA
+// with the reference's arithmetic per cell (two-plane average and the complex products in
+// Complex{T}, the area factor and the sum in Float64).  Deterministic: per-block partial
+// sums, then one thread per frequency adds the partials in order.
+// ----------------------------------------------------------------------------
+template <class T>
+struct FluxArgs {
+  const T* M[4];     // e1, e2, h1, h2 accumulators, complex interleaved (nx,ny,nz,nf)
+  int n[4][3];       // their box extents
+  int normal, t1, t2, n1, n2, nf;
+  double dA;
+};
+
+template <class T>
+__device__ __forceinline__ void flux_val(const FluxArgs<T>& a, int m, int i1, int i2, int kf, T& re, T& im) {
+  const int* n = a.n[m];
+  const size_t ncell = (size_t)n[0] * n[1] * n[2];
+  int idx[3];
+  idx[a.t1] = i1; idx[a.t2] = i2; idx[a.normal] = 0;
+  const size_t c0 = (size_t)kf * ncell + (size_t)idx[0] + (size_t)n[0] * ((size_t)idx[1] + (size_t)n[1] * idx[2]);
+  re = a.M[m][2 * c0]; im = a.M[m][2 * c0 + 1];
+  if (n[a.normal] >= 2) {  // _avg_dim: (f[1] + f[2]) / 2 in Complex{T}
+    idx[a.normal] = 1;
+    const size_t c1 = (size_t)kf * ncell + (size_t)idx[0] + (size_t)n[0] * ((size_t)idx[1] + (size_t)n[1] * idx[2]);
+    re = (re + a.M[m][2 * c1]) / T(2);
+    im = (im + a.M[m][2 * c1 + 1]) / T(2);
+  }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) flux_kernel(const __grid_constant__ FluxArgs<T> a, double* __restrict__ partial) {
+  const int kf = blockIdx.y;
+  const long long ncell = (long long)a.n1 * a.n2;
+  double s = 0.0;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < ncell; q += (long long)gridDim.x * blockDim.x) {
+    const int i1 = (int)(q % a.n1), i2 = (int)(q / a.n1);
+    T e1r, e1i, e2r, e2i, h1r, h1i, h2r, h2i;
+    flux_val(a, 0, i1, i2, kf, e1r, e1i); flux_val(a, 1, i1, i2, kf, e2r, e2i);
+    flux_val(a, 2, i1, i2, kf, h1r, h1i); flux_val(a, 3, i1, i2, kf, h2r, h2i);
+    const T re1 = e1r * h2r + e1i * h2i;   // real(et1 * conj(ht2))
+    const T re2 = e2r * h1r + e2i * h1i;   // real(et2 * conj(ht1))
+    s += (double)(re1 - re2) * a.dA;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  __shared__ double ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int q = 0; q < 8; ++q) t += ws[q];
+    partial[(size_t)kf * gridDim.x + blockIdx.x] = t;
+  }
+}
+
+__global__ void flux_finish_kernel(const double* __restrict__ partial, int nblocks, int nf, double* __restrict__ out) {
+  const int kf = blockIdx.x * blockDim.x + threadIdx.x;
+  if (kf >= nf) return;
+  double t = 0;
+  for (int q = 0; q < nblocks; ++q) t += partial[(size_t)kf * nblocks + q];
+  out[kf] = t;
 }
 
 // sum of squares (Simulation.jl:440-445 stop_when_dft_decayed reduces |M|^2 every step)

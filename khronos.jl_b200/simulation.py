@@ -151,6 +151,32 @@ class Object:
         self.shape, self.material = shape, material
 
 
+# boundary conditions (DataStructures.jl:150-161)
+class PML:
+    code = 0
+
+
+class Periodic:
+    code = 1
+
+
+class Bloch:
+    """Bloch(k): only k == 0 (plain periodicity, real fields) is on the B200 path; k != 0 needs
+    complex fields (Fields.jl:147-159) and is rejected."""
+    code = 1
+
+    def __init__(self, k=0.0):
+        self.k = float(k)
+
+
+class PECBoundary:
+    code = 2
+
+
+class PMCBoundary:
+    code = 3
+
+
 class Absorber:
     """Boundaries.jl:17-21."""
 
@@ -215,8 +241,25 @@ class Simulation:
 
     def __init__(self, cell_size, cell_center, resolution, sources, boundaries=None, absorbers=None, geometry=None,
                  monitors=None, Courant=0.5, dtype=np.float32, device=0, rank=0, nranks=1, eps_inv=None, mu_inv=None,
-                 sigma_D=None, sigma_B=None, poles=None):
+                 sigma_D=None, sigma_B=None, poles=None, boundary_conditions=None):
         self.grid = Grid(cell_size, cell_center, resolution, Courant, dtype)
+        # boundary_conditions (DataStructures.jl:725): per axis [minus, plus] of PML / Periodic /
+        # Bloch / PECBoundary / PMCBoundary instances (or classes); None == PML everywhere
+        self.bc_codes = None
+        self.periodic = [False, False, False]
+        if boundary_conditions is not None:
+            codes = []
+            for axis_bcs in boundary_conditions:
+                for bc in axis_bcs:
+                    if isinstance(bc, Bloch) and bc.k != 0.0:
+                        raise _lib.KhronosError("Bloch(k != 0) needs complex fields (Fields.jl:147-159): not "
+                                                "supported by the B200 path")
+                    codes.append(int(bc.code))
+            if len(codes) != 6:
+                raise ValueError("boundary_conditions must be three [minus, plus] pairs")
+            self.bc_codes = codes
+            # wrap-around needs both sides periodic (Chunking.jl:1730-1733)
+            self.periodic = [codes[2 * a] == 1 and codes[2 * a + 1] == 1 for a in range(3)]
         self.T = self.grid.T
         self.sources = list(sources or [])
         self.boundaries = None if boundaries is None else [[float(a), float(b)] for a, b in boundaries]
@@ -369,9 +412,17 @@ class Simulation:
         self.slabs = chunking.z_slab_partition(g, self.boundaries, self.nranks)
         self.z_start, self.nz_local = self.slabs[self.rank]
         # boundaries (Boundaries.jl:99-164): sigma_B and sigma_D profiles are identical
+        # sigma profiles per field group [H, E].  Periodic / PEC / PMC sides drop their PML
+        # (eff_boundaries, Boundaries.jl:100-110); reference quirk: sigma_Dz is built from the
+        # raw sim.boundaries[3] (Boundaries.jl:154-161)
         self.sigma = None
         if self.boundaries is not None:
-            self.sigma = [g.compute_sigma(a, self.boundaries[a][0], self.boundaries[a][1]) for a in range(3)]
+            def eff(a, raw):
+                b = list(self.boundaries[a])
+                if self.bc_codes is not None and not raw:
+                    b = [0.0 if self.bc_codes[2 * a + sd] != 0 else b[sd] for sd in range(2)]
+                return b
+            self.sigma = [[g.compute_sigma(a, *eff(a, raw=(grp == 1 and a == 2))) for a in range(3)] for grp in range(2)]
         # geometry (Geometry.jl:450-663) + absorbers + poles
         arrays, poles = self._rasterize()
         for k, v in self.user_arrays.items():
@@ -445,7 +496,7 @@ class Simulation:
         if self.sigma is not None:
             for grp in (_lib.GROUP_H, _lib.GROUP_E):
                 for a in range(3):
-                    s = np.ascontiguousarray(self.sigma[a])
+                    s = np.ascontiguousarray(self.sigma[grp][a])
                     _lib.check(L.khr_set_pml_sigma(ctx, grp, a, s.ctypes.data, s.size))
         arrays = self.material_arrays
         kinds = {"eps_inv": _lib.MAT_EPS_INV, "mu_inv": _lib.MAT_MU_INV, "sigma_D": _lib.MAT_SIGMA_D,
@@ -480,6 +531,9 @@ class Simulation:
             _lib.check(L.khr_monitor_register(ctx, m.component, i3(*m.start), i3(*m.end), len(m.frequencies), fr,
                                               m.decimation, C.byref(mid)))
             m.id = mid.value
+        for a in range(3):
+            if self.periodic[a]:
+                _lib.check(L.khr_set_periodic(ctx, a, 1))
         _lib.check(L.khr_finalize_plan(ctx))
         if self.nranks > 1:
             if comm_id is None:
@@ -651,8 +705,16 @@ class Simulation:
     def get_flux(self, fm, dft=None):
         """FluxMonitor.jl:92-156 get_flux: Σ Re(E1·conj(H2) − E2·conj(H1))·dA per frequency.
 
-        `dft` may carry the four (already rank-reduced) DFT arrays; default reads this rank's.
+        Default: reduced on the device (`khr_flux`), only the nf values come back.  `dft` may
+        carry the four (already rank-reduced, `distributed.reduce_dft`) DFT arrays of a box that
+        is split across ranks; those go through the same formula on the host.
         """
+        if dft is None:
+            ids = (C.c_int32 * 4)(*[m.id for m in fm.monitors])
+            nf = len(fm.frequencies)
+            out = (C.c_double * nf)()
+            _lib.check(_lib.lib().khr_flux(self.ctx, ids, fm.normal, out, nf))
+            return np.array(list(out), dtype=np.float64)
         T = self.T
         ct = np.complex64 if T is np.float32 else np.complex128
         arrs = dft if dft is not None else [self.get_dft(m) for m in fm.monitors]

@@ -16,6 +16,8 @@ def oracle_from_simulation(sim):
     g = sim.grid
     o = ko.OracleSim(sim.T, g.cell_size_user, g.cell_center, g.resolution, g.courant, sim.boundaries)
     assert tuple(o.N) == tuple(g.N)
+    if getattr(sim, "bc_codes", None) is not None:
+        o.set_boundary_conditions(sim.bc_codes)
     for key in ("eps_inv", "mu_inv", "sigma_D", "sigma_B"):
         arr = sim.material_arrays[key]
         if arr is not None:

@@ -256,6 +256,11 @@ struct Sim {
   double cell_size_u[3], cell_center[3], resolution, courant;
   bool has_boundaries = false;
   T pml[3][2];
+  // boundary_conditions (src/DataStructures.jl:150-161, :725): an axis whose two sides are
+  // Periodic (or Bloch with k = 0) gets wrap-around halo connections (src/Chunking.jl:1725-1770);
+  // Periodic / PEC / PMC sides also zero the PML thickness (src/Boundaries.jl:100-110)
+  bool periodic[3] = {false, false, false};
+  bool no_pml_side[3][2] = {{false, false}, {false, false}, {false, false}};
   // --- derived grid (src/DataStructures.jl:732-741) -------------------------
   int N[3];
   T cell_size[3], dl[3], dt;
@@ -323,7 +328,41 @@ struct Sim {
       for (int a = 0; a < 3; ++a) sigma[g][a].clear();
     if (!has_boundaries) return;
     for (int g = 0; g < 2; ++g)
-      for (int a = 0; a < 3; ++a) sigma[g][a] = compute_sigma(2 * N[a] + 1, dl[a], dt, pml[a][0], pml[a][1]);
+      for (int a = 0; a < 3; ++a) {
+        // eff_boundaries (Boundaries.jl:100-110); quirk: sigma_Dz is built from sim.boundaries[3],
+        // not from eff_boundaries (Boundaries.jl:154-161)
+        const bool raw = (g == 1 && a == 2);
+        T l0 = (no_pml_side[a][0] && !raw) ? T(0) : pml[a][0];
+        T l1 = (no_pml_side[a][1] && !raw) ? T(0) : pml[a][1];
+        sigma[g][a] = compute_sigma(2 * N[a] + 1, dl[a], dt, l0, l1);
+      }
+  }
+
+  // Single-chunk wrap-around of a periodic axis (src/Chunking.jl:1752-1770 with the send / recv
+  // ranges of :1825-1852 and the component clamp of :2184-2214): last interior layer N -> ghost 0,
+  // first interior layer 1 -> ghost N+1, transverse ranges 1..N, all three components of the group.
+  void wrap_periodic(int group) {
+    if (chunks.size() != 1) return;
+    Chunk<T>& c = chunks[0];
+    for (int axis = 0; axis < 3; ++axis) {
+      if (!periodic[axis]) continue;
+      for (int d = 0; d < 3; ++d) {
+        Arr3<T>& F = (group == 0) ? c.H[d] : c.E[d];
+        if (!F.ok()) continue;
+        int n[3] = {c.n[0], c.n[1], c.n[2]};
+        int t1 = (axis + 1) % 3, t2 = (axis + 2) % 3;
+        for (int b = 1; b <= n[t2]; ++b)
+          for (int a = 1; a <= n[t1]; ++a) {
+            int lo[3], hi[3], g0[3], g1[3];
+            lo[t1] = hi[t1] = g0[t1] = g1[t1] = a;
+            lo[t2] = hi[t2] = g0[t2] = g1[t2] = b;
+            hi[axis] = n[axis]; g0[axis] = 0;          // upper interior -> lower ghost
+            lo[axis] = 1;       g1[axis] = n[axis] + 1; // lower interior -> upper ghost
+            F.at(g0[0], g0[1], g0[2]) = F.at(hi[0], hi[1], hi[2]);
+            F.at(g1[0], g1[1], g1[2]) = F.at(lo[0], lo[1], lo[2]);
+          }
+      }
+    }
   }
 
   // src/utils.jl:139-170 yee shift (Float64 SVector built from T-typed halves)
@@ -774,6 +813,20 @@ struct Sim {
   }
 
   T field_at(int comp, int gi, int gj, int gk) const {
+    if (chunks.size() == 1) {
+      // single chunk: the monitor box is intersected with the chunk's *component* grid volume,
+      // which is one cell longer on the staggered axes (src/Chunking.jl:1036-1046,
+      // src/Monitors/Monitors.jl:293-326); that extra cell is the boundary / ghost cell N+1
+      // (always 0 behind a PEC wall, the wrapped copy of cell 1 on a periodic axis)
+      const Chunk<T>& c = chunks[0];
+      int st[3];
+      comp_stagger(comp, st);
+      const int g[3] = {gi, gj, gk};
+      for (int a = 0; a < 3; ++a)
+        if (g[a] < 1 || g[a] > c.n[a] + st[a]) return T(0);
+      const Arr3<T>& F = comp < 3 ? c.E[comp] : c.H[comp - 3];
+      return F.at(gi, gj, gk);
+    }
     int q = owner(gi, gj, gk);
     if (q < 0) return T(0);
     const Chunk<T>& c = chunks[q];
@@ -864,10 +917,12 @@ struct Sim {
     if (sources_active) step_sources(0, t);
     for (auto& c : chunks) { step_curl(c, 0); update_field(c, 0); }
     if (chunks.size() > 1) exchange_halos(0);
+    wrap_periodic(0);
     update_monitors(0, t);
     if (sources_active) step_sources(1, t_half);
     for (auto& c : chunks) { step_curl(c, 1); update_field(c, 1); }
     if (chunks.size() > 1) exchange_halos(1);
+    wrap_periodic(1);
     step_polarization();
     update_monitors(1, t_half);
     timestep += 1;
@@ -1125,6 +1180,18 @@ int ko_chunk_sigma(void* hv, int q, int group, int axis, double* out) {
 void ko_step(void* hv, int nsteps) {
   Handle* h = (Handle*)hv;
   DISPATCH(h, { for (int i = 0; i < nsteps; ++i) S.step(); });
+}
+
+// bc per side: 0 = PML (default), 1 = Periodic / Bloch(k = 0), 2 = PEC, 3 = PMC.  Must be called
+// before ko_prepare.  Wrap-around needs both sides of the axis periodic (Chunking.jl:1730-1733).
+void ko_set_boundary_conditions(void* hv, const int* bc6) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, {
+    for (int a = 0; a < 3; ++a) {
+      for (int sd = 0; sd < 2; ++sd) S.no_pml_side[a][sd] = bc6[2 * a + sd] != 0;
+      S.periodic[a] = bc6[2 * a] == 1 && bc6[2 * a + 1] == 1;
+    }
+  });
 }
 
 void ko_set_sources_active(void* hv, int v) {

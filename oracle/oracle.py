@@ -69,6 +69,7 @@ def lib():
         L.ko_chunk_sigma.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, dp]
         L.ko_step.argtypes = [C.c_void_p, C.c_int]
         L.ko_set_sources_active.argtypes = [C.c_void_p, C.c_int]
+        L.ko_set_boundary_conditions.argtypes = [C.c_void_p, ip]
         L.ko_timestep.restype = C.c_long
         L.ko_num_threads.restype = C.c_int
         L.ko_set_num_threads.argtypes = [C.c_int]
@@ -252,6 +253,11 @@ class OracleSim:
         mid = self.L.ko_add_dft(self.h, int(comp), sp, ep, len(f), fp, int(decimation))
         self._monitors.append((tuple(int(x) for x in (e - s + 1)), len(f)))
         return mid
+
+    def set_boundary_conditions(self, bc6):
+        """bc6: per (axis, side) 0 = PML, 1 = Periodic, 2 = PEC, 3 = PMC (before prepare)."""
+        b, bp = _i(np.asarray(bc6, dtype=np.int32).reshape(6))
+        self.L.ko_set_boundary_conditions(self.h, bp)
 
     # ---- run ----------------------------------------------------------------
     def prepare(self, mode="single", nranks=0):

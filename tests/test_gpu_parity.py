@@ -152,3 +152,35 @@ def test_no_silent_fallback_and_errors():
     assert L.khr_step(ctx, 1) != 0  # finalize not called
     assert b"finalize" in L.khr_last_error()
     L.khr_ctx_destroy(ctx)
+
+
+@pytest.mark.parametrize("normal", [0, 1, 2])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_device_flux_all_normals(normal, dtype):
+    """khr_flux (FluxMonitor.jl:92-156 on the device) against the oracle's get_flux and against the
+    same formula evaluated on the host from the four DFT arrays: the per-cell arithmetic is the
+    reference's, only the Float64 summation order differs."""
+    size = [2.0, 2.0, 2.0]
+    size[normal] = 0.0
+    center = [0.0, 0.0, 0.0]
+    center[normal] = 0.5
+    fm = kb.FluxMonitor(center, size, [0.9, 1.0, 1.1])
+    mons = [(m.component, m.center, m.size, m.frequencies, 1) for m in fm.monitors]
+    p = Pair([4, 4, 4], 10, [1.0, 1.0, 1.0], dtype, sources=[(kb.EZ, [0, 0, 0], [0, 0, 0], CW),
+                                                              (kb.EX, [0.2, -0.1, 0.3], [0, 0, 0], CW)], monitors=mons)
+    p.step(60)
+    fm.monitors = p.kmon
+    dev = p.k.get_flux(fm)
+    host = p.k.get_flux(fm, dft=[p.k.get_dft(m) for m in fm.monitors])
+    ora = np.asarray(p.o.flux(normal, p.omon))
+    assert rel_l2(dev, host) < 1e-12, (dev, host)
+    assert rel_l2(dev, ora) < TOL[dtype] * (10 if dtype is np.float64 else 1), (dev, ora)
+
+
+def test_device_flux_argument_errors():
+    fm = kb.FluxMonitor([0.5, 0, 0], [0, 2, 2], [1.0])
+    mons = [(m.component, m.center, m.size, m.frequencies, 1) for m in fm.monitors]
+    p = Pair([4, 4, 4], 10, [1.0, 1.0, 1.0], np.float32, sources=[(kb.EZ, [0, 0, 0], [0, 0, 0], CW)], monitors=mons)
+    fm.monitors = list(reversed(p.kmon))       # H monitors first: rejected
+    with pytest.raises(kb.KhronosError):
+        p.k.get_flux(fm)
