@@ -42,8 +42,10 @@ enum { KHR_F32 = 0, KHR_F64 = 1 };
 enum { KHR_EX = 0, KHR_EY = 1, KHR_EZ = 2, KHR_HX = 3, KHR_HY = 4, KHR_HZ = 5 };
 /* field groups: the reference's :H half-step (B/H from curl E) and :E half-step */
 enum { KHR_GROUP_H = 0, KHR_GROUP_E = 1 };
-/* per-voxel material arrays (Geometry.jl:460-477): kind*3 + component */
-enum { KHR_MAT_EPS_INV = 0, KHR_MAT_MU_INV = 1, KHR_MAT_SIGMA_D = 2, KHR_MAT_SIGMA_B = 3 };
+/* per-voxel material arrays (Geometry.jl:460-477).  KHR_MAT_CHI3: the Kerr coefficient of
+ * Geometry.jl:610-660 (one array on the centre grid, component 0), consumed by the correction of
+ * Dispersive.jl:127-173 that step! applies between the E update and the ADE update */
+enum { KHR_MAT_EPS_INV = 0, KHR_MAT_MU_INV = 1, KHR_MAT_SIGMA_D = 2, KHR_MAT_SIGMA_B = 3, KHR_MAT_CHI3 = 4 };
 /* time profiles (Sources/TimeSources.jl:61-64, 123-132); HOST = amplitude pushed
  * every step with khr_source_set_amplitude (CustomSourceData, :165-171) */
 enum { KHR_TIME_CW = 0, KHR_TIME_GAUSSIAN = 1, KHR_TIME_HOST = 2 };
@@ -152,6 +154,25 @@ int32_t khr_monitor_norms(khr_ctx* ctx, double* norms, int32_t count);
  * Complex{T}, area factor and sum in Float64); replaces Array(md.fields) x4 + the host loop.
  * normal_axis 0..2.  Fails if the box is split across ranks. */
 int32_t khr_flux(khr_ctx* ctx, const int32_t monitor_ids[4], int32_t normal_axis, double* flux_out, int32_t nfreq);
+
+/* Near2Far.jl:998-1031 compute_far_field at explicit observation points (:254-371 the host loop,
+ * :103-247 / :380-560 the KernelAbstractions kernels): surface-equivalence currents J = n x H,
+ * M = -n x E of the plane's four DFT monitors (ids ordered E1, E2, H1, H2, init_near2far_monitor
+ * :1137-1200) radiated with the full dyadic Green's function green3d! (:40-96).  All arithmetic
+ * in Float64 / ComplexF64 like the reference.  base_xyz: physical position of dft[1,1,1] of each
+ * monitor (md.e1_base, e2_base, h1_base, h2_base; Monitors.jl:398-420); freqs: md.frequencies;
+ * obs_xyz: nobs points (x,y,z); eh_out: ComplexF64 (nobs, 6, nfreq) column-major, interleaved. */
+int32_t khr_near2far(khr_ctx* ctx, const int32_t monitor_ids[4], int32_t normal_axis, double normal_sign, double medium_eps,
+                     double medium_mu, const double base_xyz[12], const double* freqs, int32_t nfreq, const double* obs_xyz,
+                     int32_t nobs, double* eh_out);
+
+/* ModeMonitor.jl:345-515 compute_mode_amplitudes, the two surface sums (:462-498): mode_fields =
+ * the mode profile already interpolated onto the DFT grid (:427-457), ComplexF64 [4][nfreq][n2][n1]
+ * (e1, e2, h1, h2; n1 fastest), n1 x n2 = the common tangential extent of the four monitors.
+ * out5: per frequency P_mode, re/im of overlap_plus, re/im of overlap_minus; the caller forms
+ * a± = overlap± / (4 P_mode) (:500-503). */
+int32_t khr_mode_overlap(khr_ctx* ctx, const int32_t monitor_ids[4], int32_t normal_axis, const double* mode_fields, int32_t n1,
+                         int32_t n2, int32_t nfreq, double* out5);
 
 int32_t khr_sync(khr_ctx* ctx);
 int32_t khr_get_stream(khr_ctx* ctx, void** cuda_stream);

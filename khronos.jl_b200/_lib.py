@@ -13,7 +13,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 KHR_F32, KHR_F64 = 0, 1
 GROUP_H, GROUP_E = 0, 1
-MAT_EPS_INV, MAT_MU_INV, MAT_SIGMA_D, MAT_SIGMA_B = 0, 1, 2, 3
+MAT_EPS_INV, MAT_MU_INV, MAT_SIGMA_D, MAT_SIGMA_B, MAT_CHI3 = 0, 1, 2, 3, 4
 TIME_CW, TIME_GAUSSIAN, TIME_HOST = 0, 1, 2
 
 
@@ -61,6 +61,9 @@ _SIGNATURES = {
     "khr_finalize_plan": (_I, [_P]),
     "khr_set_periodic": (_I, [_P, _I, _I]),
     "khr_flux": (_I, [_P, C.POINTER(_I), _I, C.POINTER(C.c_double), _I]),
+    "khr_near2far": (_I, [_P, C.POINTER(_I), _I, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double),
+                          C.POINTER(C.c_double), _I, C.POINTER(C.c_double), _I, C.POINTER(C.c_double)]),
+    "khr_mode_overlap": (_I, [_P, C.POINTER(_I), _I, C.POINTER(C.c_double), _I, _I, _I, C.POINTER(C.c_double)]),
     "khr_step": (_I, [_P, _I]),
     "khr_step_h": (_I, [_P]),
     "khr_step_e": (_I, [_P]),
@@ -93,7 +96,7 @@ _LIB = None
 
 def build(force=False):
     """Compile libkhronos_b200.so in-tree with nvcc for sm_100a (no GPU needed)."""
-    srcs = [os.path.join(CSRC, f) for f in ("khronos_b200.cu", "step_kernels.cuh")]
+    srcs = [os.path.join(CSRC, f) for f in ("khronos_b200.cu", "step_kernels.cuh", "post_kernels.cuh")]
     srcs.append(os.path.join(_HERE, "..", "include", "khronos_b200.h"))
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if force or stale:

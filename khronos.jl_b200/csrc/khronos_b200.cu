@@ -8,6 +8,7 @@
 // ============================================================================
 #include "../../include/khronos_b200.h"
 #include "step_kernels.cuh"
+#include "post_kernels.cuh"
 
 #include <dlfcn.h>
 
@@ -108,6 +109,9 @@ struct Base {
   virtual double monitor_norm(int id) = 0;
   virtual void monitor_norms(double* out, int count) = 0;
   virtual void flux(const int32_t* ids4, int normal_axis, double* out, int nfreq) = 0;
+  virtual void near2far(const int32_t* ids4, int normal_axis, double normal_sign, double eps, double mu, const double* base12,
+                        const double* freqs, int nfreq, const double* obs, int nobs, double* out) = 0;
+  virtual void mode_overlap(const int32_t* ids4, int normal_axis, const double* mode, int n1, int n2, int nfreq, double* out5) = 0;
   virtual void sync() = 0;
   virtual void census(int64_t* c) = 0;
   virtual void set_profiling(int on) = 0;
@@ -174,7 +178,10 @@ struct Impl : Base {
   T m_scalar[2] = {T(1), T(1)};
   T* sigM[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // [0]=sigma_B [1]=sigma_D
   T* Cst[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
-  T* Dst[3] = {nullptr, nullptr, nullptr};  // D on dispersive voxels
+  T* Dst[3] = {nullptr, nullptr, nullptr};  // D on dispersive / Kerr voxels
+  T* chi3 = nullptr;                        // Kerr coefficient (Geometry.jl:610-660), material layout
+  int chi3_box[6] = {1, 1, 1, 0, 0, 0};
+  std::vector<uint8_t> chi3_mask;
   T* W[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
   T* U[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
   size_t slab_elems[3] = {0, 0, 0};
@@ -391,6 +398,11 @@ struct Impl : Base {
   void set_material_array(int kind, int comp, const void* dense) override {
     if (finalized) throw std::string("khr_set_material_array after khr_finalize_plan");
     if (comp < 0 || comp > 2) throw std::string("component must be 0..2");
+    if (kind == KHR_MAT_CHI3) {
+      if (comp != 0) throw std::string("chi3 is one array on the centre grid: component must be 0");
+      chi3 = upload_material(dense, chi3_box, &chi3_mask);
+      return;
+    }
     int box[6];
     std::vector<uint8_t>* mk = nullptr;
     if (kind == KHR_MAT_SIGMA_D) mk = &sd_mask[1];
@@ -524,7 +536,18 @@ struct Impl : Base {
           sigM[gq][d] = dalloc(msize);
         }
       }
-    if (!poles.empty())
+    if (chi3) {
+      // A Kerr voxel rebuilds E from the stored D every step (KernelAbstractions path,
+      // ReferenceKernels.jl:468-512); inside the PML the D-eliminated cascade has no exact
+      // counterpart for a non-linear correction
+      for (int z = 1; z <= N[2]; ++z)
+        for (int y = 1; y <= N[1]; ++y)
+          for (int x = 1; x <= N[0]; ++x)
+            if (chi3_mask[(size_t)(x - 1) + (size_t)N[0] * ((size_t)(y - 1) + (size_t)N[1] * (z - 1))] &&
+                (pml[0][x] || pml[1][y] || pml[2][z]))
+              throw std::string("chi3 != 0 inside the PML is not supported (Kerr media must end before the PML)");
+    }
+    if (!poles.empty() || chi3)
       for (int d = 0; d < 3; ++d) Dst[d] = dalloc(msize);
     // coefficient vectors
     for (int gq = 0; gq < 2; ++gq)
@@ -667,6 +690,8 @@ struct Impl : Base {
       for (size_t q = 0; q < poles.size(); ++q)
         if (boxes_hit(poles[q].box, x0, x0 + xw - 1, y0, y0 + yh - 1, z0, z0 + zn - 1))
           b += (double)count_mask(pole_mask[q]) * (10 + (q == 0 ? 12 : 0)) * w;
+    if (gq == 1 && chi3 && boxes_hit(chi3_box, x0, x0 + xw - 1, y0, y0 + yh - 1, z0, z0 + zn - 1))
+      b += (double)count_mask(chi3_mask) * 7 * w;  // chi3 read + D read/write
     return b;
   }
 
@@ -759,6 +784,9 @@ struct Impl : Base {
       if (gq == 1)
         for (auto& pl : poles)
           if (pl.box[0] <= pl.box[3]) { Box b; for (int q = 0; q < 6; ++q) b.b[q] = pl.box[q]; b.src = false; boxes.push_back(b); }
+      if (gq == 1 && chi3 && chi3_box[0] <= chi3_box[3]) {
+        Box b; for (int q = 0; q < 6; ++q) b.b[q] = chi3_box[q]; b.src = false; boxes.push_back(b);
+      }
       for (auto& bx : boxes) { czv.push_back(bx.b[2]); czv.push_back(bx.b[5] + 1); }
     }
     if (g.nranks > 1) {
@@ -1040,6 +1068,7 @@ struct Impl : Base {
     p.npole = 0;
     for (int d = 0; d < 3; ++d) p.Dst[d] = (gq == 1) ? Dst[d] : nullptr;
     p.Tsrc = Tsrc[gq];
+    p.chi3 = (gq == 1) ? chi3 : nullptr;
     if (gq == 1)
       for (auto& pl : poles) {
         PoleDesc<T>& d = p.pole[p.npole++];
@@ -1262,9 +1291,9 @@ struct Impl : Base {
   }
   void field_write(int comp, const void* in) override {
     need_final();
-    if (comp < 3 && !poles.empty())
-      throw std::string("khr_field_write: writing E is not supported when dispersive poles are registered "
-                        "(the D / P history would be inconsistent); use khr_reset_fields");
+    if (comp < 3 && (!poles.empty() || chi3))
+      throw std::string("khr_field_write: writing E is not supported when dispersive poles or a Kerr coefficient "
+                        "are registered (the D / P history would be inconsistent); use khr_reset_fields");
     for (auto& s : sources)
       if ((s.comp >= 3) == (comp >= 3))
         throw std::string("khr_field_write: not supported for a field group that has sources registered "
@@ -1385,6 +1414,104 @@ struct Impl : Base {
     CUDA_OK(cudaGetLastError());
     launches += 2;
     CUDA_OK(cudaMemcpyAsync(out, d_flux, sizeof(double) * nfreq, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+  }
+  // the four monitors of a plane as the surface-integral kernels see them (shared by khr_flux,
+  // khr_near2far and khr_mode_overlap)
+  FluxArgs<T> surface_args(const char* who, const int32_t* ids4, int normal_axis, int nfreq) {
+    need_final();
+    if (normal_axis < 0 || normal_axis > 2) throw std::string(who) + ": normal axis must be 0, 1 or 2";
+    FluxArgs<T> a;
+    a.normal = normal_axis;
+    a.t1 = normal_axis == 0 ? 1 : 0;
+    a.t2 = normal_axis == 2 ? 1 : 2;
+    a.n1 = a.n2 = 1 << 30;
+    for (int q = 0; q < 4; ++q) {
+      if (ids4[q] < 0 || ids4[q] >= (int)monitors.size()) throw std::string(who) + ": bad monitor id";
+      const Monitor& m = monitors[ids4[q]];
+      if ((int)m.freqs.size() != nfreq) throw std::string(who) + ": the four monitors must share the frequency list";
+      if ((q < 2) != (m.comp < 3)) throw std::string(who) + ": monitors must be ordered E1, E2, H1, H2";
+      if (g.nranks > 1 && (m.s[2] < g.z_start || m.e[2] > g.z_start + N[2] - 1 + (g.rank == g.nranks - 1 ? 1 : 0)))
+        throw std::string(who) + ": the monitor box is split across ranks; reduce the DFT arrays first "
+                                 "(distributed.reduce_dft) and use the host formula";
+      a.M[q] = m.M;
+      for (int d = 0; d < 3; ++d) a.n[q][d] = m.n[d];
+      if (m.n[normal_axis] < 1) throw std::string(who) + ": empty monitor box";
+      a.n1 = std::min(a.n1, m.n[a.t1]);
+      a.n2 = std::min(a.n2, m.n[a.t2]);
+    }
+    a.nf = nfreq;
+    a.dA = (double)dl[a.t1] * (double)dl[a.t2];
+    return a;
+  }
+  double* scratch_f64(size_t need) {
+    if (need > d_flux_cap) {
+      d_flux = (double*)dalloc((sizeof(double) * need + sizeof(T) - 1) / sizeof(T), false);
+      d_flux_cap = need;
+    }
+    return d_flux;
+  }
+  // Near2Far.jl:254-371 / :380-560 compute_far_field at explicit observation points: EH (nobs, 6, nf)
+  // ComplexF64.  The DFT arrays stay on the device; obs in, 6 nobs nf complex numbers out.
+  void near2far(const int32_t* ids4, int normal_axis, double normal_sign, double eps, double mu, const double* base12,
+                const double* freqs, int nfreq, const double* obs, int nobs, double* out) override {
+    N2FArgs<T> a;
+    a.s = surface_args("khr_near2far", ids4, normal_axis, nfreq);
+    if (!(eps > 0) || !(mu > 0)) throw std::string("khr_near2far: medium eps and mu must be positive");
+    if (nobs < 1) throw std::string("khr_near2far: no observation points");
+    if (nfreq > 65535) throw std::string("khr_near2far: too many frequencies");
+    const size_t nout = (size_t)2 * 6 * nobs * nfreq;
+    if (a.s.n1 < 1 || a.s.n2 < 1) { for (size_t k = 0; k < nout; ++k) out[k] = 0.0; return; }
+    for (int q = 0; q < 4; ++q)
+      for (int d = 0; d < 3; ++d) a.base[q][d] = base12[3 * q + d];
+    a.d1 = (double)dl[a.s.t1]; a.d2 = (double)dl[a.s.t2];
+    a.ns = normal_sign; a.eps = eps; a.mu = mu;
+    a.nobs = nobs;
+    // enough CTAs to fill the GPU several times over even for a handful of observation points
+    const long long ncell = (long long)a.s.n1 * a.s.n2;
+    long long nchunk = (148 * 8 + (long long)nobs * nfreq - 1) / ((long long)nobs * nfreq);
+    nchunk = std::max<long long>(1, std::min<long long>(nchunk, (ncell + 255) / 256));
+    nchunk = std::min<long long>(nchunk, 65535);
+    a.nchunk = (int)nchunk;
+    const size_t n_part = (size_t)12 * nchunk * nfreq * nobs;
+    double* buf = scratch_f64(n_part + nout + (size_t)3 * nobs + nfreq);
+    double* d_part = buf;
+    double* d_out = d_part + n_part;
+    double* d_obs = d_out + nout;
+    double* d_fr = d_obs + (size_t)3 * nobs;
+    CUDA_OK(cudaMemcpyAsync(d_obs, obs, sizeof(double) * 3 * nobs, cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaMemcpyAsync(d_fr, freqs, sizeof(double) * nfreq, cudaMemcpyHostToDevice, stream));
+    a.obs = d_obs; a.freqs = d_fr;
+    near2far_kernel<T><<<dim3((unsigned)nobs, (unsigned)nfreq, (unsigned)nchunk), 256, 0, stream>>>(a, d_part);
+    const long long nt = (long long)nobs * nfreq * 6;
+    near2far_finish_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, stream>>>(d_part, (int)nchunk, nfreq, nobs, d_out);
+    CUDA_OK(cudaGetLastError());
+    launches += 2;
+    CUDA_OK(cudaMemcpyAsync(out, d_out, sizeof(double) * nout, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+  }
+  // ModeMonitor.jl:462-498: P_mode and the two overlap sums per frequency; out5 = nf x
+  // (P, re o+, im o+, re o-, im o-).  mode: ComplexF64 [4][nf][n2][n1] (e1, e2, h1, h2 on the DFT grid)
+  void mode_overlap(const int32_t* ids4, int normal_axis, const double* mode, int n1, int n2, int nfreq, double* out5) override {
+    FluxArgs<T> a = surface_args("khr_mode_overlap", ids4, normal_axis, nfreq);
+    if (n1 != a.n1 || n2 != a.n2)
+      throw std::string("khr_mode_overlap: the mode profile extent must equal the common tangential extent of the monitors (") +
+          std::to_string(a.n1) + " x " + std::to_string(a.n2) + ")";
+    if (nfreq > 65535) throw std::string("khr_mode_overlap: too many frequencies");
+    if (a.n1 < 1 || a.n2 < 1) { for (int k = 0; k < 5 * nfreq; ++k) out5[k] = 0.0; return; }
+    const size_t ncell = (size_t)n1 * n2;
+    const int nblocks = (int)std::min<size_t>((ncell + 255) / 256, 256);
+    const size_t n_mode = (size_t)2 * 4 * nfreq * ncell, n_part = (size_t)5 * nfreq * nblocks;
+    double* buf = scratch_f64(n_mode + n_part + (size_t)5 * nfreq);
+    double* d_mode = buf;
+    double* d_part = d_mode + n_mode;
+    double* d_out = d_part + n_part;
+    CUDA_OK(cudaMemcpyAsync(d_mode, mode, sizeof(double) * n_mode, cudaMemcpyHostToDevice, stream));
+    mode_overlap_kernel<T><<<dim3((unsigned)nblocks, (unsigned)nfreq), 256, 0, stream>>>(a, d_mode, d_part);
+    mode_overlap_finish_kernel<<<(5 * nfreq + 63) / 64, 64, 0, stream>>>(d_part, nblocks, nfreq, d_out);
+    CUDA_OK(cudaGetLastError());
+    launches += 2;
+    CUDA_OK(cudaMemcpyAsync(out5, d_out, sizeof(double) * 5 * nfreq, cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
   }
   double* d_norm = nullptr;
@@ -1611,6 +1738,19 @@ int32_t khr_flux(khr_ctx* ctx, const int32_t monitor_ids[4], int32_t normal_axis
   NEED_CTX
   if (!monitor_ids || !flux_out || nfreq < 1) return khr::fail("bad argument");
   KHR_TRY(ctx->impl->flux(monitor_ids, normal_axis, flux_out, nfreq))
+}
+int32_t khr_near2far(khr_ctx* ctx, const int32_t monitor_ids[4], int32_t normal_axis, double normal_sign, double medium_eps,
+                     double medium_mu, const double base_xyz[12], const double* freqs, int32_t nfreq, const double* obs_xyz,
+                     int32_t nobs, double* eh_out) {
+  NEED_CTX
+  if (!monitor_ids || !base_xyz || !freqs || !obs_xyz || !eh_out || nfreq < 1) return khr::fail("bad argument");
+  KHR_TRY(ctx->impl->near2far(monitor_ids, normal_axis, normal_sign, medium_eps, medium_mu, base_xyz, freqs, nfreq, obs_xyz, nobs, eh_out))
+}
+int32_t khr_mode_overlap(khr_ctx* ctx, const int32_t monitor_ids[4], int32_t normal_axis, const double* mode_fields, int32_t n1,
+                         int32_t n2, int32_t nfreq, double* out5) {
+  NEED_CTX
+  if (!monitor_ids || !mode_fields || !out5 || nfreq < 1) return khr::fail("bad argument");
+  KHR_TRY(ctx->impl->mode_overlap(monitor_ids, normal_axis, mode_fields, n1, n2, nfreq, out5))
 }
 int32_t khr_sync(khr_ctx* ctx) {
   NEED_CTX

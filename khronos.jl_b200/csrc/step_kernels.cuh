@@ -107,7 +107,8 @@ struct StepParams {
   // ADE
   int npole;
   PoleDesc<T> pole[MAXPOLE];
-  T* Dst[3];          // D kept on dispersive voxels (material layout), as the reference does
+  T* Dst[3];          // D kept on dispersive / Kerr voxels (material layout), as the reference does
+  const T* chi3;      // Kerr coefficient per voxel (material layout) or null; E group only
   T* Tsrc;            // B/D kept on source voxels (compact, one slot per (component, cell))
   // chain mode (one stream, programmatic dependent launch): per z chunk, done_*[c] counts the
   // work items of a field group that have finished since the last reset
@@ -376,7 +377,8 @@ __global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(c
 #pragma unroll
           for (int d = 0; d < 3; ++d) { pf_l2(p.pole[q].Pc[d] + nm); pf_l2(p.pole[q].Pp[d] + nm); }
         }
-        if (p.npole > 0 && p.Dst[0] != nullptr) { pf_l2(p.Dst[0] + nm); pf_l2(p.Dst[1] + nm); pf_l2(p.Dst[2] + nm); }
+        if (p.chi3 != nullptr) pf_l2(p.chi3 + nm);
+        if ((p.npole > 0 || p.chi3 != nullptr) && p.Dst[0] != nullptr) { pf_l2(p.Dst[0] + nm); pf_l2(p.Dst[1] + nm); pf_l2(p.Dst[2] + nm); }
       }
       if (p.sigD[0] != nullptr) {
         pf_l2(p.sigD[0] + nm); pf_l2(p.sigD[1] + nm); pf_l2(p.sigD[2] + nm);
@@ -553,7 +555,9 @@ __global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(c
         bool has_sd = false, use_c = false;
         bool pol_on[MAXPOLE];
         bool pol_any = false;
-        bool disp[4] = {false, false, false, false};  // cell carries a pole
+        bool disp[4] = {false, false, false, false};  // cell carries a pole or a Kerr coefficient: D is kept
+        V4<T> c3 = zero4<T>();                         // chi3 of the 4 cells
+        bool chi_any = false;
         int sslot[3][4];                               // flux-accumulator slot of a source voxel, -1 if none
         T su[3][4], pu[3][4];                          // unscaled S(t) and sum of P^n
 #pragma unroll
@@ -586,6 +590,11 @@ __global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(c
           }
           // polarisation: the stored E carries -eps^-1 P^{n-1}; this step puts -eps^-1 P^n
           if constexpr (GROUP == 1) {
+            if (p.chi3 != nullptr) {
+              c3 = ld4(p.chi3 + mbase);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { disp[e] |= (c3.v[e] != T(0)); chi_any |= (c3.v[e] != T(0)); }
+            }
 #pragma unroll
             for (int q = 0; q < MAXPOLE; ++q) {
               pol_on[q] = false;
@@ -664,7 +673,7 @@ __global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(c
           // (Kernels.jl:315,371: fPD present -> no D elimination): D += K (or the sigma_D stage),
           // E = eps^-1 * ((D + S) - P) (Helpers.jl:332-338).  |P| >> |eps E| in a metal, so
           // recomputing E from D each step avoids a random walk of the P round-off in E.
-          if (pol_any && p.Dst[0] != nullptr) {
+          if ((pol_any || chi_any) && p.Dst[0] != nullptr) {
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
               V4<T> dv = ld4(p.Dst[d] + mbase);
@@ -684,6 +693,22 @@ __global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(c
                 }
               }
               st4(p.Dst[d] + mbase, dv);
+            }
+          }
+        }
+        if constexpr (EXTRAS && GROUP == 1) {
+          // Kerr correction (Dispersive.jl:127-148): E <- E / (1 + chi3 |E|^2), the three components
+          // taken at the same array index, applied to the freshly rebuilt E = eps^-1 (D + S - P) and
+          // before the ADE update, which therefore sees the corrected E (Kernels.jl:76-83)
+          if (chi_any) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (c3.v[e] != T(0) && valid[e]) {
+                const T ex = fx.v[e], ey = fy.v[e], ez = fz.v[e];
+                const T e_sq = (ex * ex + ey * ey) + ez * ez;
+                const T corr = T(1) / (T(1) + c3.v[e] * e_sq);
+                fx.v[e] = ex * corr; fy.v[e] = ey * corr; fz.v[e] = ez * corr;
+              }
             }
           }
         }

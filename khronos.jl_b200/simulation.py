@@ -18,7 +18,7 @@ import numpy as np
 
 from . import _lib
 from . import chunking
-from .grid import EX, EY, EZ, HX, HY, HZ, Grid, component_stagger, interpolation_weight
+from .grid import CENTER, EX, EY, EZ, HX, HY, HZ, Grid, component_stagger, interpolation_weight
 
 # --------------------------------------------------------------------------
 # time profiles (src/Sources/TimeSources.jl)
@@ -122,10 +122,11 @@ def DrudeSusceptibility(gamma, sigma):
 
 
 class Material:
-    def __init__(self, epsilon=1.0, mu=1.0, sigma_D=0.0, sigma_B=0.0, susceptibilities=None):
+    def __init__(self, epsilon=1.0, mu=1.0, sigma_D=0.0, sigma_B=0.0, susceptibilities=None, chi3=None):
         self.epsilon, self.mu = float(epsilon), float(mu)
         self.sigma_D, self.sigma_B = float(sigma_D), float(sigma_B)
         self.susceptibilities = list(susceptibilities or [])
+        self.chi3 = None if chi3 is None else float(chi3)  # Kerr coefficient (DataStructures.jl:271)
 
 
 class Ball:
@@ -223,6 +224,26 @@ class FluxMonitor:
         ]
 
 
+class Near2FarMonitor(FluxMonitor):
+    """Near2FarMonitor (DataStructures.jl:441-455, init_near2far_monitor Near2Far.jl:1137-1200): the
+    same four tangential DFT monitors as a flux plane plus the far-field description."""
+
+    def __init__(self, center, size, frequencies, observation_points=None, theta=None, phi=None, r=1e6,
+                 normal_dir="+", medium_eps=1.0, medium_mu=1.0, decimation=1):
+        super().__init__(center, size, frequencies, decimation)
+        self.observation_points = None if observation_points is None else np.asarray(observation_points, dtype=np.float64)
+        self.theta = None if theta is None else np.asarray(theta, dtype=np.float64)
+        self.phi = None if phi is None else np.asarray(phi, dtype=np.float64)
+        self.r = float(r)
+        self.normal_sign = 1.0 if normal_dir in ("+", 1, +1.0) else -1.0
+        self.medium_eps, self.medium_mu = float(medium_eps), float(medium_mu)
+
+
+class ModeMonitor(FluxMonitor):
+    """ModeMonitor (DataStructures.jl:512-519): four tangential DFT monitors on a plane; the mode
+    profiles themselves come from the caller (the mode solver is outside the hot path)."""
+
+
 # --------------------------------------------------------------------------
 # Simulation
 # --------------------------------------------------------------------------
@@ -241,7 +262,7 @@ class Simulation:
 
     def __init__(self, cell_size, cell_center, resolution, sources, boundaries=None, absorbers=None, geometry=None,
                  monitors=None, Courant=0.5, dtype=np.float32, device=0, rank=0, nranks=1, eps_inv=None, mu_inv=None,
-                 sigma_D=None, sigma_B=None, poles=None, boundary_conditions=None):
+                 sigma_D=None, sigma_B=None, poles=None, boundary_conditions=None, chi3=None):
         self.grid = Grid(cell_size, cell_center, resolution, Courant, dtype)
         # boundary_conditions (DataStructures.jl:725): per axis [minus, plus] of PML / Periodic /
         # Bloch / PECBoundary / PMCBoundary instances (or classes); None == PML everywhere
@@ -269,6 +290,7 @@ class Simulation:
         self.device, self.rank, self.nranks = int(device), int(rank), int(nranks)
         self.user_arrays = {"eps_inv": eps_inv, "mu_inv": mu_inv, "sigma_D": sigma_D, "sigma_B": sigma_B}
         self.user_poles = list(poles or [])  # (omega_0, gamma, sigma_array) triples
+        self.user_chi3 = chi3                # dense (Nx,Ny,Nz) Kerr coefficient on the centre grid
         self.ctx = None
         self.is_prepared = False
         self.dft_monitors = []
@@ -288,7 +310,7 @@ class Simulation:
         cell i takes the material of the first object containing the component position."""
         T = self.T
         g = self.grid
-        arrays = {k: None for k in ("eps_inv", "mu_inv", "sigma_D", "sigma_B")}
+        arrays = {k: None for k in ("eps_inv", "mu_inv", "sigma_D", "sigma_B", "chi3")}
         poles = []
         if not self.geometry:
             return arrays, poles
@@ -319,6 +341,17 @@ class Simulation:
             arrays["sigma_D"] = paint(EX, "sigma_D", False)
         if need_sb:
             arrays["sigma_B"] = paint(HX, "sigma_B", False)
+        # Kerr coefficient on the centre grid (Geometry.jl:610-635): later objects first, earlier ones
+        # paint over them, objects without chi3 paint nothing
+        if any(o.material.chi3 is not None for o in self.geometry):
+            xs, ys, zs = self._coords(CENTER)
+            X, Y, Z = np.meshgrid(xs, ys, zs, indexing="ij", sparse=True)
+            a = np.zeros(shape, dtype=T)
+            for obj in reversed(self.geometry):
+                v = T(0) if obj.material.chi3 is None else T(obj.material.chi3)
+                if v != 0:
+                    a[np.broadcast_to(obj.shape.contains(X, Y, Z), shape)] = v
+            arrays["chi3"] = a
         # dispersive poles: sigma rasterised on the Ex grid, shared by x/y/z (Geometry.jl:1146-1177)
         uniq = []
         for obj in self.geometry:
@@ -428,6 +461,8 @@ class Simulation:
         for k, v in self.user_arrays.items():
             if v is not None:
                 arrays[k] = [np.array(x, dtype=T) for x in v]
+        if self.user_chi3 is not None:
+            arrays["chi3"] = np.array(self.user_chi3, dtype=T)
         arrays = self._apply_absorbers(arrays)
         poles = poles + [(w, gam, np.asarray(s, dtype=T)) for (w, gam, s) in self.user_poles]
         poles = [(w, gam, self._zero_pole_sigma_in_pml(s)) for (w, gam, s) in poles]
@@ -507,6 +542,9 @@ class Simulation:
             for d in range(3):
                 a = np.asfortranarray(arrays[k][d][:, :, zsl])
                 _lib.check(L.khr_set_material_array(ctx, kind, d, a.ctypes.data))
+        if arrays.get("chi3") is not None:
+            a = np.asfortranarray(arrays["chi3"][:, :, zsl])
+            _lib.check(L.khr_set_material_array(ctx, _lib.MAT_CHI3, 0, a.ctypes.data))
         for (w0, gam, s) in self.poles:
             a = np.asfortranarray(s[:, :, zsl])
             pid = C.c_int32()
@@ -738,6 +776,92 @@ class Simulation:
         re2 = e2.real * h1.real + e2.imag * h1.imag
         s = (re1 - re2).astype(np.float64) * dA
         return s.sum(axis=(0, 1))
+
+    def _plane_bases(self, fm):
+        """md.e1_base, e2_base, h1_base, h2_base (Monitors.jl:398-420): physical position of
+        dft[1,1,1] = component origin + (start_idx - 1) * Δ, Float64."""
+        g = self.grid
+        out = []
+        for m in fm.monitors:
+            o = g.component_origin(m.component)
+            out.append([o[a] + (float(m.start[a]) - 1.0) * float(g.dl[a]) for a in range(3)])
+        return np.asarray(out, dtype=np.float64)
+
+    def far_field_points(self, fm):
+        """Observation points of compute_far_field (Near2Far.jl:1004-1021): theta/phi/r grid (phi
+        outer, theta inner) or the explicit list."""
+        if fm.theta is not None and fm.phi is not None:
+            pts = [[fm.r * math.sin(t) * math.cos(p), fm.r * math.sin(t) * math.sin(p), fm.r * math.cos(t)]
+                   for p in fm.phi for t in fm.theta]
+            return np.asarray(pts, dtype=np.float64)
+        if fm.observation_points is not None:
+            return np.asarray(fm.observation_points, dtype=np.float64).reshape(-1, 3)
+        raise ValueError("Near2FarMonitorData must have either theta/phi or observation_points")
+
+    def compute_far_field(self, fm, obs_points=None):
+        """Near2Far.jl:998-1031 compute_far_field (free-space Green's function; layer stacks are not
+        on this path): EH complex128 (nobs, 6, nf), evaluated on the device (`khr_near2far`)."""
+        obs = np.ascontiguousarray(self.far_field_points(fm) if obs_points is None
+                                   else np.asarray(obs_points, dtype=np.float64).reshape(-1, 3))
+        nobs, nf = obs.shape[0], len(fm.frequencies)
+        ids = (C.c_int32 * 4)(*[m.id for m in fm.monitors])
+        bases = np.ascontiguousarray(self._plane_bases(fm).reshape(12))
+        freqs = np.asarray([float(f) for f in fm.frequencies], dtype=np.float64)  # Float64.(monitor.frequencies)
+        out = np.zeros(2 * nobs * 6 * nf, dtype=np.float64)
+        dp = C.POINTER(C.c_double)
+        _lib.check(_lib.lib().khr_near2far(self.ctx, ids, fm.normal, fm.normal_sign, fm.medium_eps, fm.medium_mu,
+                                           bases.ctypes.data_as(dp), freqs.ctypes.data_as(dp), nf,
+                                           obs.ctypes.data_as(dp), nobs, out.ctypes.data_as(dp)))
+        z = out[0::2] + 1j * out[1::2]
+        return z.reshape(nf, 6, nobs).transpose(2, 1, 0)
+
+    @staticmethod
+    def compute_far_field_power(EH, theta, phi, eps=1.0, mu=1.0):
+        """Near2Far.jl:1043-1072: radiated power per solid angle from the first frequency of EH."""
+        Z = math.sqrt(mu / eps)
+        power = np.zeros((len(theta), len(phi)))
+        idx = 0
+        for ip, ph in enumerate(phi):
+            for it, th in enumerate(theta):
+                ex, ey, ez = EH[idx, 0, 0], EH[idx, 1, 0], EH[idx, 2, 0]
+                th_hat = (math.cos(th) * math.cos(ph), math.cos(th) * math.sin(ph), -math.sin(th))
+                ph_hat = (-math.sin(ph), math.cos(ph), 0.0)
+                e_th = ex * th_hat[0] + ey * th_hat[1] + ez * th_hat[2]
+                e_ph = ex * ph_hat[0] + ey * ph_hat[1] + ez * ph_hat[2]
+                power[it, ip] = 0.5 * (abs(e_th) ** 2 + abs(e_ph) ** 2) / Z
+                idx += 1
+        return power
+
+    def compute_mode_amplitudes(self, fm, mode_fields):
+        """ModeMonitor.jl:345-515 compute_mode_amplitudes with the surface sums on the device
+        (`khr_mode_overlap`).  mode_fields: complex (4, n1, n2, nf) = mode e1, e2, h1, h2 already
+        interpolated onto the DFT grid (:427-457).  Returns (a_plus, a_minus)."""
+        m = np.asarray(mode_fields, dtype=np.complex128)
+        if m.ndim != 4 or m.shape[0] != 4 or m.shape[3] != len(fm.frequencies):
+            raise ValueError("mode_fields must be complex (4, n1, n2, nf)")
+        n1, n2, nf = m.shape[1], m.shape[2], m.shape[3]
+        flat = np.ascontiguousarray(m.transpose(0, 3, 2, 1)).ravel()  # [4][nf][n2][n1]
+        ri = np.empty(2 * flat.size, dtype=np.float64)
+        ri[0::2] = flat.real
+        ri[1::2] = flat.imag
+        ids = (C.c_int32 * 4)(*[mm.id for mm in fm.monitors])
+        out = np.zeros(5 * nf, dtype=np.float64)
+        dp = C.POINTER(C.c_double)
+        _lib.check(_lib.lib().khr_mode_overlap(self.ctx, ids, fm.normal, ri.ctypes.data_as(dp), n1, n2, nf,
+                                               out.ctypes.data_as(dp)))
+        o = out.reshape(nf, 5)
+        a_plus = np.zeros(nf, dtype=np.complex128)
+        a_minus = np.zeros(nf, dtype=np.complex128)
+        for k in range(nf):
+            P = o[k, 0]
+            if abs(P) > 1e-30:
+                a_plus[k] = complex(o[k, 1], o[k, 2]) / (4.0 * P)
+                a_minus[k] = complex(o[k, 3], o[k, 4]) / (4.0 * P)
+        return a_plus, a_minus
+
+    def get_mode_transmission(self, fm, mode_fields):
+        """ModeMonitor.jl:515-518: |a+|^2 per frequency."""
+        return np.abs(self.compute_mode_amplitudes(fm, mode_fields)[0]) ** 2
 
     def set_profiling(self, mode):
         _lib.check(_lib.lib().khr_set_profiling(self.ctx, int(mode)))

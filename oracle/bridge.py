@@ -23,6 +23,8 @@ def oracle_from_simulation(sim):
         if arr is not None:
             for d in range(3):
                 o.set_material_array(key, d, arr[d])
+    if sim.material_arrays.get("chi3") is not None:
+        o.set_material_array("chi3", 0, sim.material_arrays["chi3"])
     for (w0, gam, s) in sim.poles:
         o.add_pole(w0, gam, s)
     for sd in sim.source_data:

@@ -271,6 +271,13 @@ struct Sim {
   T eps_inv = 1, mu_inv = 1;
   Arr3<T> eps_inv_a[3], mu_inv_a[3];
   Arr3<T> sigD[3], sigB[3];  // material conductivity; !ok() == nothing
+  // Kerr coefficient per voxel on the centre grid (src/Geometry.jl:610-660); !ok() == nothing
+  Arr3<T> chi3;
+  // false (canonical, SURVEY 8(c') style decision): the correction is applied before the halo /
+  // wrap copies, so neighbours see the corrected E, as they do inside a chunk.  true: the literal
+  // order of step! (Kernels.jl:76-79: exchange_halos! at the end of step_E_fused!, then
+  // step_chi3_correction!), which leaves the uncorrected value in the ghost copies.
+  bool chi3_literal_order = false;
   std::vector<Pole<T>> poles;
   std::vector<Source<T>> sources;
   std::vector<DFTMon<T>> monitors;
@@ -897,6 +904,28 @@ struct Sim {
     }
   }
 
+  // step_chi3_correction! (src/Kernels/Dispersive.jl:127-173): E <- E / (1 + chi3 |E|^2) with the
+  // three components taken at the same array index (no interpolation), only where chi3 != 0.
+  void step_chi3() {
+    if (!chi3.ok()) return;
+    for (auto& c : chunks) {
+#pragma omp parallel for collapse(2) schedule(static)
+      for (int iz = 1; iz <= c.n[2]; ++iz)
+        for (int iy = 1; iy <= c.n[1]; ++iy)
+          for (int ix = 1; ix <= c.n[0]; ++ix) {
+            T chi3_val = chi3.at(c.s[0] + ix - 2, c.s[1] + iy - 2, c.s[2] + iz - 2);
+            if (chi3_val != T(0)) {
+              T ex = c.E[0].at(ix, iy, iz), ey = c.E[1].at(ix, iy, iz), ez = c.E[2].at(ix, iy, iz);
+              T E_sq = (ex * ex + ey * ey) + ez * ez;
+              T correction = T(1) / (T(1) + chi3_val * E_sq);
+              c.E[0].at(ix, iy, iz) = ex * correction;
+              c.E[1].at(ix, iy, iz) = ey * correction;
+              c.E[2].at(ix, iy, iz) = ez * correction;
+            }
+          }
+    }
+  }
+
   // step! (src/Kernels/Kernels.jl:20-88); t = Float64(timestep * Δt) with the
   // product formed in T (src/Simulation.jl:22).
   void step() {
@@ -921,8 +950,10 @@ struct Sim {
     update_monitors(0, t);
     if (sources_active) step_sources(1, t_half);
     for (auto& c : chunks) { step_curl(c, 1); update_field(c, 1); }
+    if (!chi3_literal_order) step_chi3();
     if (chunks.size() > 1) exchange_halos(1);
     wrap_periodic(1);
+    if (chi3_literal_order) step_chi3();
     step_polarization();
     update_monitors(1, t_half);
     timestep += 1;
@@ -1066,12 +1097,12 @@ void ko_set_material_scalar(void* hv, int kind, double v) {
   });
 }
 
-// kind: 0..2 eps_inv_{x,y,z}; 3..5 mu_inv; 6..8 sigma_D; 9..11 sigma_B. Dense (Nx,Ny,Nz).
+// kind: 0..2 eps_inv_{x,y,z}; 3..5 mu_inv; 6..8 sigma_D; 9..11 sigma_B; 12 chi3. Dense (Nx,Ny,Nz).
 void ko_set_material_array(void* hv, int kind, const double* a) {
   Handle* h = (Handle*)hv;
   DISPATCH(h, {
     int d = kind % 3, g = kind / 3;
-    auto& dst = (g == 0) ? S.eps_inv_a[d] : (g == 1) ? S.mu_inv_a[d] : (g == 2) ? S.sigD[d] : S.sigB[d];
+    auto& dst = (g == 0) ? S.eps_inv_a[d] : (g == 1) ? S.mu_inv_a[d] : (g == 2) ? S.sigD[d] : (g == 3) ? S.sigB[d] : S.chi3;
     copy_in(dst, a, S.N[0], S.N[1], S.N[2]);
     if (g == 0) S.eps_is_array = true;
     if (g == 1) S.mu_is_array = true;
@@ -1192,6 +1223,11 @@ void ko_set_boundary_conditions(void* hv, const int* bc6) {
       S.periodic[a] = bc6[2 * a] == 1 && bc6[2 * a + 1] == 1;
     }
   });
+}
+
+void ko_set_chi3_literal_order(void* hv, int v) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, S.chi3_literal_order = v != 0);
 }
 
 void ko_set_sources_active(void* hv, int v) {
@@ -1324,6 +1360,172 @@ void ko_flux(void* hv, int normal_axis /*0..2*/, const int* ids4, double* flux_o
           s += (double)(re1 - re2) * dA;
         }
       flux_out[kf] = s;
+    }
+  });
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Post-processing of the DFT accumulators, restated from the reference's
+// host loops; Float64 / ComplexF64 arithmetic like the reference.
+// ---------------------------------------------------------------------------
+namespace {
+typedef std::complex<double> cd;
+
+// green3d! (src/Monitors/Near2Far.jl:40-96)
+inline void green3d(cd* EH, const double* x, double freq, double eps, double mu, const double* x0, int c0, cd f0) {
+  const double pi = 3.141592653589793;
+  double rv[3] = {x[0] - x0[0], x[1] - x0[1], x[2] - x0[2]};
+  double r = std::sqrt((rv[0] * rv[0] + rv[1] * rv[1]) + rv[2] * rv[2]);
+  if (r >= 1e-20) {
+    double rh[3] = {rv[0] / r, rv[1] / r, rv[2] / r};
+    double n = std::sqrt(eps * mu);
+    double k = 2 * pi * freq * n;
+    double Z = std::sqrt(mu / eps);
+    cd ikr = cd(0.0, 1.0) * k * r;
+    double ikr2 = -((k * r) * (k * r));
+    cd expfac = f0 * (k * n / (4 * pi * r)) * std::exp(cd(0.0, 1.0) * (k * r + pi / 2));
+    int pc = (c0 - 1) % 3;  // mod1(c0, 3) - 1
+    double p[3] = {pc == 0 ? 1.0 : 0.0, pc == 1 ? 1.0 : 0.0, pc == 2 ? 1.0 : 0.0};
+    double pdotrhat = (p[0] * rh[0] + p[1] * rh[1]) + p[2] * rh[2];
+    double rxp[3] = {rh[1] * p[2] - rh[2] * p[1], rh[2] * p[0] - rh[0] * p[2], rh[0] * p[1] - rh[1] * p[0]};
+    cd term1 = 1.0 - 1.0 / ikr + 1.0 / ikr2;
+    cd term2 = (-1.0 + 3.0 / ikr - 3.0 / ikr2) * pdotrhat;
+    cd term3 = 1.0 - 1.0 / ikr;
+    if (c0 <= 3) {
+      cd ef = expfac / eps;
+      for (int j = 0; j < 3; ++j) {
+        EH[j] += ef * (term1 * p[j] + term2 * rh[j]);
+        EH[3 + j] += ef * term3 * rxp[j] / Z;
+      }
+    } else {
+      cd ef = expfac / mu;
+      for (int j = 0; j < 3; ++j) {
+        EH[j] += -ef * term3 * rxp[j] * Z;
+        EH[3 + j] += ef * (term1 * p[j] + term2 * rh[j]);
+      }
+    }
+  }
+}
+
+// the four tangential monitors of a plane, averaged over the two planes along the normal in
+// Complex{T} (_avg_dim), widened to ComplexF64
+template <class S>
+struct Surface {
+  const S& sim;
+  const int* ids;
+  int normal, t1, t2, n1, n2, nf;
+  Surface(const S& s, const int* ids4, int normal_axis) : sim(s), ids(ids4), normal(normal_axis) {
+    t1 = normal == 0 ? 1 : 0;
+    t2 = normal == 2 ? 1 : 2;
+    n1 = n2 = 1 << 30;
+    for (int q = 0; q < 4; ++q) {
+      n1 = std::min(n1, sim.monitors[ids[q]].n[t1]);
+      n2 = std::min(n2, sim.monitors[ids[q]].n[t2]);
+    }
+    nf = (int)sim.monitors[ids[0]].freqs.size();
+  }
+  cd val(int m, int i1, int i2, int kf) const {
+    using TT = std::remove_const_t<std::remove_reference_t<decltype(sim.dt)>>;
+    const auto& mm = sim.monitors[ids[m]];
+    size_t ncell = (size_t)mm.n[0] * mm.n[1] * mm.n[2];
+    auto at = [&](int q) {
+      int idx[3];
+      idx[normal] = q; idx[t1] = i1; idx[t2] = i2;
+      return mm.M[(size_t)kf * ncell + (size_t)idx[0] + (size_t)mm.n[0] * ((size_t)idx[1] + (size_t)mm.n[1] * idx[2])];
+    };
+    if (mm.n[normal] >= 2) {
+      std::complex<TT> a = at(0), b = at(1);
+      std::complex<TT> sum(a.real() + b.real(), a.imag() + b.imag());
+      return cd((double)(sum.real() / TT(2)), (double)(sum.imag() / TT(2)));
+    }
+    std::complex<TT> a = at(0);
+    return cd((double)a.real(), (double)a.imag());
+  }
+};
+}  // namespace
+
+template <class SimT>
+static void near2far_impl(const SimT& S, int normal_axis, const int* ids4, double ns, double eps, double mu, const double* base12,
+                          const double* freqs, const double* obs, int nobs, double* out) {
+    Surface<SimT> sf(S, ids4, normal_axis);
+    const int t1 = sf.t1, t2 = sf.t2;
+    const double d1 = (double)S.dl[t1], d2 = (double)S.dl[t2];
+    const double dA = d1 * d2;
+    // (field index, current component, sign) of the four equivalent currents per normal axis
+    // (:324-360): J = n x H, M = -n x E
+    static const int F_[3][4] = {{3, 2, 1, 0}, {2, 3, 0, 1}, {3, 2, 1, 0}};
+    static const int C_[3][4] = {{2, 3, 5, 6}, {3, 1, 6, 4}, {1, 2, 4, 5}};
+    static const double S_[4] = {1, -1, -1, 1};
+    const int* fld = F_[normal_axis];
+    const int* cc = C_[normal_axis];
+    for (int kf = 0; kf < sf.nf; ++kf) {
+      const double freq = freqs[kf];
+#pragma omp parallel for schedule(static)
+      for (int io = 0; io < nobs; ++io) {
+        const double x[3] = {obs[3 * io], obs[3 * io + 1], obs[3 * io + 2]};
+        cd EH[6] = {0, 0, 0, 0, 0, 0};
+        for (int i2 = 0; i2 < sf.n2; ++i2)
+          for (int i1 = 0; i1 < sf.n1; ++i1)
+            for (int q = 0; q < 4; ++q) {
+              const int m = fld[q];
+              double x0[3] = {base12[3 * m], base12[3 * m + 1], base12[3 * m + 2]};
+              x0[t1] = base12[3 * m + t1] + i1 * d1;
+              x0[t2] = base12[3 * m + t2] + i2 * d2;
+              green3d(EH, x, freq, eps, mu, x0, cc[q], (S_[q] * ns) * sf.val(m, i1, i2, kf) * dA);
+            }
+        for (int j = 0; j < 6; ++j) {
+          size_t o = (size_t)io + (size_t)nobs * ((size_t)j + 6 * (size_t)kf);
+          out[2 * o] = EH[j].real();
+          out[2 * o + 1] = EH[j].imag();
+        }
+      }
+    }
+}
+
+extern "C" {
+
+// _compute_far_field_cpu (src/Monitors/Near2Far.jl:254-371).  ids4 = E1, E2, H1, H2 monitors;
+// base12 = e1/e2/h1/h2 base positions; out = ComplexF64 (nobs, 6, nf) column-major, interleaved.
+void ko_near2far(void* hv, int normal_axis, const int* ids4, double ns, double eps, double mu, const double* base12,
+                 const double* freqs, const double* obs, int nobs, double* out) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, near2far_impl(S, normal_axis, ids4, ns, eps, mu, base12, freqs, obs, nobs, out));
+}
+
+// compute_mode_amplitudes (src/Monitors/ModeMonitor.jl:345-515) from mode profiles already on the DFT
+// grid: mode = ComplexF64 [4][nf][n2][n1] (e1, e2, h1, h2).  out: a_plus (2 nf), a_minus (2 nf), P_mode (nf)
+void ko_mode_amplitudes(void* hv, int normal_axis, const int* ids4, const double* mode, double* a_plus, double* a_minus,
+                        double* p_mode) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, {
+    Surface<std::remove_reference_t<decltype(S)>> sf(S, ids4, normal_axis);
+    const double dA = (double)S.dl[sf.t1] * (double)S.dl[sf.t2];
+    const size_t ncell = (size_t)sf.n1 * sf.n2;
+    for (int kf = 0; kf < sf.nf; ++kf) {
+      auto md = [&](int c, int i1, int i2) {
+        const double* p = mode + 2 * (((size_t)c * sf.nf + kf) * ncell + (size_t)i1 + (size_t)sf.n1 * i2);
+        return cd(p[0], p[1]);
+      };
+      double P = 0.0;
+      for (int i2 = 0; i2 < sf.n2; ++i2)
+        for (int i1 = 0; i1 < sf.n1; ++i1)
+          P += 0.5 * std::real(md(0, i1, i2) * std::conj(md(3, i1, i2)) - md(1, i1, i2) * std::conj(md(2, i1, i2))) * dA;
+      cd op(0, 0), om(0, 0);
+      for (int i2 = 0; i2 < sf.n2; ++i2)
+        for (int i1 = 0; i1 < sf.n1; ++i1) {
+          cd et1 = sf.val(0, i1, i2, kf), et2 = sf.val(1, i1, i2, kf), ht1 = sf.val(2, i1, i2, kf), ht2 = sf.val(3, i1, i2, kf);
+          cd scm = et1 * std::conj(md(3, i1, i2)) - et2 * std::conj(md(2, i1, i2));
+          cd mcs = std::conj(md(0, i1, i2)) * ht2 - std::conj(md(1, i1, i2)) * ht1;
+          op += (scm + mcs) * dA;
+          om += (scm - mcs) * dA;
+        }
+      cd ap(0, 0), am(0, 0);
+      if (std::abs(P) > 1e-30) { ap = op / (4.0 * P); am = om / (4.0 * P); }
+      a_plus[2 * kf] = ap.real(); a_plus[2 * kf + 1] = ap.imag();
+      a_minus[2 * kf] = am.real(); a_minus[2 * kf + 1] = am.imag();
+      p_mode[kf] = P;
     }
   });
 }

@@ -69,6 +69,7 @@ def lib():
         L.ko_chunk_sigma.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, dp]
         L.ko_step.argtypes = [C.c_void_p, C.c_int]
         L.ko_set_sources_active.argtypes = [C.c_void_p, C.c_int]
+        L.ko_set_chi3_literal_order.argtypes = [C.c_void_p, C.c_int]
         L.ko_set_boundary_conditions.argtypes = [C.c_void_p, ip]
         L.ko_timestep.restype = C.c_long
         L.ko_num_threads.restype = C.c_int
@@ -79,6 +80,8 @@ def lib():
         L.ko_get_dft.restype = C.c_size_t
         L.ko_get_dft.argtypes = [C.c_void_p, C.c_int, dp]
         L.ko_flux.argtypes = [C.c_void_p, C.c_int, ip, dp]
+        L.ko_near2far.argtypes = [C.c_void_p, C.c_int, ip, C.c_double, C.c_double, C.c_double, dp, dp, dp, C.c_int, dp]
+        L.ko_mode_amplitudes.argtypes = [C.c_void_p, C.c_int, ip, dp, dp, dp, dp]
         _LIB = L
     return _LIB
 
@@ -208,7 +211,7 @@ class OracleSim:
     def set_material_scalar(self, kind, v):
         self.L.ko_set_material_scalar(self.h, {"eps_inv": 0, "mu_inv": 1}[kind], float(v))
 
-    _KINDS = {"eps_inv": 0, "mu_inv": 3, "sigma_D": 6, "sigma_B": 9}
+    _KINDS = {"eps_inv": 0, "mu_inv": 3, "sigma_D": 6, "sigma_B": 9, "chi3": 12}
 
     def set_material_array(self, kind, comp, arr):
         """arr: (Nx,Ny,Nz) numpy array (any order; converted to x-fastest)."""
@@ -253,6 +256,11 @@ class OracleSim:
         mid = self.L.ko_add_dft(self.h, int(comp), sp, ep, len(f), fp, int(decimation))
         self._monitors.append((tuple(int(x) for x in (e - s + 1)), len(f)))
         return mid
+
+    def set_chi3_literal_order(self, on):
+        """True: apply the Kerr correction after the halo / wrap copies, the literal order of step!
+        (Kernels.jl:76-79); default False = before them (neighbours see the corrected E)."""
+        self.L.ko_set_chi3_literal_order(self.h, int(bool(on)))
 
     def set_boundary_conditions(self, bc6):
         """bc6: per (axis, side) 0 = PML, 1 = Periodic, 2 = PEC, 3 = PMC (before prepare)."""
@@ -317,3 +325,31 @@ class OracleSim:
         out = np.zeros(nf)
         self.L.ko_flux(self.h, int(normal_axis), ip, out.ctypes.data_as(C.POINTER(C.c_double)))
         return out
+
+    def near2far(self, normal_axis, ids4, normal_sign, eps, mu, bases, freqs, obs):
+        """_compute_far_field_cpu (Near2Far.jl:254-371): EH complex (nobs, 6, nf)."""
+        i4, ip = _i(ids4)
+        b, bp = _d(np.asarray(bases, dtype=np.float64).reshape(12))
+        f, fp = _d(freqs)
+        o, op = _d(np.asarray(obs, dtype=np.float64).reshape(-1, 3))
+        nobs, nf = o.shape[0], len(f)
+        out = np.zeros(2 * nobs * 6 * nf)
+        self.L.ko_near2far(self.h, int(normal_axis), ip, float(normal_sign), float(eps), float(mu), bp, fp, op, nobs,
+                           out.ctypes.data_as(C.POINTER(C.c_double)))
+        z = out[0::2] + 1j * out[1::2]
+        return z.reshape(nf, 6, nobs).transpose(2, 1, 0)
+
+    def mode_amplitudes(self, normal_axis, ids4, mode_fields):
+        """compute_mode_amplitudes (ModeMonitor.jl:345-515); mode_fields complex (4, n1, n2, nf) on the DFT grid."""
+        i4, ip = _i(ids4)
+        m = np.asarray(mode_fields, dtype=np.complex128)
+        nf = m.shape[3]
+        flat = np.ascontiguousarray(m.transpose(0, 3, 2, 1)).ravel()  # [4][nf][n2][n1]
+        ri = np.empty(2 * flat.size)
+        ri[0::2] = flat.real
+        ri[1::2] = flat.imag
+        ap, am, pm = np.zeros(2 * nf), np.zeros(2 * nf), np.zeros(nf)
+        dp = C.POINTER(C.c_double)
+        self.L.ko_mode_amplitudes(self.h, int(normal_axis), ip, ri.ctypes.data_as(dp), ap.ctypes.data_as(dp),
+                                  am.ctypes.data_as(dp), pm.ctypes.data_as(dp))
+        return ap[0::2] + 1j * ap[1::2], am[0::2] + 1j * am[1::2], pm

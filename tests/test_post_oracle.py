@@ -1,0 +1,106 @@
+"""CPU checks of the oracle's post-processing restatements (no GPU): the near-to-far Green's
+function must satisfy Maxwell's equations away from the surface, and the mode-overlap sums must
+give a+ = 1 for a mode equal to the recorded field."""
+import numpy as np
+
+import khronos_b200 as kb
+from common import Pair
+
+CW = kb.ContinuousWaveSource(fcen=1.0)
+
+
+def _oracle_plane(normal, cls=kb.Near2FarMonitor, **kw):
+    size = [1.2, 1.2, 1.2]
+    size[normal] = 0.0
+    center = [0.0, 0.0, 0.0]
+    center[normal] = 0.4
+    fm = cls(center, size, [1.0], **kw)
+    mons = [(m.component, m.center, m.size, m.frequencies, 1) for m in fm.monitors]
+    p = Pair([2.4, 2.4, 2.4], 10, [0.5, 0.5, 0.5], np.float64, build_gpu=False,
+             sources=[(kb.EZ, [0, 0, 0], [0, 0, 0], CW), (kb.EX, [0.1, -0.1, 0.2], [0, 0, 0], CW)], monitors=mons)
+    p.o.step(40)
+    fm.monitors = p.kmon
+    return p, fm
+
+
+def test_near2far_fields_satisfy_maxwell():
+    """curl E = i w mu H and curl H = -i w eps E (time convention exp(-i w t), c = 1) for the
+    radiated field of the equivalent currents, by central differences of the oracle's output."""
+    eps, mu, f = 2.25, 1.3, 1.0
+    w = 2 * np.pi * f
+    h = 1e-4
+    for normal in (0, 1, 2):
+        p, fm = _oracle_plane(normal, medium_eps=eps, medium_mu=mu)
+        x = np.array([2.3, -1.7, 3.1])
+        pts = [x]
+        for a in range(3):
+            for s in (+1, -1):
+                d = np.zeros(3)
+                d[a] = s * h
+                pts.append(x + d)
+        EH = p.o.near2far(normal, p.omon, 1.0, eps, mu, p.k._plane_bases(fm), [f], np.array(pts))[:, :, 0]
+
+        def curl(F):  # F: index -> (point, 3)
+            dF = [(F[1 + 2 * a] - F[2 + 2 * a]) / (2 * h) for a in range(3)]  # d/dx_a of the vector
+            return np.array([dF[1][2] - dF[2][1], dF[2][0] - dF[0][2], dF[0][1] - dF[1][0]])
+
+        E, H = EH[:, 0:3], EH[:, 3:6]
+        cE, cH = curl(E), curl(H)
+        assert np.linalg.norm(cE - 1j * w * mu * H[0]) < 1e-5 * np.linalg.norm(cE), normal
+        assert np.linalg.norm(cH + 1j * w * eps * E[0]) < 1e-5 * np.linalg.norm(cH), normal
+
+
+def test_near2far_far_zone_is_transverse_and_decays_like_1_over_r():
+    p, fm = _oracle_plane(2)
+    d = np.array([0.3, -0.5, 0.81])
+    d /= np.linalg.norm(d)
+    EH = p.o.near2far(2, p.omon, 1.0, 1.0, 1.0, p.k._plane_bases(fm), [1.0], np.array([1e4 * d, 2e4 * d]))[:, :, 0]
+    E1, E2 = EH[0, 0:3], EH[1, 0:3]
+    assert abs(np.dot(E1, d)) < 1e-3 * np.linalg.norm(E1)
+    assert abs(np.linalg.norm(E1) / np.linalg.norm(E2) - 2.0) < 1e-3
+    # |E| = Z |H| in the far zone (Z = 1)
+    assert abs(np.linalg.norm(E1) / np.linalg.norm(EH[0, 3:6]) - 1.0) < 1e-3
+
+
+def test_mode_overlap_identity():
+    p, fm = _oracle_plane(0, cls=kb.ModeMonitor)
+    dft = [p.o.get_dft(m) for m in p.omon]
+    t1, t2 = fm.tangential
+    n1 = min(a.shape[t1] for a in dft)
+    n2 = min(a.shape[t2] for a in dft)
+
+    def avg(a):
+        a = (np.take(a, 0, axis=0) + np.take(a, 1, axis=0)) / 2 if a.shape[0] >= 2 else np.take(a, 0, axis=0)
+        return a[:n1, :n2, :]
+
+    mode = np.stack([avg(a) for a in dft])
+    ap, am, P = p.o.mode_amplitudes(0, p.omon, mode)
+    assert P[0] != 0 and abs(ap[0] - 1.0) < 1e-12 and abs(am[0].real) < 1e-12
+    ap2, _, _ = p.o.mode_amplitudes(0, p.omon, 3.0 * mode)   # a+ scales like 1 / |mode| for a fixed field
+    assert abs(ap2[0] - 1.0 / 3.0) < 1e-12
+
+
+def test_oracle_kerr_correction():
+    """chi3 == 0 everywhere is bit-identical to no chi3; E of a Kerr voxel is E_lin / (1 + chi3 |E_lin|^2)
+    with E_lin rebuilt from D every step (no compounding); the literal step! order (correction after
+    the wrap copy) differs from the canonical one only in ghost-dependent cells of a periodic box."""
+    N = (24, 24, 24)
+    src = [(kb.EZ, [0, 0, 0], [0, 0, 0], CW)]
+    base = Pair([2.4, 2.4, 2.4], 10, [0.5, 0.5, 0.5], np.float64, build_gpu=False, sources=src)
+    zero = Pair([2.4, 2.4, 2.4], 10, [0.5, 0.5, 0.5], np.float64, build_gpu=False, sources=src,
+                chi3=np.zeros(N))
+    chi = np.zeros(N)
+    chi[8:16, 8:16, 8:16] = 5.0
+    kerr = Pair([2.4, 2.4, 2.4], 10, [0.5, 0.5, 0.5], np.float64, build_gpu=False, sources=src, chi3=chi)
+    for q in (base, zero, kerr):
+        q.o.step(30)
+    assert np.array_equal(base.o.get_field(kb.EZ), zero.o.get_field(kb.EZ))
+    assert not np.array_equal(base.o.get_field(kb.EZ), kerr.o.get_field(kb.EZ))
+    # one more step by hand on a voxel inside the block: E_new = eps_inv * D_new / (1 + chi3 |...|^2)
+    kerr.o.step(1)
+    D = [kerr.o.get_field(c, which="DB") for c in range(3)]
+    E = [kerr.o.get_field(c) for c in range(3)]
+    i = (11, 12, 10)
+    e_lin = np.array([D[c][i] for c in range(3)])     # vacuum, no sources at this voxel: E_lin = D
+    want = e_lin / (1.0 + 5.0 * ((e_lin[0] * e_lin[0] + e_lin[1] * e_lin[1]) + e_lin[2] * e_lin[2]))
+    assert np.allclose([E[c][i] for c in range(3)], want, rtol=1e-14, atol=0)
