@@ -1,0 +1,84 @@
+"""Value anchor for the oracle (and, on the GPU, for the product): the reference's own analytic
+validation, examples/dielectric_slab.jl — normal-incidence transmission of an n = 2, 0.5 um slab
+(periodic x/y, PML z, Gaussian-pulse sheet source, flux monitor behind the slab, two runs
+normalised by the empty cell) against the Fresnel / Fabry-Perot formula (:211-222), at the
+reference's own pass mark `max |T_sim - T_analytic| < 0.08` (:244).  No reference test pins field
+values after N steps; this is the physics anchor the survey names instead."""
+import numpy as np
+import pytest
+
+import khronos_b200 as kb
+from bridge import oracle_from_simulation
+
+N_SLAB, THICK = 2.0, 0.5
+FREQS = np.linspace(1.0 / 1.5, 1.0 / 0.6, 21)
+
+
+def _build(with_slab, dtype, res=40):
+    cell_xy, buffer, pml = 0.1, 1.5, 1.0
+    cell_z = THICK + 2 * buffer + 2 * pml
+    fwidth = 2 * np.pi * 0.5 * (1.0 / 0.6 - 1.0 / 1.5)
+    src = kb.UniformSource(kb.GaussianPulseSource(fcen=1.0, fwidth=fwidth), kb.EX,
+                           [0.0, 0.0, -THICK / 2 - buffer / 2], [cell_xy + 1.0, cell_xy + 1.0, 0.0])
+    # (the sheet is larger than the periodic cell so that every node gets interpolation weight 1: a
+    # source that is not uniform in x/y would also feed waves circulating around the periodic cell
+    # with k_z = 0, which never reach the z PML)
+    # decimation 2 is given explicitly: left at 1 it would be raised to floor(1/(2 f_max dt)) = 10
+    # (Monitors.jl:59-73), and the broadband start-up transient of this very short pulse (its
+    # envelope starts 3 sigma before the peak, TimeSources.jl:91-108) then aliases into the band:
+    # measured max |T - T_analytic| = 0.21 with D = 10 against 0.051 with D = 2
+    fm = kb.FluxMonitor([0.0, 0.0, THICK / 2 + buffer / 2], [cell_xy, cell_xy, 0.0], list(FREQS), decimation=2)
+    # The product rasterises by point sampling (subpixel smoothing is outside the hot path): the slab
+    # is shifted by half a cell so that its faces fall between two Ex nodes and exactly
+    # THICK * res nodes carry eps, i.e. the rasterised slab is THICK thick.
+    geom = [kb.Object(kb.Cuboid([0, 0, 0.5 / res], [cell_xy + 1.0, cell_xy + 1.0, THICK]),
+                      kb.Material(epsilon=N_SLAB ** 2))]
+    sim = kb.Simulation([cell_xy, cell_xy, cell_z], [0, 0, 0], res, [src], boundaries=[[0, 0], [0, 0], [pml, pml]],
+                        boundary_conditions=[[kb.Periodic(), kb.Periodic()], [kb.Periodic(), kb.Periodic()],
+                                             [kb.PML(), kb.PML()]],
+                        geometry=geom if with_slab else None, monitors=[fm], dtype=dtype)
+    return sim, fm
+
+
+def _fresnel_slab_transmission(freq):
+    r12 = (1.0 - N_SLAB) / (1.0 + N_SLAB)
+    t12, t21 = 2.0 / (1.0 + N_SLAB), 2.0 * N_SLAB / (1.0 + N_SLAB)
+    phase = N_SLAB * 2 * np.pi * freq * THICK
+    return np.abs(t12 * t21 * np.exp(1j * phase) / (1.0 + r12 * (-r12) * np.exp(2j * phase))) ** 2
+
+
+T_ANALYTIC = np.array([_fresnel_slab_transmission(f) for f in FREQS])
+NSTEPS = 4800  # t = 60: the pulse (cutoff 1.6) and its slab echoes (|r|^2 = 1/9 per bounce) have left
+
+
+def _oracle_flux(with_slab, dtype):
+    sim, fm = _build(with_slab, dtype)
+    o, mids = oracle_from_simulation(sim)
+    o.step(NSTEPS)
+    return o.flux(fm.normal, mids)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_oracle_slab_transmission_matches_fresnel(dtype):
+    T = _oracle_flux(True, dtype) / _oracle_flux(False, dtype)
+    err = np.max(np.abs(T - T_ANALYTIC))
+    assert err < 0.08, (err, T, T_ANALYTIC)      # the reference's pass mark
+    # what the restatement reaches at res 40 (numerical dispersion at 12 cells per wavelength in the
+    # slab); the error is second order: 0.051 at res 40, 0.0127 at res 80 (measured, Float64)
+    assert err < 0.06, err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_gpu_slab_transmission_matches_fresnel_and_oracle(dtype):
+    flux = []
+    for with_slab in (False, True):
+        sim, fm = _build(with_slab, dtype)
+        sim.prepare_simulation()
+        sim.step(NSTEPS)
+        flux.append(sim.get_flux(fm))
+        sim.close()
+    T = flux[1] / flux[0]
+    assert np.max(np.abs(T - T_ANALYTIC)) < 0.06
+    T_oracle = _oracle_flux(True, dtype) / _oracle_flux(False, dtype)
+    assert np.max(np.abs(T - T_oracle)) < (1e-9 if dtype is np.float64 else 1e-3), np.max(np.abs(T - T_oracle))
