@@ -105,8 +105,21 @@ int32_t khr_monitor_register(khr_ctx* ctx, int32_t comp, const int32_t start[3],
  * ghost and the first interior layer to the upper ghost, for the three components of the
  * group (z on several ranks: the wrap closes the halo ring).  The caller passes PML
  * thickness 0 on such an axis (eff_boundaries, Boundaries.jl:100-110).  Before
- * khr_finalize_plan.  Bloch k != 0 (complex fields) is not supported. */
+ * khr_finalize_plan.  For Bloch boundaries see khr_set_complex_fields / khr_set_bloch. */
 int32_t khr_set_periodic(khr_ctx* ctx, int32_t axis, int32_t on);
+
+/* Fields.jl:140-159 _needs_complex_fields: any Bloch boundary makes every field array Complex{T}.
+ * Call right after khr_ctx_create (before any registration).  The library keeps the real and the
+ * imaginary parts as two real field sets with identical layout and runs the same real kernels on
+ * both (every update coefficient is real, so real x complex products never mix the parts); they
+ * meet only in the Bloch phase of the wrap-around copy and in the DFT phasor product.  Sources
+ * drive the real part only, as in the reference (`+= real(a(t) * A[x])`, Sources.jl:355-356).
+ * Single GPU (nranks == 1), no chi3. */
+int32_t khr_set_complex_fields(khr_ctx* ctx);
+/* Chunking.jl:1735-1764 Bloch wrap-around on `axis` (both sides Bloch / Periodic): like
+ * khr_set_periodic, with the ghost copies multiplied by exp(-i k L) (lower ghost) and exp(+i k L)
+ * (upper ghost) in ComplexF64 (:2163-2167).  k_times_L = bloch.k * sim.cell_size[axis] (Float64). */
+int32_t khr_set_bloch(khr_ctx* ctx, int32_t axis, double k_times_L);
 
 /* builds region/work tables, allocates PML auxiliary slabs; call once after all
  * registrations (tail of prepare_simulation!, Simulation.jl:198-280) */
@@ -136,6 +149,8 @@ int32_t khr_halo_exchange(khr_ctx* ctx, int32_t group);
 /* --- data access ---------------------------------------------------------- */
 /* Visualization.jl:294-333 _pull_fields_from_device: dense (Nx,Ny,Nz_local) copy of cells 1..N */
 int32_t khr_field_read(khr_ctx* ctx, int32_t comp, void* dense_out);
+/* imaginary part of a complex field (khr_set_complex_fields), same layout as khr_field_read */
+int32_t khr_field_read_imag(khr_ctx* ctx, int32_t comp, void* dense_out);
 int32_t khr_field_write(khr_ctx* ctx, int32_t comp, const void* dense_in);
 /* raw device view: element (ix,iy,iz_local) (1-based cells, 0 = lower ghost) lives at
  * ptr[offset + ix*stride[0] + iy*stride[1] + iz*stride[2]] */

@@ -60,6 +60,9 @@ _SIGNATURES = {
     "khr_monitor_register": (_I, [_P, _I, C.POINTER(_I), C.POINTER(_I), _I, C.POINTER(C.c_double), _I, C.POINTER(_I)]),
     "khr_finalize_plan": (_I, [_P]),
     "khr_set_periodic": (_I, [_P, _I, _I]),
+    "khr_set_complex_fields": (_I, [_P]),
+    "khr_set_bloch": (_I, [_P, _I, C.c_double]),
+    "khr_field_read_imag": (_I, [_P, _I, _P]),
     "khr_flux": (_I, [_P, C.POINTER(_I), _I, C.POINTER(C.c_double), _I]),
     "khr_near2far": (_I, [_P, C.POINTER(_I), _I, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double),
                           C.POINTER(C.c_double), _I, C.POINTER(C.c_double), _I, C.POINTER(C.c_double)]),

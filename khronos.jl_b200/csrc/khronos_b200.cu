@@ -117,6 +117,12 @@ struct Base {
   virtual void set_profiling(int on) = 0;
   virtual int kernel_stat(int idx, khr_kernel_stat* out) = 0;
   bool periodic[3] = {false, false, false};
+  // complex fields (Bloch boundaries): this context holds the real parts, `partner` (owned by the
+  // khr_ctx) the imaginary parts of every field; bloch_kl[a] = k * L of the axis
+  bool in_pair = false, is_imag = false;
+  double bloch_kl[3] = {0.0, 0.0, 0.0};
+  virtual void set_partner(Base* p) = 0;
+  bool registered_any = false;
   int64_t timestep = 0;
   int sources_mode = -1;
   bool sources_active = true;
@@ -272,6 +278,16 @@ struct Impl : Base {
   cudaEvent_t ev_boundary = nullptr, ev_comm = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   int64_t launches = 0;
 
+  Impl<T>* im = nullptr;   // imaginary parts (complex fields); null for real fields and for the imaginary context itself
+  cudaEvent_t ev_pair_a = nullptr, ev_pair_b = nullptr;
+  void set_partner(Base* p) override {
+    im = dynamic_cast<Impl<T>*>(p);
+    if (!im) throw std::string("complex fields: partner context has another dtype");
+    in_pair = true;
+    im->in_pair = true; im->is_imag = true;
+    CUDA_OK(cudaEventCreateWithFlags(&ev_pair_a, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&ev_pair_b, cudaEventDisableTiming));
+  }
   std::vector<void*> allocs;
   T* dalloc(size_t n, bool zero = true) {
     void* p = nullptr;
@@ -484,7 +500,9 @@ struct Impl : Base {
   void finalize() override {
     if (finalized) throw std::string("khr_finalize_plan called twice");
     // the wrap kernels are plain launches between the chain kernels: keep stream semantics simple
-    if (any_periodic()) pdl = false;
+    if (any_periodic() || in_pair) pdl = false;
+    if (in_pair && g.nranks > 1) throw std::string("complex fields (Bloch boundaries) are single-GPU for now: nranks must be 1");
+    if (in_pair && chi3) throw std::string("chi3 with complex fields is not supported (|E|^2 couples the real and imaginary parts)");
     // per-axis PML cell sets from both groups' profiles
     std::vector<char> pml[3];
     for (int a = 0; a < 3; ++a) {
@@ -573,7 +591,7 @@ struct Impl : Base {
       for (size_t q = 0; q < monitors.size(); ++q) {
         Monitor& m = monitors[q];
         MonDesc<T>& d = h[q];
-        d.M = m.M; d.F = F[m.comp]; d.freqs = m.d_freqs; d.nf = (int)m.freqs.size();
+        d.M = m.M; d.F = F[m.comp]; d.Fi = im ? im->F[m.comp] : nullptr; d.freqs = m.d_freqs; d.nf = (int)m.freqs.size();
         d.decimation = m.decimation; d.group = m.comp >= 3 ? 0 : 1;
         // this rank accumulates the planes it owns; the top rank also owns the
         // staggered extra plane Nz+1 (never updated, zero, but part of the box)
@@ -1162,21 +1180,51 @@ struct Impl : Base {
     } else {
       if (gq == 0) launch_group<0>(p, 1, marr); else launch_group<1>(p, 1, marr);
     }
-    if (any_periodic()) wrap_periodic(gq);
+    if (any_periodic() && !in_pair) wrap_periodic(gq);
     if (gq == 1) for (auto& pl : poles) pl.cur = 1 - pl.cur;
     epochs[gq] += 1;
+  }
+  // complex fields: the same half-step on the imaginary parts (own streams, no sources), then the
+  // wrap-around copies of both parts with the Bloch phase on this context's stream
+  void half_step_all(int gq, double t_src) {
+    half_step(gq, t_src);
+    if (!im) return;
+    im->half_step(gq, t_src);
+    launches += im->launches; im->launches = 0;
+    CUDA_OK(cudaEventRecord(ev_pair_a, im->stream));
+    CUDA_OK(cudaStreamWaitEvent(stream, ev_pair_a, 0));
+    const long long st[3] = {1, (long long)PX, (long long)PX * PY};
+    for (int a = 0; a < 3; ++a) {
+      if (!periodic[a]) continue;
+      BlochWrapArgs<T> w;
+      for (int d = 0; d < 3; ++d) { w.fr[d] = gq == 0 ? F[3 + d] : F[d]; w.fi[d] = gq == 0 ? im->F[3 + d] : im->F[d]; }
+      const int t1 = (a + 1) % 3, t2 = (a + 2) % 3;
+      w.base = XO; w.sa = st[a]; w.s1 = st[t1]; w.s2 = st[t2];
+      w.n_axis = N[a]; w.n1 = N[t1]; w.n2 = N[t2];
+      // phase_fwd = exp(i k L), phase_rev = exp(-i k L) (Chunking.jl:1746-1747)
+      w.fwd_re = std::cos(bloch_kl[a]); w.fwd_im = std::sin(bloch_kl[a]);
+      w.rev_re = std::cos(-bloch_kl[a]); w.rev_im = std::sin(-bloch_kl[a]);
+      w.apply_fwd = !(w.fwd_re == 1.0 && w.fwd_im == 0.0);
+      w.apply_rev = !(w.rev_re == 1.0 && w.rev_im == 0.0);
+      const long long cells = (long long)N[t1] * N[t2];
+      bloch_wrap_kernel<T><<<dim3((unsigned)((cells + 255) / 256), 3), 256, 0, stream>>>(w);
+      ++launches;
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventRecord(ev_pair_b, stream));
+    CUDA_OK(cudaStreamWaitEvent(im->stream, ev_pair_b, 0));
   }
 
   void step_h() override {
     need_final();
     double t = time_now();
     update_sources_active(t);
-    half_step(0, t);
+    half_step_all(0, t);
   }
   void step_e() override {
     need_final();
     double t = time_now() + (double)(dt / T(2));
-    half_step(1, t);
+    half_step_all(1, t);
   }
   void dft_update(int group, double time) override {
     need_final();
@@ -1230,11 +1278,12 @@ struct Impl : Base {
       double t = time_now();
       double th = t + (double)(dt / T(2));
       update_sources_active(t);
-      half_step(0, t);
+      half_step_all(0, t);
       dft_update(0, t);
-      half_step(1, th);
+      half_step_all(1, th);
       dft_update(1, th);
       timestep += 1;
+      if (im) im->timestep = timestep;
     }
     CUDA_OK(cudaEventRecord(ev_t1, stream));
     last_launches = launches;
@@ -1565,7 +1614,15 @@ struct Impl : Base {
 // ============================================================================
 struct khr_ctx {
   khr::Base* impl;
+  khr::Base* impl_im = nullptr;   // imaginary parts of the fields (khr_set_complex_fields)
 };
+// registrations that describe the medium go to both parts of a complex simulation
+#define KHR_BOTH(call)                                   \
+  do {                                                   \
+    ctx->impl->registered_any = true;                    \
+    ctx->impl->call;                                     \
+    if (ctx->impl_im) ctx->impl_im->call;                \
+  } while (0)
 
 #define KHR_TRY(...)                               \
   try {                                            \
@@ -1607,33 +1664,39 @@ int32_t khr_ctx_create(int32_t device, const khr_grid_desc* grid, khr_ctx** out)
 }
 int32_t khr_ctx_destroy(khr_ctx* ctx) {
   if (!ctx) return 0;
-  KHR_TRY({ delete ctx->impl; delete ctx; })
+  KHR_TRY({ delete ctx->impl; delete ctx->impl_im; delete ctx; })
 }
 int32_t khr_set_pml_sigma(khr_ctx* ctx, int32_t group, int32_t axis, const void* sigma, int32_t len) {
   NEED_CTX
   if (group < 0 || group > 1 || axis < 0 || axis > 2 || !sigma) return khr::fail("bad argument");
-  KHR_TRY(ctx->impl->set_pml_sigma(group, axis, sigma, len))
+  KHR_TRY(KHR_BOTH(set_pml_sigma(group, axis, sigma, len)))
 }
 int32_t khr_set_material_scalar(khr_ctx* ctx, int32_t kind, double value) {
   NEED_CTX
-  KHR_TRY(ctx->impl->set_material_scalar(kind, value))
+  KHR_TRY(KHR_BOTH(set_material_scalar(kind, value)))
 }
 int32_t khr_set_material_array(khr_ctx* ctx, int32_t kind, int32_t comp, const void* dense) {
   NEED_CTX
   if (!dense) return khr::fail("null array");
-  KHR_TRY(ctx->impl->set_material_array(kind, comp, dense))
+  KHR_TRY(KHR_BOTH(set_material_array(kind, comp, dense)))
 }
 int32_t khr_pole_register(khr_ctx* ctx, double omega0, double gamma, const void* sigma_dense, int32_t* pole_id) {
   NEED_CTX
   if (!sigma_dense) return khr::fail("null array");
-  KHR_TRY({ int id = ctx->impl->pole_register(omega0, gamma, sigma_dense); if (pole_id) *pole_id = id; })
+  KHR_TRY({
+    ctx->impl->registered_any = true;
+    int id = ctx->impl->pole_register(omega0, gamma, sigma_dense);
+    if (ctx->impl_im) ctx->impl_im->pole_register(omega0, gamma, sigma_dense);
+    if (pole_id) *pole_id = id;
+  })
 }
 int32_t khr_source_register(khr_ctx* ctx, int32_t comp, const int32_t start[3], const int32_t dims[3],
                             const void* amp_complex, int32_t time_kind, const double tp[4], int32_t* source_id) {
   NEED_CTX
   if (comp < 0 || comp > 5 || !start || !dims || !amp_complex || !tp) return khr::fail("bad argument");
   if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1) return khr::fail("empty source box");
-  KHR_TRY({ int id = ctx->impl->source_register(comp, start, dims, amp_complex, time_kind, tp); if (source_id) *source_id = id; })
+  // complex fields: sources drive the real part only (`+= real(a * A)`, Sources.jl:355-356)
+  KHR_TRY({ ctx->impl->registered_any = true; int id = ctx->impl->source_register(comp, start, dims, amp_complex, time_kind, tp); if (source_id) *source_id = id; })
 }
 int32_t khr_source_set_amplitude(khr_ctx* ctx, int32_t source_id, double re, double im) {
   NEED_CTX
@@ -1650,17 +1713,38 @@ int32_t khr_monitor_register(khr_ctx* ctx, int32_t comp, const int32_t start[3],
                              const double* freqs, int32_t decimation, int32_t* monitor_id) {
   NEED_CTX
   if (comp < 0 || comp > 5 || !start || !end || nfreq < 1 || !freqs) return khr::fail("bad argument");
-  KHR_TRY({ int id = ctx->impl->monitor_register(comp, start, end, nfreq, freqs, decimation); if (monitor_id) *monitor_id = id; })
+  KHR_TRY({ ctx->impl->registered_any = true; int id = ctx->impl->monitor_register(comp, start, end, nfreq, freqs, decimation); if (monitor_id) *monitor_id = id; })
 }
 int32_t khr_set_periodic(khr_ctx* ctx, int32_t axis, int32_t on) {
   NEED_CTX
   if (axis < 0 || axis > 2) return khr::fail("axis must be 0, 1 or 2");
   ctx->impl->periodic[axis] = on != 0;
+  if (ctx->impl_im) ctx->impl_im->periodic[axis] = on != 0;
+  return 0;
+}
+int32_t khr_set_complex_fields(khr_ctx* ctx) {
+  NEED_CTX
+  KHR_TRY({
+    if (ctx->impl_im) return 0;
+    if (ctx->impl->registered_any) throw std::string("khr_set_complex_fields must be called right after khr_ctx_create, before any registration");
+    const khr_grid_desc& g = ctx->impl->g;
+    if (g.dtype == KHR_F32) ctx->impl_im = new khr::Impl<float>(ctx->impl->device, g);
+    else ctx->impl_im = new khr::Impl<double>(ctx->impl->device, g);
+    ctx->impl->set_partner(ctx->impl_im);
+  })
+}
+int32_t khr_set_bloch(khr_ctx* ctx, int32_t axis, double k_times_L) {
+  NEED_CTX
+  if (axis < 0 || axis > 2) return khr::fail("axis must be 0, 1 or 2");
+  if (!ctx->impl_im) return khr::fail("khr_set_bloch needs complex fields: call khr_set_complex_fields first");
+  ctx->impl->periodic[axis] = true;
+  ctx->impl_im->periodic[axis] = true;
+  ctx->impl->bloch_kl[axis] = k_times_L;
   return 0;
 }
 int32_t khr_finalize_plan(khr_ctx* ctx) {
   NEED_CTX
-  KHR_TRY(ctx->impl->finalize())
+  KHR_TRY({ if (ctx->impl_im) ctx->impl_im->finalize(); ctx->impl->finalize(); })
 }
 int32_t khr_step(khr_ctx* ctx, int32_t nsteps) {
   NEED_CTX
@@ -1686,11 +1770,12 @@ int32_t khr_get_timestep(khr_ctx* ctx, int64_t* timestep) {
 int32_t khr_set_timestep(khr_ctx* ctx, int64_t timestep) {
   NEED_CTX
   ctx->impl->timestep = timestep;
+  if (ctx->impl_im) ctx->impl_im->timestep = timestep;
   return 0;
 }
 int32_t khr_reset_fields(khr_ctx* ctx) {
   NEED_CTX
-  KHR_TRY(ctx->impl->reset_fields())
+  KHR_TRY({ ctx->impl->reset_fields(); if (ctx->impl_im) ctx->impl_im->reset_fields(); })
 }
 int32_t khr_comm_unique_id(void* out128) {
   KHR_TRY({ khr::load_nccl(); NCCL_OK(khr::g_nccl.GetUniqueId(out128)); })
@@ -1707,6 +1792,12 @@ int32_t khr_field_read(khr_ctx* ctx, int32_t comp, void* dense_out) {
   NEED_CTX
   if (comp < 0 || comp > 5 || !dense_out) return khr::fail("bad argument");
   KHR_TRY(ctx->impl->field_read(comp, dense_out))
+}
+int32_t khr_field_read_imag(khr_ctx* ctx, int32_t comp, void* dense_out) {
+  NEED_CTX
+  if (comp < 0 || comp > 5 || !dense_out) return khr::fail("bad argument");
+  if (!ctx->impl_im) return khr::fail("khr_field_read_imag: the context has real fields");
+  KHR_TRY(ctx->impl_im->field_read(comp, dense_out))
 }
 int32_t khr_field_write(khr_ctx* ctx, int32_t comp, const void* dense_in) {
   NEED_CTX
@@ -1754,7 +1845,7 @@ int32_t khr_mode_overlap(khr_ctx* ctx, const int32_t monitor_ids[4], int32_t nor
 }
 int32_t khr_sync(khr_ctx* ctx) {
   NEED_CTX
-  KHR_TRY(ctx->impl->sync())
+  KHR_TRY({ ctx->impl->sync(); if (ctx->impl_im) ctx->impl_im->sync(); })
 }
 int32_t khr_get_stream(khr_ctx* ctx, void** cuda_stream) {
   NEED_CTX
@@ -1763,7 +1854,7 @@ int32_t khr_get_stream(khr_ctx* ctx, void** cuda_stream) {
 }
 int32_t khr_last_step_timing(khr_ctx* ctx, double* ms, int64_t* kernel_launches) {
   NEED_CTX
-  KHR_TRY({ ctx->impl->sync(); if (ms) *ms = ctx->impl->last_ms; if (kernel_launches) *kernel_launches = ctx->impl->last_launches; })
+  KHR_TRY({ ctx->impl->sync(); if (ctx->impl_im) ctx->impl_im->sync(); if (ms) *ms = ctx->impl->last_ms; if (kernel_launches) *kernel_launches = ctx->impl->last_launches; })
 }
 int32_t khr_voxel_census(khr_ctx* ctx, int64_t counts[4]) {
   NEED_CTX
@@ -1771,7 +1862,7 @@ int32_t khr_voxel_census(khr_ctx* ctx, int64_t counts[4]) {
 }
 int32_t khr_set_profiling(khr_ctx* ctx, int32_t mode) {
   NEED_CTX
-  KHR_TRY(ctx->impl->set_profiling(mode))
+  KHR_TRY({ ctx->impl->set_profiling(mode); if (ctx->impl_im) ctx->impl_im->set_profiling(mode); })
 }
 int32_t khr_kernel_stat_get(khr_ctx* ctx, int32_t index, khr_kernel_stat* out, int32_t* count) {
   NEED_CTX
@@ -1779,7 +1870,7 @@ int32_t khr_kernel_stat_get(khr_ctx* ctx, int32_t index, khr_kernel_stat* out, i
 }
 int32_t khr_device_bytes(khr_ctx* ctx, int64_t* bytes) {
   NEED_CTX
-  *bytes = ctx->impl->dev_bytes;
+  *bytes = ctx->impl->dev_bytes + (ctx->impl_im ? ctx->impl_im->dev_bytes : 0);
   return 0;
 }
 

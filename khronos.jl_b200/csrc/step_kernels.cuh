@@ -794,6 +794,7 @@ template <class T>
 struct MonDesc {
   T* M;               // complex interleaved (nx,ny,nz,nf)
   const T* F;         // field array (ghosted layout)
+  const T* Fi;        // imaginary part of the field (complex fields, Bloch boundaries) or null
   const T* freqs;     // nf values
   int s[3];           // local start cell (may start below 1 in z when clipped by host)
   int n[3];           // extent of the part this rank accumulates
@@ -832,7 +833,8 @@ __global__ void __launch_bounds__(256) dft_kernel(const MonDesc<T>* __restrict__
   const int x = (int)(cell % m.n[0]);
   const int y = (int)((cell / m.n[0]) % m.n[1]);
   const int z = (int)(cell / ((long long)m.n[0] * m.n[1]));
-  const T f = m.F[plane * (long long)(m.s[2] + z) + (long long)px * (m.s[1] + y) + (m.s[0] + x + XO)];
+  const long long fo = plane * (long long)(m.s[2] + z) + (long long)px * (m.s[1] + y) + (m.s[0] + x + XO);
+  const T f = m.F[fo];
   const long long mcell = (long long)(x + m.moff[0]) +
                           (long long)m.mn[0] * ((long long)(y + m.moff[1]) + (long long)m.mn[1] * (z + m.moff[2]));
   const long long mstride = (long long)m.mn[0] * m.mn[1] * m.mn[2];
@@ -841,8 +843,16 @@ __global__ void __launch_bounds__(256) dft_kernel(const MonDesc<T>* __restrict__
     T* mp = m.M + 2 * (mcell + mstride * (k0 + k));
     // M += (dt * e) * F  (complex accumulate, Monitors.jl:353-357)
     T re = mp[0], im = mp[1];
-    mp[0] = re + bt.ph_re[off + k] * f;
-    mp[1] = im + bt.ph_im[off + k] * f;
+    if (m.Fi == nullptr) {
+      mp[0] = re + bt.ph_re[off + k] * f;
+      mp[1] = im + bt.ph_im[off + k] * f;
+    } else {
+      // complex field: (dt e) * (f + i fi) = (pr f - pi fi) + i (pr fi + pi f)
+      const T fi = m.Fi[fo];
+      const T pr = bt.ph_re[off + k], pi = bt.ph_im[off + k];
+      mp[0] = re + (pr * f - pi * fi);
+      mp[1] = im + (pr * fi + pi * f);
+    }
   }
 }
 
@@ -863,6 +873,39 @@ __global__ void __launch_bounds__(256) wrap_kernel(T* f0, T* f1, T* f2, long lon
   T* f = blockIdx.y == 0 ? f0 : (blockIdx.y == 1 ? f1 : f2);
   f[o] = f[o + sa * n_axis];              // ghost 0    <- cell N
   f[o + sa * (n_axis + 1)] = f[o + sa];   // ghost N+1  <- cell 1
+}
+
+// Bloch / periodic wrap-around of complex fields kept as two real arrays (real and imaginary
+// parts, identical layout): copy, then multiply by the phase in ComplexF64 and store back as
+// Complex{T} (Chunking.jl:1735-1764, 2163-2167).  rev = exp(-i k L) goes with the lower ghost,
+// fwd = exp(+i k L) with the upper one; a factor of exactly 1 is skipped like the reference does.
+template <class T>
+struct BlochWrapArgs {
+  T* fr[3];
+  T* fi[3];
+  long long base, sa, s1, s2;
+  int n_axis, n1, n2;
+  double rev_re, rev_im, fwd_re, fwd_im;
+  int apply_rev, apply_fwd;
+};
+template <class T>
+__global__ void __launch_bounds__(256) bloch_wrap_kernel(const __grid_constant__ BlochWrapArgs<T> a) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (long long)a.n1 * a.n2) return;
+  const int i1 = (int)(q % a.n1) + 1, i2 = (int)(q / a.n1) + 1;
+  const long long o = a.base + a.s1 * i1 + a.s2 * i2;
+  T* fr = a.fr[blockIdx.y];
+  T* fi = a.fi[blockIdx.y];
+  {  // ghost 0 <- cell N
+    double vr = (double)fr[o + a.sa * a.n_axis], vi = (double)fi[o + a.sa * a.n_axis];
+    if (a.apply_rev) { const double r = vr * a.rev_re - vi * a.rev_im, i = vr * a.rev_im + vi * a.rev_re; vr = r; vi = i; }
+    fr[o] = (T)vr; fi[o] = (T)vi;
+  }
+  {  // ghost N+1 <- cell 1
+    double vr = (double)fr[o + a.sa], vi = (double)fi[o + a.sa];
+    if (a.apply_fwd) { const double r = vr * a.fwd_re - vi * a.fwd_im, i = vr * a.fwd_im + vi * a.fwd_re; vr = r; vi = i; }
+    fr[o + a.sa * (a.n_axis + 1)] = (T)vr; fi[o + a.sa * (a.n_axis + 1)] = (T)vi;
+  }
 }
 
 // ----------------------------------------------------------------------------

@@ -162,8 +162,8 @@ class Periodic:
 
 
 class Bloch:
-    """Bloch(k): only k == 0 (plain periodicity, real fields) is on the B200 path; k != 0 needs
-    complex fields (Fields.jl:147-159) and is rejected."""
+    """Bloch(k) (DataStructures.jl:158-160): wrap-around with the phase exp(i k L); any Bloch side
+    switches the simulation to complex fields (Fields.jl:140-159)."""
     code = 1
 
     def __init__(self, k=0.0):
@@ -268,14 +268,20 @@ class Simulation:
         # Bloch / PECBoundary / PMCBoundary instances (or classes); None == PML everywhere
         self.bc_codes = None
         self.periodic = [False, False, False]
+        self.complex_fields = False          # _needs_complex_fields (Fields.jl:140-159)
+        self.bloch_k = [0.0, 0.0, 0.0]
         if boundary_conditions is not None:
             codes = []
-            for axis_bcs in boundary_conditions:
+            for a, axis_bcs in enumerate(boundary_conditions):
                 for bc in axis_bcs:
-                    if isinstance(bc, Bloch) and bc.k != 0.0:
-                        raise _lib.KhronosError("Bloch(k != 0) needs complex fields (Fields.jl:147-159): not "
-                                                "supported by the B200 path")
+                    if isinstance(bc, Bloch):
+                        self.complex_fields = True
                     codes.append(int(bc.code))
+                # Chunking.jl:1739-1744: k of the first side if it is Bloch, else of the second
+                if isinstance(axis_bcs[0], Bloch):
+                    self.bloch_k[a] = axis_bcs[0].k
+                elif len(axis_bcs) > 1 and isinstance(axis_bcs[1], Bloch):
+                    self.bloch_k[a] = axis_bcs[1].k
             if len(codes) != 6:
                 raise ValueError("boundary_conditions must be three [minus, plus] pairs")
             self.bc_codes = codes
@@ -527,6 +533,8 @@ class Simulation:
         ctx = C.c_void_p()
         _lib.check(L.khr_ctx_create(self.device, C.byref(desc), C.byref(ctx)))
         self.ctx = ctx
+        if self.complex_fields:
+            _lib.check(L.khr_set_complex_fields(ctx))
         zsl = slice(z_start - 1, z_start - 1 + nzl)
         if self.sigma is not None:
             for grp in (_lib.GROUP_H, _lib.GROUP_E):
@@ -570,7 +578,10 @@ class Simulation:
                                               m.decimation, C.byref(mid)))
             m.id = mid.value
         for a in range(3):
-            if self.periodic[a]:
+            if self.periodic[a] and self.complex_fields:
+                # phase = exp(i * bloch_k * L), L = sim.cell_size[axis] (Chunking.jl:1745-1747)
+                _lib.check(L.khr_set_bloch(ctx, a, float(self.bloch_k[a]) * float(g.cell_size[a])))
+            elif self.periodic[a]:
                 _lib.check(L.khr_set_periodic(ctx, a, 1))
         _lib.check(L.khr_finalize_plan(ctx))
         if self.nranks > 1:
@@ -719,11 +730,18 @@ class Simulation:
         self.timestep = 0
 
     # -------------------------------------------------------------- access
-    def get_field(self, comp):
-        """Local slab of a field component, dense (Nx,Ny,Nz_local) (Visualization.jl:294-333)."""
+    def get_field(self, comp, part="real"):
+        """Local slab of a field component, dense (Nx,Ny,Nz_local) (Visualization.jl:294-333);
+        part="imag" / "complex" for complex fields (Bloch boundaries)."""
+        L = _lib.lib()
         out = np.empty((self.Nx, self.Ny, self.nz_local), dtype=self.T, order="F")
-        _lib.check(_lib.lib().khr_field_read(self.ctx, comp, out.ctypes.data))
-        return out
+        if part in ("real", "complex"):
+            _lib.check(L.khr_field_read(self.ctx, comp, out.ctypes.data))
+        if part == "real":
+            return out
+        im = np.empty((self.Nx, self.Ny, self.nz_local), dtype=self.T, order="F")
+        _lib.check(L.khr_field_read_imag(self.ctx, comp, im.ctypes.data))
+        return im if part == "imag" else out + 1j * im
 
     def set_field(self, comp, arr):
         a = np.asfortranarray(np.asarray(arr, dtype=self.T))

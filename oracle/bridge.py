@@ -18,6 +18,9 @@ def oracle_from_simulation(sim):
     assert tuple(o.N) == tuple(g.N)
     if getattr(sim, "bc_codes", None) is not None:
         o.set_boundary_conditions(sim.bc_codes)
+    if getattr(sim, "complex_fields", False):
+        for a in range(3):
+            o.set_bloch(a, sim.bloch_k[a])
     for key in ("eps_inv", "mu_inv", "sigma_D", "sigma_B"):
         arr = sim.material_arrays[key]
         if arr is not None:

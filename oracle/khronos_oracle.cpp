@@ -261,6 +261,17 @@ struct Sim {
   // Periodic / PEC / PMC sides also zero the PML thickness (src/Boundaries.jl:100-110)
   bool periodic[3] = {false, false, false};
   bool no_pml_side[3][2] = {{false, false}, {false, false}, {false, false}};
+  // Bloch boundaries (src/DataStructures.jl:158-160): any Bloch side makes every field array
+  // Complex{T} (src/Fields.jl:140-159).  All update coefficients are real and Julia multiplies a
+  // real by a complex componentwise, so the complex simulation is restated as two real ones that
+  // share every input: this object carries the real parts, `im` the imaginary parts.  They couple
+  // only where the reference multiplies two complex numbers: the Bloch phase of the wrap-around
+  // copy (src/Chunking.jl:1735-1764, 2164-2167) and the DFT phasor (src/Monitors/Monitors.jl:355,375).
+  // Sources drive the real part only (`+= real(a * A)`, src/Sources/Sources.jl:355-356).
+  bool complex_fields = false;
+  double bloch_k[3] = {0.0, 0.0, 0.0};
+  Sim<T>* im = nullptr;
+  ~Sim() { delete im; }
   // --- derived grid (src/DataStructures.jl:732-741) -------------------------
   int N[3];
   T cell_size[3], dl[3], dt;
@@ -365,8 +376,26 @@ struct Sim {
             lo[t2] = hi[t2] = g0[t2] = g1[t2] = b;
             hi[axis] = n[axis]; g0[axis] = 0;          // upper interior -> lower ghost
             lo[axis] = 1;       g1[axis] = n[axis] + 1; // lower interior -> upper ghost
-            F.at(g0[0], g0[1], g0[2]) = F.at(hi[0], hi[1], hi[2]);
-            F.at(g1[0], g1[1], g1[2]) = F.at(lo[0], lo[1], lo[2]);
+            if (!im) {
+              F.at(g0[0], g0[1], g0[2]) = F.at(hi[0], hi[1], hi[2]);
+              F.at(g1[0], g1[1], g1[2]) = F.at(lo[0], lo[1], lo[2]);
+            } else {
+              // copy, then `dst .*= phase_factor` in ComplexF64, stored back as Complex{T}
+              // (Chunking.jl:2163-2167); phase_rev = exp(-i k L) on the lower ghost, phase_fwd =
+              // exp(+i k L) on the upper one (:1746-1764); skipped when the factor is exactly 1
+              Arr3<T>& G = (group == 0) ? im->chunks[0].H[d] : im->chunks[0].E[d];
+              const double kl = bloch_k[axis] * (double)cell_size[axis];
+              const std::complex<double> pf = std::exp(std::complex<double>(0.0, 1.0) * kl);
+              const std::complex<double> pr = std::exp(-std::complex<double>(0.0, 1.0) * kl);
+              auto put = [&](const int* dst, const int* src, const std::complex<double>& ph) {
+                std::complex<double> v((double)F.at(src[0], src[1], src[2]), (double)G.at(src[0], src[1], src[2]));
+                if (ph != std::complex<double>(1.0)) v = v * ph;
+                F.at(dst[0], dst[1], dst[2]) = (T)v.real();
+                G.at(dst[0], dst[1], dst[2]) = (T)v.imag();
+              };
+              put(g0, hi, pr);
+              put(g1, lo, pf);
+            }
           }
       }
     }
@@ -589,6 +618,15 @@ struct Sim {
     timestep = 0;
     sources_active = true;
     prepared = true;
+    if (im) { delete im; im = nullptr; }
+    if (complex_fields) {
+      im = new Sim<T>(*this);          // same grid, materials, sigma profiles, poles
+      im->im = nullptr;
+      im->complex_fields = false;
+      im->sources.clear();             // the imaginary part has no sources
+      im->monitors.clear();            // the accumulators live here and read both parts
+      im->prepare(mode_, nranks);
+    }
   }
 
   // ------------------------------------------------------------------------
@@ -861,7 +899,13 @@ struct Sim {
             for (int x = 0; x < m.n[0]; ++x) {
               T F = field_at(m.comp, m.start[0] + x, m.start[1] + y, m.start[2] + z);
               std::complex<T>& M = m.M[k * ncell + (size_t)x + (size_t)m.n[0] * ((size_t)y + (size_t)m.n[1] * z)];
-              M = std::complex<T>(M.real() + wr * F, M.imag() + wi * F);
+              if (!im) {
+                M = std::complex<T>(M.real() + wr * F, M.imag() + wi * F);
+              } else {
+                // (dt e) * F with F complex: (wr Fr - wi Fi, wr Fi + wi Fr)
+                T Fi = im->field_at(m.comp, m.start[0] + x, m.start[1] + y, m.start[2] + z);
+                M = std::complex<T>(M.real() + (wr * F - wi * Fi), M.imag() + (wr * Fi + wi * F));
+              }
             }
       }
     }
@@ -945,16 +989,19 @@ struct Sim {
     }
     if (sources_active) step_sources(0, t);
     for (auto& c : chunks) { step_curl(c, 0); update_field(c, 0); }
+    if (im) for (auto& c : im->chunks) { im->step_curl(c, 0); im->update_field(c, 0); }
     if (chunks.size() > 1) exchange_halos(0);
     wrap_periodic(0);
     update_monitors(0, t);
     if (sources_active) step_sources(1, t_half);
     for (auto& c : chunks) { step_curl(c, 1); update_field(c, 1); }
+    if (im) for (auto& c : im->chunks) { im->step_curl(c, 1); im->update_field(c, 1); }
     if (!chi3_literal_order) step_chi3();
     if (chunks.size() > 1) exchange_halos(1);
     wrap_periodic(1);
     if (chi3_literal_order) step_chi3();
     step_polarization();
+    if (im) im->step_polarization();
     update_monitors(1, t_half);
     timestep += 1;
   }
@@ -1225,6 +1272,13 @@ void ko_set_boundary_conditions(void* hv, const int* bc6) {
   });
 }
 
+// Bloch(k) on `axis` (both sides; the periodic flag itself comes from ko_set_boundary_conditions):
+// switches the simulation to complex fields.  Before ko_prepare.  Single chunk, no chi3.
+void ko_set_bloch(void* hv, int axis, double k) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, { S.complex_fields = true; S.bloch_k[axis] = k; });
+}
+
 void ko_set_chi3_literal_order(void* hv, int v) {
   Handle* h = (Handle*)hv;
   DISPATCH(h, S.chi3_literal_order = v != 0);
@@ -1264,7 +1318,8 @@ void ko_get_field(void* hv, int which, int comp, double* out) {
   DISPATCH(h, {
     size_t nx = S.N[0], ny = S.N[1];
     for (auto& c : S.chunks) {
-      auto& F = (which == 0) ? (comp < 3 ? c.E[comp] : c.H[comp - 3]) : (comp < 3 ? c.D[comp] : c.B[comp - 3]);
+      auto& ci = (which == 2) ? S.im->chunks[&c - &S.chunks[0]] : c;   // which == 2: imaginary part of E/H
+      auto& F = (which != 1) ? (comp < 3 ? ci.E[comp] : ci.H[comp - 3]) : (comp < 3 ? c.D[comp] : c.B[comp - 3]);
       for (int iz = 1; iz <= c.n[2]; ++iz)
         for (int iy = 1; iy <= c.n[1]; ++iy)
           for (int ix = 1; ix <= c.n[0]; ++ix)

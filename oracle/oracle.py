@@ -70,6 +70,7 @@ def lib():
         L.ko_step.argtypes = [C.c_void_p, C.c_int]
         L.ko_set_sources_active.argtypes = [C.c_void_p, C.c_int]
         L.ko_set_chi3_literal_order.argtypes = [C.c_void_p, C.c_int]
+        L.ko_set_bloch.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.ko_set_boundary_conditions.argtypes = [C.c_void_p, ip]
         L.ko_timestep.restype = C.c_long
         L.ko_num_threads.restype = C.c_int
@@ -262,6 +263,11 @@ class OracleSim:
         (Kernels.jl:76-79); default False = before them (neighbours see the corrected E)."""
         self.L.ko_set_chi3_literal_order(self.h, int(bool(on)))
 
+    def set_bloch(self, axis, k):
+        """Bloch(k) on both sides of `axis` (DataStructures.jl:158-160): complex fields; the axis must
+        also be flagged periodic through set_boundary_conditions."""
+        self.L.ko_set_bloch(self.h, int(axis), float(k))
+
     def set_boundary_conditions(self, bc6):
         """bc6: per (axis, side) 0 = PML, 1 = Periodic, 2 = PEC, 3 = PMC (before prepare)."""
         b, bp = _i(np.asarray(bc6, dtype=np.int32).reshape(6))
@@ -303,7 +309,8 @@ class OracleSim:
 
     def get_field(self, comp, which="EH"):
         out = np.zeros(self.N[::-1])
-        self.L.ko_get_field(self.h, 0 if which == "EH" else 1, int(comp), out.ctypes.data_as(C.POINTER(C.c_double)))
+        self.L.ko_get_field(self.h, {"EH": 0, "DB": 1, "imag": 2}[which], int(comp),
+                            out.ctypes.data_as(C.POINTER(C.c_double)))
         return out.transpose(2, 1, 0)
 
     def set_field(self, comp, arr):

@@ -36,10 +36,50 @@ def test_oracle_periodic_translation_invariance():
     assert np.abs(a[2][0, 0, 0]) > 0
 
 
-def test_bloch_nonzero_k_is_rejected():
-    with pytest.raises(kb.KhronosError):
-        kb.Simulation([2, 2, 2], [0, 0, 0], 10, [], boundaries=[[0, 0]] * 3,
-                      boundary_conditions=[[kb.Bloch(k=0.3), kb.Bloch(k=0.3)], [kb.PML(), kb.PML()], [kb.PML(), kb.PML()]])
+def _oracle_bloch(center, nsteps, k, dtype=np.float64):
+    from bridge import oracle_from_simulation
+    bc = [[kb.Bloch(k[0]), kb.Bloch(k[0])], [kb.Bloch(k[1]), kb.Periodic()], [kb.Periodic(), kb.Bloch(k[2])]]
+    sim = kb.Simulation([2.0, 1.5, 1.0], [0, 0, 0], 8, [kb.UniformSource(CW, kb.EZ, center, [0, 0, 0]),
+                                                         kb.UniformSource(CW, kb.HX, center, [0, 0, 0])],
+                        boundaries=[[0.0, 0.0]] * 3, boundary_conditions=bc, dtype=dtype)
+    assert sim.complex_fields and sim.bloch_k == list(k)
+    o, _ = oracle_from_simulation(sim)
+    o.step(nsteps)
+    return [o.get_field(c) + 1j * o.get_field(c, which="imag") for c in range(6)], sim
+
+
+def test_oracle_bloch_k0_is_bit_identical_to_periodic():
+    """Bloch(k = 0) allocates complex fields (Fields.jl:140-159) but its phase factor is exactly 1
+    and is skipped (Chunking.jl:2165): real parts equal the Periodic run, imaginary parts stay 0."""
+    a = _oracle_fields([0.25, 0.0, -0.125], 40, np.float64)
+    b, _ = _oracle_bloch([0.25, 0.0, -0.125], 40, (0.0, 0.0, 0.0))
+    for fa, fb in zip(a, b):
+        assert np.array_equal(fa, fb.real) and not fb.imag.any()
+
+
+def test_oracle_bloch_translation_covariance():
+    """Exact symmetry of the discrete update with f(x + L) = f(x) exp(i k L) on every axis: moving the
+    source by whole cells rolls the fields, and the cells that wrapped around pick up exp(-i k L)
+    (positive shift) or exp(+i k L) (negative shift).  Pins the sign convention of both ghost copies
+    (Chunking.jl:1735-1764) and the complex arithmetic of the wrap."""
+    k = (0.7, -0.4, 1.1)
+    a, sim = _oracle_bloch([0.0, 0.0, 0.0], 48, k)
+    b, _ = _oracle_bloch([0.5, -0.375, 0.25], 48, k)       # +4, -3, +2 cells
+    L = [float(v) for v in sim.grid.cell_size]
+    shifts = (4, -3, 2)
+    assert max(np.abs(f.imag).max() for f in a) > 1e-3      # the phase really mixes the two parts
+    for fa, fb in zip(a, b):
+        want = fa.copy()
+        for ax, m in enumerate(shifts):
+            want = np.roll(want, m, axis=ax)
+            sl = [slice(None)] * 3
+            if m > 0:
+                sl[ax] = slice(0, m)
+                want[tuple(sl)] *= np.exp(-1j * k[ax] * L[ax])
+            else:
+                sl[ax] = slice(m, None)
+                want[tuple(sl)] *= np.exp(+1j * k[ax] * L[ax])
+        assert np.linalg.norm(want - fb) < 1e-12 * np.linalg.norm(fb)
 
 
 def test_periodic_sides_drop_their_pml_except_sigma_dz_quirk():
@@ -96,3 +136,67 @@ def test_gpu_periodic_z_with_sigma_dz_quirk():
     p.step(25)
     assert p.total_field_error() < 1e-5
     assert rel_l2(p.k.get_dft(p.kmon[0]), p.o.get_dft(p.omon[0])) < 1e-5
+
+
+def _bloch_pair(dtype, bc, pml, poles=()):
+    return Pair([2.0, 1.6, 2.4], 10, pml, dtype, boundary_conditions=bc, poles=poles,
+                sources=[(kb.EZ, [0.1, -0.2, 0.0], [0, 0, 0], CW), (kb.HY, [-0.3, 0.1, 0.2], [0.4, 0, 0], CW)],
+                monitors=[(kb.EZ, [0, 0, 0.3], [2.0, 1.6, 0], [0.9, 1.1], 1), (kb.HX, [0, 0.2, 0], [2.0, 0, 1.0], [1.0], 1)])
+
+
+def _check_complex(p, nsteps, tol):
+    p.step(nsteps)
+    num = den = 0.0
+    for c in range(6):
+        a = p.k.get_field(c, part="complex").astype(np.complex128)
+        b = p.o.get_field(c) + 1j * p.o.get_field(c, which="imag")
+        num += np.sum(np.abs(a - b) ** 2)
+        den += np.sum(np.abs(b) ** 2)
+    assert den > 0 and (num / den) ** 0.5 < tol, (num / den) ** 0.5
+    for km, om in zip(p.kmon, p.omon):
+        assert rel_l2(p.k.get_dft(km), p.o.get_dft(om)) < tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_gpu_bloch_xy_pml_z(dtype):
+    """Bloch(k) on x and y (complex fields as two real field sets, phase in the wrap), PML on z,
+    complex DFT accumulation, a Drude block that the imaginary part must also carry."""
+    bc = [[kb.Bloch(0.7), kb.Bloch(0.7)], [kb.Periodic(), kb.Bloch(-0.4)], [kb.PML(), kb.PML()]]
+    sg = np.zeros((20, 16, 24), dtype=dtype)
+    sg[5:12, 3:9, 10:15] = 1.5
+    p = _bloch_pair(dtype, bc, [0.0, 0.0, 0.6], poles=[(0.0, 0.3, sg)])
+    _check_complex(p, 90, 1e-5 if dtype is np.float32 else 1e-12)
+    assert np.abs(p.k.get_field(kb.EZ, part="imag")).max() > 1e-3
+
+
+@pytest.mark.gpu
+def test_gpu_bloch_all_axes_and_translation_covariance():
+    bc = [[kb.Bloch(0.7), kb.Bloch(0.7)], [kb.Bloch(-0.4), kb.Bloch(-0.4)], [kb.Bloch(1.1), kb.Bloch(1.1)]]
+    p = _bloch_pair(np.float64, bc, [0.0, 0.0, 0.0])
+    _check_complex(p, 60, 1e-12)
+
+
+@pytest.mark.gpu
+def test_gpu_bloch_k0_is_bit_identical_to_periodic():
+    bc0 = [[kb.Bloch(0.0), kb.Bloch(0.0)], [kb.Periodic(), kb.Periodic()], [kb.PML(), kb.PML()]]
+    bcp = [[kb.Periodic(), kb.Periodic()], [kb.Periodic(), kb.Periodic()], [kb.PML(), kb.PML()]]
+    a = _bloch_pair(np.float32, bc0, [0.0, 0.0, 0.6])
+    b = _bloch_pair(np.float32, bcp, [0.0, 0.0, 0.6])
+    a.k.step(50)
+    b.k.step(50)
+    for c in range(6):
+        assert np.array_equal(a.k.get_field(c), b.k.get_field(c))
+        assert not a.k.get_field(c, part="imag").any()
+    for ka, kb_ in zip(a.kmon, b.kmon):
+        assert np.array_equal(a.k.get_dft(ka), b.k.get_dft(kb_))
+
+
+@pytest.mark.gpu
+def test_gpu_complex_field_restrictions():
+    bc = [[kb.Bloch(0.7), kb.Bloch(0.7)], [kb.PML(), kb.PML()], [kb.PML(), kb.PML()]]
+    chi3 = np.zeros((20, 16, 24), dtype=np.float32)
+    chi3[8:12, 6:10, 10:14] = 1.0
+    with pytest.raises(kb.KhronosError, match="chi3"):
+        Pair([2.0, 1.6, 2.4], 10, [0.0, 0.4, 0.4], np.float32, boundary_conditions=bc, chi3=chi3,
+             sources=[(kb.EZ, [0, 0, 0], [0, 0, 0], CW)])
