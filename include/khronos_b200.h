@@ -75,6 +75,13 @@ int32_t khr_ctx_destroy(khr_ctx* ctx);
  * group: KHR_GROUP_H -> σB*, KHR_GROUP_E -> σD*. */
 int32_t khr_set_pml_sigma(khr_ctx* ctx, int32_t group, int32_t axis, const void* sigma, int32_t len);
 
+/* DataStructures.jl:737-739: non-uniform grid — Δ of `axis` as a vector with one spacing per
+ * cell (N global values, context dtype).  The curl then multiplies by inv(Δ[i]) of the updated
+ * cell (get_inv_dx(Δ::AbstractVector, i), Helpers.jl:283-291); khr_grid_desc.dl keeps the
+ * representative scalar the reference uses elsewhere (Δ[1], utils.jl:4-5) and dt =
+ * min over all spacings x Courant (DataStructures.jl:692,740).  Before khr_finalize_plan. */
+int32_t khr_set_grid_spacing(khr_ctx* ctx, int32_t axis, const void* spacing, int32_t len);
+
 /* Geometry.jl:450-663 init_geometry outputs: scalar ε⁻¹/μ⁻¹ or per-voxel arrays,
  * and the material conductivities σD/σB (absorbers, Geometry.jl:708-789). */
 int32_t khr_set_material_scalar(khr_ctx* ctx, int32_t kind, double value);

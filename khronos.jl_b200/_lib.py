@@ -51,6 +51,7 @@ _SIGNATURES = {
     "khr_ctx_create": (_I, [_I, C.POINTER(GridDesc), C.POINTER(_P)]),
     "khr_ctx_destroy": (_I, [_P]),
     "khr_set_pml_sigma": (_I, [_P, _I, _I, _P, _I]),
+    "khr_set_grid_spacing": (_I, [_P, _I, _P, _I]),
     "khr_set_material_scalar": (_I, [_P, _I, C.c_double]),
     "khr_set_material_array": (_I, [_P, _I, _I, _P]),
     "khr_pole_register": (_I, [_P, C.c_double, C.c_double, _P, C.POINTER(_I)]),

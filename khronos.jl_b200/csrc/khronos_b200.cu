@@ -86,6 +86,7 @@ struct Base {
   virtual ~Base() {}
   khr_grid_desc g;
   virtual void set_pml_sigma(int group, int axis, const void* s, int len) = 0;
+  virtual void set_grid_spacing(int axis, const void* d, int len) = 0;
   virtual void set_material_scalar(int kind, double v) = 0;
   virtual void set_material_array(int kind, int comp, const void* dense) = 0;
   virtual int pole_register(double omega0, double gamma, const void* sigma) = 0;
@@ -185,6 +186,8 @@ struct Impl : Base {
   T* sigM[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // [0]=sigma_B [1]=sigma_D
   T* Cst[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
   T* Dst[3] = {nullptr, nullptr, nullptr};  // D on dispersive / Kerr voxels
+  T* idv[3] = {nullptr, nullptr, nullptr};  // non-uniform grid: inv(Δ[i]) per local cell (null: uniform axis)
+  bool nonuniform = false;
   T* chi3 = nullptr;                        // Kerr coefficient (Geometry.jl:610-660), material layout
   int chi3_box[6] = {1, 1, 1, 0, 0, 0};
   std::vector<uint8_t> chi3_mask;
@@ -370,6 +373,24 @@ struct Impl : Base {
     for (int i = 1; i <= nl; ++i) v[i - 1] = sp[2 * (i + off) - 2];
     have_sigma[group][axis] = true;
   }
+  // DataStructures.jl:737-739: Δx/Δy/Δz may be vectors (one spacing per cell); the kernels then use
+  // inv(Δ[i]) of the updated cell (Helpers.jl:283-291).  `d`: N global values of the context dtype.
+  void set_grid_spacing(int axis, const void* d, int len) override {
+    if (finalized) throw std::string("khr_set_grid_spacing after khr_finalize_plan");
+    if (len != g.n[axis]) throw std::string("grid spacing vector must have one entry per cell of the axis");
+    const T* sp = (const T*)d;
+    const int nl = N[axis], off = (axis == 2) ? g.z_start - 1 : 0;
+    const int cap = round_up(nl, 4) + 8;
+    std::vector<T> inv((size_t)cap, T(1) / dl[axis]);
+    for (int i = 0; i < nl; ++i) {
+      if (!(sp[i + off] > T(0))) throw std::string("grid spacing must be positive");
+      inv[(size_t)i] = T(1) / sp[i + off];   // inv(Δ[i])
+    }
+    if (!idv[axis]) idv[axis] = dalloc((size_t)cap, false);
+    CUDA_OK(cudaMemcpyAsync(idv[axis], inv.data(), (size_t)cap * sizeof(T), cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    nonuniform = true;
+  }
   void set_material_scalar(int kind, double v) override {
     if (kind == KHR_MAT_EPS_INV) m_scalar[1] = (T)v;
     else if (kind == KHR_MAT_MU_INV) m_scalar[0] = (T)v;
@@ -500,7 +521,8 @@ struct Impl : Base {
   void finalize() override {
     if (finalized) throw std::string("khr_finalize_plan called twice");
     // the wrap kernels are plain launches between the chain kernels: keep stream semantics simple
-    if (any_periodic() || in_pair) pdl = false;
+    if (any_periodic() || in_pair || nonuniform) pdl = false;
+    if (nonuniform) axis_spec = false;
     if (in_pair && g.nranks > 1) throw std::string("complex fields (Bloch boundaries) are single-GPU for now: nranks must be 1");
     if (in_pair && chi3) throw std::string("chi3 with complex fields is not supported (|E|^2 couples the real and imaginary parts)");
     // per-axis PML cell sets from both groups' profiles
@@ -583,6 +605,15 @@ struct Impl : Base {
         CUDA_OK(cudaMemcpyAsync(coef[gq][a][2], ip.data(), len * sizeof(T), cudaMemcpyHostToDevice, stream));
         CUDA_OK(cudaStreamSynchronize(stream));
       }
+    if (nonuniform)
+      for (int a = 0; a < 3; ++a)
+        if (!idv[a]) {  // a uniform axis of a non-uniform grid: constant vector
+          const int cap = round_up(N[a], 4) + 8;
+          std::vector<T> inv((size_t)cap, T(1) / dl[a]);
+          idv[a] = dalloc((size_t)cap, false);
+          CUDA_OK(cudaMemcpyAsync(idv[a], inv.data(), (size_t)cap * sizeof(T), cudaMemcpyHostToDevice, stream));
+          CUDA_OK(cudaStreamSynchronize(stream));
+        }
     build_source_slots();
     build_tables();
     // monitors
@@ -969,6 +1000,14 @@ struct Impl : Base {
       cfg.attrs = at; cfg.numAttrs = 1;
       if (marr) CUDA_OK(cudaLaunchKernelEx(&cfg, step_kernel<T, GROUP, MODE, true, AXM>, p));
       else CUDA_OK(cudaLaunchKernelEx(&cfg, step_kernel<T, GROUP, MODE, false, AXM>, p));
+    } else if (nonuniform) {
+      // non-uniform grids use the general (AXM = 7) kernels
+      if constexpr (AXM == 7) {
+        if (marr) step_kernel<T, GROUP, MODE, true, 7, true><<<n, CTA, 0, st>>>(p);
+        else step_kernel<T, GROUP, MODE, false, 7, true><<<n, CTA, 0, st>>>(p);
+      } else {
+        throw std::string("internal: axis-specialised kernels have no non-uniform variant");
+      }
     } else {
       if (marr) step_kernel<T, GROUP, MODE, true, AXM><<<n, CTA, 0, st>>>(p);
       else step_kernel<T, GROUP, MODE, false, AXM><<<n, CTA, 0, st>>>(p);
@@ -1055,6 +1094,7 @@ struct Impl : Base {
       p.C[d] = Cst[gq][d];
       p.n[d] = N[d];
       p.idl[d] = T(1) / dl[d];  // inv(Δ) (Helpers.jl:283)
+      p.idv[d] = idv[d];
     }
     p.plane = (long long)PX * PY;
     p.px = PX;
@@ -1670,6 +1710,11 @@ int32_t khr_set_pml_sigma(khr_ctx* ctx, int32_t group, int32_t axis, const void*
   NEED_CTX
   if (group < 0 || group > 1 || axis < 0 || axis > 2 || !sigma) return khr::fail("bad argument");
   KHR_TRY(KHR_BOTH(set_pml_sigma(group, axis, sigma, len)))
+}
+int32_t khr_set_grid_spacing(khr_ctx* ctx, int32_t axis, const void* spacing, int32_t len) {
+  NEED_CTX
+  if (axis < 0 || axis > 2 || !spacing) return khr::fail("bad argument");
+  KHR_TRY(KHR_BOTH(set_grid_spacing(axis, spacing, len)))
 }
 int32_t khr_set_material_scalar(khr_ctx* ctx, int32_t kind, double value) {
   NEED_CTX

@@ -83,6 +83,7 @@ struct StepParams {
   int px;             // PX
   int n[3];           // local cells
   T dt, idl[3];
+  const T* idv[3];    // non-uniform grid: inv(Δ[i]) per cell and axis, index i-1 (Helpers.jl:283-284), else null
   // constitutive factor
   T m_inv;
   const T* m_arr[3];  // material layout or null
@@ -265,7 +266,9 @@ constexpr int min_ctas() {
 //            cuts the items at the PML faces).  Coefficients of the other axes are the
 //            compile-time constants (0, 1, 1), so their stages fold away exactly (x*1 == x):
 //            a single-axis PML tile carries one W and one U array and nothing else.
-template <class T, int GROUP, int MODE, bool MARR, int AXM = 7>
+//   NU     : non-uniform grid — the curl uses inv(Δx[ix]), inv(Δy[iy]), inv(Δz[iz]) of the updated cell
+//            (get_inv_dx(Δ::AbstractVector, i), Helpers.jl:283-291) instead of three scalars
+template <class T, int GROUP, int MODE, bool MARR, int AXM = 7, bool NU = false>
 __global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(const __grid_constant__ StepParams<T> p) {
   constexpr int IC = (GROUP == 0) ? 1 : -1;
   constexpr bool GENERAL = MODE >= 1;   // PML cascade
@@ -294,7 +297,17 @@ __global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(c
   const T* __restrict__ Ax = p.A[0];
   const T* __restrict__ Ay = p.A[1];
   const T* __restrict__ Az = p.A[2];
-  const T dt = p.dt, idx_ = p.idl[0], idy_ = p.idl[1], idz_ = p.idl[2];
+  const T dt = p.dt;
+  T idx_ = p.idl[0], idy_ = p.idl[1], idz_ = p.idl[2];
+  T idxv[4] = {idx_, idx_, idx_, idx_};
+  if constexpr (NU) {
+    if (act) {
+      const V4<T> v = ld4(p.idv[0] + gx - 1);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) idxv[e] = v.v[e];
+      idy_ = p.idv[1][iy - 1];
+    }
+  }
 
   // ---- per-thread constants of the general path ----
   Co<T> cx[4], cyc;
@@ -425,6 +438,7 @@ __global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(c
     const long long base = p.plane * (long long)iz + fo;
     const long long mbase = p.mplane * (long long)(iz - 1) + mo;
     const bool more = iz + 1 < z_end;
+    if constexpr (NU) idz_ = p.idv[2][iz - 1];
 #if KHR_PREFETCH
     if (act) {
       if (iz == it.z0) {
@@ -528,8 +542,9 @@ __global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(c
         }
         // K = dt * curl (Helpers.jl:286-298), same operation order as the reference
         const T k0 = dt * (idz_ * (ay_z.v[e] - ay0.v[e]) - idy_ * (az_y.v[e] - az0.v[e]));
-        const T k1 = dt * (idx_ * (azx - az0.v[e]) - idz_ * (ax_z.v[e] - ax0.v[e]));
-        const T k2 = dt * (idy_ * (ax_y.v[e] - ax0.v[e]) - idx_ * (ayx - ay0.v[e]));
+        const T idxe = NU ? idxv[e] : idx_;
+        const T k1 = dt * (idxe * (azx - az0.v[e]) - idz_ * (ax_z.v[e] - ax0.v[e]));
+        const T k2 = dt * (idy_ * (ax_y.v[e] - ax0.v[e]) - idxe * (ayx - ay0.v[e]));
         kx[e] = KHR_M0(e) * k0;
         ky[e] = KHR_M1(e) * k1;
         kz[e] = KHR_M2(e) * k2;

@@ -36,7 +36,7 @@ class Grid:
     product formed in Float64 (Courant is still the user's Float64 there).
     """
 
-    def __init__(self, cell_size, cell_center, resolution, courant=0.5, dtype=np.float32):
+    def __init__(self, cell_size, cell_center, resolution, courant=0.5, dtype=np.float32, spacing=None):
         self.T = np.dtype(dtype).type
         T = self.T
         self.cell_size_user = [float(v) for v in cell_size]
@@ -48,7 +48,20 @@ class Grid:
             raise ValueError("3-D grids only: every axis needs at least one cell (2-D, Nz == 0, is not supported)")
         self.cell_size = [T(L) for L in self.cell_size_user]
         self.dl = [T(L / n) for L, n in zip(self.cell_size_user, self.N)]
-        self.dt = T(float(min(self.dl)) * self.courant)
+        # non-uniform grid (DataStructures.jl:737-739): Δ of an axis given as one spacing per cell.
+        # dl[a] becomes the representative scalar the reference uses outside the kernels
+        # (_scalar_spacing(Δ) = Δ[1], utils.jl:4-5); Δt = min over all spacings * Courant (:692,740)
+        self.dlv = [None, None, None]
+        for a, v in enumerate(spacing or [None, None, None]):
+            if v is None:
+                continue
+            v = np.asarray(v, dtype=T)
+            if v.shape != (self.N[a],) or not np.all(v > 0):
+                raise ValueError("grid spacing of axis %d must be %d positive values" % (a, self.N[a]))
+            self.dlv[a] = v
+            self.dl[a] = T(v[0])
+        mins = [float(self.dl[a]) if self.dlv[a] is None else float(self.dlv[a].min()) for a in range(3)]
+        self.dt = T(min(mins) * self.courant)
 
     # src/utils.jl:26-38
     def component_voxel_count(self, comp):
@@ -126,6 +139,39 @@ class Grid:
             return T(u0(length_right) * u((length_right - (total - real_idx)) / length_right))
         return T(0)
 
+    # sigma_helper for a spacing vector (Boundaries.jl:23-38 with _pml_total_length / _pml_position,
+    # :44-62): positions accumulate in Float64, the total length is a sum in T (left to right here;
+    # Julia's sum may reassociate, so these profiles match the reference to rounding only)
+    def _sigma_helper_nu(self, idx, Ns, dxv, length_left, length_right):
+        T = self.T
+        dt = self.dt
+
+        def u0(L):
+            den = T(4) * L
+            den = den * T(1)
+            den = den / T(3)
+            return (-math.log(1e-15) / float(den)) * (0.5 * float(dt))
+
+        def u(x):
+            sgn = 1.0 if x > 0 else (-1.0 if x < 0 else 0.0)
+            return ((x * x) * 0.5) * (sgn + 1.0)
+
+        n = len(dxv)
+        total = T(0)
+        for k in range(min(Ns // 2, n)):
+            total = T(total + dxv[k])
+        cell, frac = idx // 2, (idx % 2) * 0.5
+        pos = 0.0
+        for k in range(1, min(cell, n) + 1):
+            pos += float(dxv[k - 1])
+        if cell < n:
+            pos += frac * float(dxv[min(cell + 1, n) - 1])
+        if pos < float(length_left):
+            return T(u0(length_left) * u((float(length_left) - pos) / float(length_left)))
+        if (float(total) - pos) < float(length_right):
+            return T(u0(length_right) * u((float(length_right) - (float(total) - pos)) / float(length_right)))
+        return T(0)
+
     # src/Boundaries.jl:64-72 compute_sigma: length 2N+1, zeros when both thicknesses are 0
     def compute_sigma(self, axis, length_left, length_right):
         T = self.T
@@ -134,7 +180,10 @@ class Grid:
         ll, lr = T(length_left), T(length_right)
         if ll != 0 or lr != 0:
             for idx in range(1, Ns + 1):
-                s[idx - 1] = self._sigma_helper(idx, Ns, self.dl[axis], ll, lr)
+                if self.dlv[axis] is None:
+                    s[idx - 1] = self._sigma_helper(idx, Ns, self.dl[axis], ll, lr)
+                else:
+                    s[idx - 1] = self._sigma_helper_nu(idx, Ns, self.dlv[axis], ll, lr)
         return s
 
     # src/Chunking.jl:642-643: PML cell counts per side (T-typed quotient, then ceil)

@@ -262,8 +262,10 @@ class Simulation:
 
     def __init__(self, cell_size, cell_center, resolution, sources, boundaries=None, absorbers=None, geometry=None,
                  monitors=None, Courant=0.5, dtype=np.float32, device=0, rank=0, nranks=1, eps_inv=None, mu_inv=None,
-                 sigma_D=None, sigma_B=None, poles=None, boundary_conditions=None, chi3=None):
-        self.grid = Grid(cell_size, cell_center, resolution, Courant, dtype)
+                 sigma_D=None, sigma_B=None, poles=None, boundary_conditions=None, chi3=None, grid_spacing=None):
+        # grid_spacing: [Δx, Δy, Δz], each None (uniform) or one spacing per cell — the reference's
+        # Simulation(Δx = vector, ...) (DataStructures.jl:737-739)
+        self.grid = Grid(cell_size, cell_center, resolution, Courant, dtype, spacing=grid_spacing)
         # boundary_conditions (DataStructures.jl:725): per axis [minus, plus] of PML / Periodic /
         # Bloch / PECBoundary / PMCBoundary instances (or classes); None == PML everywhere
         self.bc_codes = None
@@ -309,7 +311,14 @@ class Simulation:
     def _coords(self, comp):
         """Coordinates of cells 1..N of a component grid (Geometry.jl _precompute_coords)."""
         o = self.grid.component_origin(comp)
-        return [o[a] + np.arange(self.grid.N[a], dtype=np.float64) * float(self.grid.dl[a]) for a in range(3)]
+        out = []
+        for a in range(3):
+            if self.grid.dlv[a] is None:
+                out.append(o[a] + np.arange(self.grid.N[a], dtype=np.float64) * float(self.grid.dl[a]))
+            else:  # _build_coords(Δ::AbstractVector, ...) (Geometry.jl:377-395): origin + sum(Δ[1:i-1])
+                cum = np.concatenate([[0.0], np.cumsum(self.grid.dlv[a].astype(np.float64))[:-1]])
+                out.append(o[a] + cum)
+        return out
 
     def _rasterize(self):
         """Point-sampled stand-in for init_geometry (Geometry.jl:450-663): per Yee component,
@@ -535,6 +544,10 @@ class Simulation:
         self.ctx = ctx
         if self.complex_fields:
             _lib.check(L.khr_set_complex_fields(ctx))
+        for a in range(3):
+            if g.dlv[a] is not None:
+                v = np.ascontiguousarray(g.dlv[a])
+                _lib.check(L.khr_set_grid_spacing(ctx, a, v.ctypes.data, v.size))
         zsl = slice(z_start - 1, z_start - 1 + nzl)
         if self.sigma is not None:
             for grp in (_lib.GROUP_H, _lib.GROUP_E):

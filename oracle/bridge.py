@@ -16,6 +16,10 @@ def oracle_from_simulation(sim):
     g = sim.grid
     o = ko.OracleSim(sim.T, g.cell_size_user, g.cell_center, g.resolution, g.courant, sim.boundaries)
     assert tuple(o.N) == tuple(g.N)
+    for a in range(3):
+        if g.dlv[a] is not None:
+            o.set_grid_spacing(a, g.dlv[a])
+    assert o.dt == float(g.dt), (o.dt, float(g.dt))
     if getattr(sim, "bc_codes", None) is not None:
         o.set_boundary_conditions(sim.bc_codes)
     if getattr(sim, "complex_fields", False):

@@ -275,6 +275,10 @@ struct Sim {
   // --- derived grid (src/DataStructures.jl:732-741) -------------------------
   int N[3];
   T cell_size[3], dl[3], dt;
+  // non-uniform grid (src/DataStructures.jl:737-739): one spacing per cell; empty == scalar Δ.
+  // dl[a] then holds the representative scalar the reference uses outside the kernels
+  // (_scalar_spacing(Δ) = Δ[1], src/utils.jl:4-5).
+  std::vector<T> dlv[3];
   // --- boundary data (src/Boundaries.jl:99-164) -----------------------------
   std::vector<T> sigma[2][3];  // [group][axis], length 2N+1; empty == nothing
   // --- materials (global, cells 1..N only; gidx never exceeds N) ------------
@@ -313,6 +317,48 @@ struct Sim {
     dt = (T)((double)m * courant);
   }
 
+  // Δt = min over all spacings * Courant (src/DataStructures.jl:692,740)
+  void set_spacing(int axis, const std::vector<T>& v) {
+    dlv[axis] = v;
+    dl[axis] = v[0];
+    T m = dl[0];
+    for (int a = 0; a < 3; ++a) {
+      if (dlv[a].empty()) m = std::min(m, dl[a]);
+      else for (T x : dlv[a]) m = std::min(m, x);
+    }
+    dt = (T)((double)m * courant);
+  }
+  // sigma_helper for a spacing vector (src/Boundaries.jl:23-38 with _pml_total_length /
+  // _pml_position of :44-62): positions accumulate in Float64, the total length is a sum in T
+  // (Julia's sum reassociates under @simd; a left-to-right sum is used here, so non-uniform sigma
+  // profiles agree with the reference to rounding, not bit for bit)
+  T sigma_helper_nu(int idx, int Ns, const std::vector<T>& dxv, T Dt, T length_left, T length_right) const {
+    auto u0 = [&](T pml_length) -> double {
+      T den = T(4) * pml_length;
+      den = den * T(1);
+      den = den / T(3);
+      return (-std::log(1e-15) / (double)den) * (0.5 * (double)Dt);
+    };
+    auto u = [&](double x) -> double {
+      double sgn = (x > 0) ? 1.0 : ((x < 0) ? -1.0 : 0.0);
+      return ((x * x) * 0.5) * (sgn + 1.0);
+    };
+    const int len = (int)dxv.size();
+    int n_cells = Ns / 2;
+    T total_length = T(0);
+    for (int k = 0; k < std::min(n_cells, len); ++k) total_length += dxv[k];
+    int cell = idx / 2;
+    double frac = (idx % 2) * 0.5;
+    double pos = 0.0;
+    for (int k = 1; k <= std::min(cell, len); ++k) pos += (double)dxv[k - 1];
+    if (cell < len) pos += frac * (double)dxv[std::min(cell + 1, len) - 1];
+    if (pos < (double)length_left) {
+      return (T)(u0(length_left) * u(((double)length_left - pos) / (double)length_left));
+    } else if (((double)total_length - pos) < (double)length_right) {
+      return (T)(u0(length_right) * u(((double)length_right - ((double)total_length - pos)) / (double)length_right));
+    }
+    return T(0);
+  }
   // src/Boundaries.jl:23-38 sigma_helper; :64-72 compute_sigma
   T sigma_helper(int idx, int Ns, T dx, T Dt, T length_left, T length_right) const {
     auto u0 = [&](T pml_length) -> double {
@@ -352,7 +398,14 @@ struct Sim {
         const bool raw = (g == 1 && a == 2);
         T l0 = (no_pml_side[a][0] && !raw) ? T(0) : pml[a][0];
         T l1 = (no_pml_side[a][1] && !raw) ? T(0) : pml[a][1];
-        sigma[g][a] = compute_sigma(2 * N[a] + 1, dl[a], dt, l0, l1);
+        if (dlv[a].empty()) sigma[g][a] = compute_sigma(2 * N[a] + 1, dl[a], dt, l0, l1);
+        else {
+          const int Ns = 2 * N[a] + 1;
+          std::vector<T> sv((size_t)Ns, T(0));
+          if ((l0 != T(0)) || (l1 != T(0)))
+            for (int idx = 1; idx <= Ns; ++idx) sv[idx - 1] = sigma_helper_nu(idx, Ns, dlv[a], dt, l0, l1);
+          sigma[g][a] = sv;
+        }
       }
   }
 
@@ -728,13 +781,18 @@ struct Sim {
     const std::vector<T>* sg = c.sig[group];
     const bool has_pml_sigma = !sg[0].empty();
     const T Dt = dt;
-    const T idx_ = T(1) / dl[0], idy_ = T(1) / dl[1], idz_ = T(1) / dl[2];
+    const T idx_u = T(1) / dl[0], idy_u = T(1) / dl[1], idz_u = T(1) / dl[2];
+    const bool nux = !dlv[0].empty(), nuy = !dlv[1].empty(), nuz = !dlv[2].empty();
     const int mode_l = mode;
 #pragma omp parallel for collapse(2) schedule(static)
     for (int iz = 1; iz <= c.n[2]; ++iz)
       for (int iy = 1; iy <= c.n[1]; ++iy)
         for (int ix = 1; ix <= c.n[0]; ++ix) {
           const int fx = ix, fy = iy, fz = iz;  // 0-based raw == Julia (ix+1)-1
+          // get_inv_dx (Helpers.jl:283-284): inv(Δ) or inv(Δ[i]) of the updated (global) cell
+          const T idx_ = nux ? T(1) / dlv[0][c.s[0] + ix - 2] : idx_u;
+          const T idy_ = nuy ? T(1) / dlv[1][c.s[1] + iy - 2] : idy_u;
+          const T idz_ = nuz ? T(1) / dlv[2][c.s[2] + iz - 2] : idz_u;
           // curl (src/Kernels/Helpers.jl:286-298); K = Δt * curl
           T dAy_dz = idz_ * (A[1].at(fx, fy, fz + ic) - A[1].at(fx, fy, fz));
           T dAz_dy = idy_ * (A[2].at(fx, fy + ic, fz) - A[2].at(fx, fy, fz));
@@ -1277,6 +1335,17 @@ void ko_set_boundary_conditions(void* hv, const int* bc6) {
 void ko_set_bloch(void* hv, int axis, double k) {
   Handle* h = (Handle*)hv;
   DISPATCH(h, { S.complex_fields = true; S.bloch_k[axis] = k; });
+}
+
+// non-uniform grid: one spacing per cell of `axis` (before ko_prepare)
+void ko_set_grid_spacing(void* hv, int axis, const double* d, int len) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, {
+    using TT = std::remove_reference_t<decltype(S.dt)>;
+    std::vector<TT> v((size_t)len);
+    for (int i = 0; i < len; ++i) v[(size_t)i] = (TT)d[i];
+    S.set_spacing(axis, v);
+  });
 }
 
 void ko_set_chi3_literal_order(void* hv, int v) {

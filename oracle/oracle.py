@@ -71,6 +71,7 @@ def lib():
         L.ko_set_sources_active.argtypes = [C.c_void_p, C.c_int]
         L.ko_set_chi3_literal_order.argtypes = [C.c_void_p, C.c_int]
         L.ko_set_bloch.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.ko_set_grid_spacing.argtypes = [C.c_void_p, C.c_int, dp, C.c_int]
         L.ko_set_boundary_conditions.argtypes = [C.c_void_p, ip]
         L.ko_timestep.restype = C.c_long
         L.ko_num_threads.restype = C.c_int
@@ -262,6 +263,19 @@ class OracleSim:
         """True: apply the Kerr correction after the halo / wrap copies, the literal order of step!
         (Kernels.jl:76-79); default False = before them (neighbours see the corrected E)."""
         self.L.ko_set_chi3_literal_order(self.h, int(bool(on)))
+
+    def set_grid_spacing(self, axis, spacing):
+        """Non-uniform grid (DataStructures.jl:737-739): one spacing per cell of `axis`; updates dt."""
+        d, dp_ = _d(spacing)
+        assert len(d) == self.N[axis]
+        self.L.ko_set_grid_spacing(self.h, int(axis), dp_, len(d))
+        N = np.zeros(3, dtype=np.int32)
+        dl = np.zeros(3)
+        dt = C.c_double()
+        self.L.ko_grid(self.h, N.ctypes.data_as(C.POINTER(C.c_int)), dl.ctypes.data_as(C.POINTER(C.c_double)),
+                       C.byref(dt))
+        self.dl = tuple(float(x) for x in dl)
+        self.dt = dt.value
 
     def set_bloch(self, axis, k):
         """Bloch(k) on both sides of `axis` (DataStructures.jl:158-160): complex fields; the axis must
