@@ -87,6 +87,32 @@ int32_t khr_set_grid_spacing(khr_ctx* ctx, int32_t axis, const void* spacing, in
 int32_t khr_set_material_scalar(khr_ctx* ctx, int32_t kind, double value);
 int32_t khr_set_material_array(khr_ctx* ctx, int32_t kind, int32_t comp, const void* dense);
 
+/* Geometry on the device: replaces the rasterisation loop of init_geometry
+ * (Geometry.jl:450-605, _rasterize_object_yrange! :150-246: objects painted last to first inside
+ * their bounding-box index ranges, earlier objects win) and _apply_subpixel_smoothing!
+ * (:795-972) for scenes of spheres and cuboids, writing eps^-1 / mu^-1 / sigma_D / sigma_B
+ * straight into the library's device arrays.  Shape predicates follow GeometryPrimitives.jl
+ * (`in`, `bounds`, `surfpt_nearby`, `level`, `volfrac`; not vendored by the reference).
+ *   objects      : priority order (index 0 wins), painted values already 1/eps etc. in dtype precision
+ *   kinds_mask   : bit KHR_MAT_* set for every array to produce (needs_perm / needs_conductivities)
+ *   smoothing    : 0 NoSmoothing, 1 VolumeAveraging, 2 AnisotropicSmoothing (DataStructures.jl:66-76)
+ *   origins      : get_component_origin (utils.jl:156-170) of Ex,Ey,Ez,Hx,Hy,Hz, 6 x (x,y,z)
+ *   smoothed_out : interface voxels rewritten per E component (may be NULL)
+ * Uniform grids only; before khr_finalize_plan. */
+enum { KHR_SHAPE_SPHERE = 0, KHR_SHAPE_CUBOID = 1 };
+typedef struct khr_object {
+  int32_t kind;
+  int32_t pad_;
+  double center[3];
+  double size[3];     /* sphere: size[0] = radius; cuboid: full edge lengths along its axes */
+  double axes[9];     /* cuboid: rows = axis vectors (orthogonal; normalised by the library); all zero = identity */
+  double eps_inv[3], mu_inv[3], sigma_d[3], sigma_b[3];
+} khr_object;
+int32_t khr_geometry_rasterize(khr_ctx* ctx, const khr_object* objects, int32_t nobj, int32_t kinds_mask, int32_t smoothing,
+                               const double origins[18], int64_t smoothed_out[3]);
+/* dense (Nx,Ny,Nz_local) copy of a per-voxel material array (kind = KHR_MAT_*) */
+int32_t khr_material_read(khr_ctx* ctx, int32_t kind, int32_t comp, void* dense_out);
+
 /* Geometry.jl:1136-1355 init_polarization! output for one pole: σ array shared by
  * x/y/z (Geometry.jl:1291-1302) and the pole parameters; coefficients follow
  * Susceptibility.jl:74-85. */

@@ -30,6 +30,23 @@ class GridDesc(C.Structure):
     ]
 
 
+SHAPE_SPHERE, SHAPE_CUBOID = 0, 1
+
+
+class KhrObject(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("pad_", C.c_int32),
+        ("center", C.c_double * 3),
+        ("size", C.c_double * 3),
+        ("axes", C.c_double * 9),
+        ("eps_inv", C.c_double * 3),
+        ("mu_inv", C.c_double * 3),
+        ("sigma_d", C.c_double * 3),
+        ("sigma_b", C.c_double * 3),
+    ]
+
+
 class KernelStat(C.Structure):
     _fields_ = [
         ("name", C.c_char * 96),
@@ -52,6 +69,8 @@ _SIGNATURES = {
     "khr_ctx_destroy": (_I, [_P]),
     "khr_set_pml_sigma": (_I, [_P, _I, _I, _P, _I]),
     "khr_set_grid_spacing": (_I, [_P, _I, _P, _I]),
+    "khr_geometry_rasterize": (_I, [_P, C.POINTER(KhrObject), _I, _I, _I, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "khr_material_read": (_I, [_P, _I, _I, _P]),
     "khr_set_material_scalar": (_I, [_P, _I, C.c_double]),
     "khr_set_material_array": (_I, [_P, _I, _I, _P]),
     "khr_pole_register": (_I, [_P, C.c_double, C.c_double, _P, C.POINTER(_I)]),
@@ -100,7 +119,7 @@ _LIB = None
 
 def build(force=False):
     """Compile libkhronos_b200.so in-tree with nvcc for sm_100a (no GPU needed)."""
-    srcs = [os.path.join(CSRC, f) for f in ("khronos_b200.cu", "step_kernels.cuh", "post_kernels.cuh")]
+    srcs = [os.path.join(CSRC, f) for f in ("khronos_b200.cu", "step_kernels.cuh", "post_kernels.cuh", "geom_kernels.cuh")]
     srcs.append(os.path.join(_HERE, "..", "include", "khronos_b200.h"))
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if force or stale:

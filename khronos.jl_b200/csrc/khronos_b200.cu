@@ -9,6 +9,7 @@
 #include "../../include/khronos_b200.h"
 #include "step_kernels.cuh"
 #include "post_kernels.cuh"
+#include "geom_kernels.cuh"
 
 #include <dlfcn.h>
 
@@ -87,6 +88,9 @@ struct Base {
   khr_grid_desc g;
   virtual void set_pml_sigma(int group, int axis, const void* s, int len) = 0;
   virtual void set_grid_spacing(int axis, const void* d, int len) = 0;
+  virtual void geometry_rasterize(const khr_object* objs, int nobj, int kinds_mask, int smoothing, const double* origins18,
+                                  int64_t* smoothed3) = 0;
+  virtual void material_read(int kind, int comp, void* out) = 0;
   virtual void set_material_scalar(int kind, double v) = 0;
   virtual void set_material_array(int kind, int comp, const void* dense) = 0;
   virtual int pole_register(double omega0, double gamma, const void* sigma) = 0;
@@ -390,6 +394,192 @@ struct Impl : Base {
     CUDA_OK(cudaMemcpyAsync(idv[axis], inv.data(), (size_t)cap * sizeof(T), cudaMemcpyHostToDevice, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
     nonuniform = true;
+  }
+  // ---- geometry on the device (geom_kernels.cuh; Geometry.jl:150-246, 450-605, 795-972) --------
+  // coordinate of local/global cell i on a component grid, the same expression as the kernels
+  static double gcoord(double origin, int i, T d) { return origin + (double)((T)(i - 1) * d); }
+  void geometry_rasterize(const khr_object* objs, int nobj, int kinds_mask, int smoothing, const double* origins18,
+                          int64_t* smoothed3) override {
+    if (finalized) throw std::string("khr_geometry_rasterize after khr_finalize_plan");
+    if (nobj < 1) throw std::string("khr_geometry_rasterize: no objects");
+    if (smoothing < 0 || smoothing > 2) throw std::string("khr_geometry_rasterize: smoothing must be 0 (none), 1 (volume averaging) or 2 (anisotropic)");
+    if (nonuniform) throw std::string("khr_geometry_rasterize: non-uniform grids are rasterised by the caller");
+    std::vector<GeomObj> h((size_t)nobj);
+    for (int q = 0; q < nobj; ++q) {
+      const khr_object& in = objs[q];
+      GeomObj& o = h[(size_t)q];
+      memset(&o, 0, sizeof(o));
+      o.kind = in.kind;
+      for (int k = 0; k < 3; ++k) o.c[k] = in.center[k];
+      if (in.kind == KHR_SHAPE_SPHERE) {
+        if (!(in.size[0] > 0)) throw std::string("khr_geometry_rasterize: sphere radius must be positive");
+        o.r[0] = in.size[0];
+        for (int k = 0; k < 3; ++k) { o.bmin[k] = o.c[k] - o.r[0]; o.bmax[k] = o.c[k] + o.r[0]; }   // bounds(::Sphere)
+      } else if (in.kind == KHR_SHAPE_CUBOID) {
+        bool ident = true;
+        for (int k = 0; k < 9; ++k) ident = ident && in.axes[k] == 0.0;
+        for (int k = 0; k < 3; ++k) {
+          if (!(in.size[k] > 0)) throw std::string("khr_geometry_rasterize: cuboid sizes must be positive");
+          o.r[k] = in.size[k] / 2;                                  // Cuboid(c, d, axes): r = d / 2
+          double nr = 0;
+          for (int j = 0; j < 3; ++j) { o.ax[3 * k + j] = ident ? (j == k ? 1.0 : 0.0) : in.axes[3 * k + j]; nr += o.ax[3 * k + j] * o.ax[3 * k + j]; }
+          nr = std::sqrt(nr);
+          if (!(nr > 0)) throw std::string("khr_geometry_rasterize: zero cuboid axis");
+          for (int j = 0; j < 3; ++j) o.ax[3 * k + j] /= nr;
+        }
+        for (int a = 0; a < 3; ++a)
+          for (int b = a + 1; b < 3; ++b) {
+            double dot = 0;
+            for (int j = 0; j < 3; ++j) dot += o.ax[3 * a + j] * o.ax[3 * b + j];
+            if (std::fabs(dot) > 1e-12) throw std::string("khr_geometry_rasterize: cuboid axes must be orthogonal");
+          }
+        for (int i = 0; i < 3; ++i) {   // bounds(::Cuboid): c -+ sum_j |axis_j[i]| r_j
+          double m = 0;
+          for (int j = 0; j < 3; ++j) m += std::fabs(o.ax[3 * j + i]) * o.r[j];
+          o.bmin[i] = o.c[i] - m; o.bmax[i] = o.c[i] + m;
+        }
+      } else {
+        throw std::string("khr_geometry_rasterize: shape kind must be KHR_SHAPE_SPHERE or KHR_SHAPE_CUBOID");
+      }
+      for (int k = 0; k < 3; ++k) {
+        o.val[0][k] = (double)(T)in.eps_inv[k]; o.val[1][k] = (double)(T)in.mu_inv[k];
+        o.val[2][k] = (double)(T)in.sigma_d[k]; o.val[3][k] = (double)(T)in.sigma_b[k];
+      }
+    }
+    GeomObj* d_objs = nullptr;
+    int* d_owner = nullptr;
+    PaintItem* d_items = nullptr;
+    unsigned long long* d_cnt3 = nullptr;
+    const size_t nown = (size_t)MPX * N[1] * (size_t)(N[2] + 2);
+    auto cleanup = [&]() { cudaFree(d_objs); cudaFree(d_owner); cudaFree(d_items); cudaFree(d_cnt3); };
+    try {
+      CUDA_OK(cudaMalloc((void**)&d_objs, sizeof(GeomObj) * (size_t)nobj));
+      CUDA_OK(cudaMalloc((void**)&d_owner, sizeof(int) * nown));
+      CUDA_OK(cudaMalloc((void**)&d_cnt3, sizeof(unsigned long long) * 3));
+      CUDA_OK(cudaMemsetAsync(d_cnt3, 0, sizeof(unsigned long long) * 3, stream));
+      CUDA_OK(cudaMemcpyAsync(d_objs, h.data(), sizeof(GeomObj) * (size_t)nobj, cudaMemcpyHostToDevice, stream));
+      size_t items_cap = 0;
+      for (int c = 0; c < 6; ++c) {
+        const int grp = c < 3 ? 1 : 0, d = c % 3;             // material group index: [0] = H side, [1] = E side
+        const int perm_kind = c < 3 ? KHR_MAT_EPS_INV : KHR_MAT_MU_INV, sig_kind = c < 3 ? KHR_MAT_SIGMA_D : KHR_MAT_SIGMA_B;
+        const bool want_perm = (kinds_mask >> perm_kind) & 1, want_sig = (kinds_mask >> sig_kind) & 1;
+        if (!want_perm && !want_sig) continue;
+        GeomGrid gg;
+        for (int a = 0; a < 3; ++a) { gg.origin[a] = origins18[3 * c + a]; gg.n[a] = N[a]; }
+        gg.nzg = g.n[2]; gg.z_off = g.z_start - 1; gg.mpx = MPX;
+        // bounding-box index ranges on this grid: first cell with coord >= bmin .. last with coord <= bmax
+        // (searchsortedfirst / searchsortedlast, Geometry.jl:188-194), clamped to the cells this slab
+        // stores (z: one ghost plane either side, inside the global grid)
+        std::vector<PaintItem> items;
+        const int CH = 8192;
+        for (int q = 0; q < nobj; ++q) {
+          const GeomObj& o = h[(size_t)q];
+          int lo[3], hi[3];
+          bool empty = false;
+          for (int a = 0; a < 3; ++a) {
+            const int off = a == 2 ? gg.z_off : 0;
+            const int cmin = a == 2 ? std::max(1 - off, 0) : 1;
+            const int cmax = a == 2 ? std::min(g.n[2] - off, N[2] + 1) : N[a];
+            const double dd = (double)dl[a];
+            int i0 = (int)std::floor((o.bmin[a] - gg.origin[a]) / dd) + 1 - off - 2;
+            int i1 = (int)std::ceil((o.bmax[a] - gg.origin[a]) / dd) + 1 - off + 2;
+            i0 = std::max(i0, cmin); i1 = std::min(i1, cmax);
+            while (i0 <= i1 && !(gcoord(gg.origin[a], i0 + off, dl[a]) >= o.bmin[a])) ++i0;
+            while (i1 >= i0 && !(gcoord(gg.origin[a], i1 + off, dl[a]) <= o.bmax[a])) --i1;
+            lo[a] = i0; hi[a] = i1;
+            if (i0 > i1) empty = true;
+          }
+          if (empty) continue;
+          const long long nv = (long long)(hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
+          for (long long f = 0; f < nv; f += CH) {
+            PaintItem it;
+            it.obj = q;
+            for (int a = 0; a < 3; ++a) { it.lo[a] = lo[a]; it.n[a] = hi[a] - lo[a] + 1; }
+            it.first = f; it.count = (int)std::min<long long>(CH, nv - f);
+            items.push_back(it);
+          }
+        }
+        CUDA_OK(cudaMemsetAsync(d_owner, 0x7f, sizeof(int) * nown, stream));
+        if (!items.empty()) {
+          if (items.size() > items_cap) {
+            CUDA_OK(cudaStreamSynchronize(stream));
+            cudaFree(d_items); d_items = nullptr;
+            items_cap = items.size() * 2;
+            CUDA_OK(cudaMalloc((void**)&d_items, sizeof(PaintItem) * items_cap));
+          }
+          CUDA_OK(cudaMemcpyAsync(d_items, items.data(), sizeof(PaintItem) * items.size(), cudaMemcpyHostToDevice, stream));
+          geom_paint_kernel<T><<<(unsigned)items.size(), 256, 0, stream>>>(d_objs, d_items, gg, dl[0], dl[1], dl[2], d_owner);
+          CUDA_OK(cudaGetLastError());
+          CUDA_OK(cudaStreamSynchronize(stream));   // `items` is reused by the next grid
+        }
+        const long long nvox = (long long)N[0] * N[1] * N[2];
+        const unsigned fb = (unsigned)std::min<long long>((nvox + 255) / 256, 148 * 32);
+        if (want_perm) {
+          if (!m_arr[grp][d]) m_arr[grp][d] = dalloc(msize);
+          geom_fill_kernel<T><<<fb, 256, 0, stream>>>(d_objs, d_owner, gg, perm_kind, d, m_arr[grp][d]);
+        }
+        if (want_sig) {
+          if (!sigM[grp][d]) sigM[grp][d] = dalloc(msize);
+          geom_fill_kernel<T><<<fb, 256, 0, stream>>>(d_objs, d_owner, gg, sig_kind, d, sigM[grp][d]);
+          has_sd[grp] = true;
+        }
+        if (want_perm && c < 3 && smoothing != 0)
+          geom_smooth_kernel<T><<<(unsigned)((nvox + 255) / 256), 256, 0, stream>>>(d_objs, nobj, d_owner, gg, dl[0], dl[1], dl[2], d, smoothing,
+                                                                                  m_arr[grp][d], d_cnt3 + d);
+        CUDA_OK(cudaGetLastError());
+        launches += 3;
+      }
+      unsigned long long cnt[3] = {0, 0, 0};
+      CUDA_OK(cudaMemcpyAsync(cnt, d_cnt3, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
+      CUDA_OK(cudaStreamSynchronize(stream));
+      if (smoothed3) for (int k = 0; k < 3; ++k) smoothed3[k] = (int64_t)cnt[k];
+    } catch (...) {
+      cudaStreamSynchronize(stream);
+      cleanup();
+      throw;
+    }
+    cleanup();
+    // planner boxes of the conductive objects (cells, conservative: their bounding boxes on the cell-centre scale)
+    for (int grp = 0; grp < 2; ++grp) {
+      const int kind = grp == 1 ? KHR_MAT_SIGMA_D : KHR_MAT_SIGMA_B;
+      if (!((kinds_mask >> kind) & 1)) continue;
+      for (int q = 0; q < nobj; ++q) {
+        const GeomObj& o = h[(size_t)q];
+        if (o.val[kind][0] == 0 && o.val[kind][1] == 0 && o.val[kind][2] == 0) continue;
+        int b[6];
+        bool empty = false;
+        for (int a = 0; a < 3; ++a) {
+          const int off = a == 2 ? g.z_start - 1 : 0;
+          // all six component grids lie within half a cell of the centre grid: pad by one cell
+          const double org = origins18[3 * (grp == 1 ? 0 : 3) + a];
+          int i0 = (int)std::floor((o.bmin[a] - org) / (double)dl[a]) + 1 - off - 1;
+          int i1 = (int)std::ceil((o.bmax[a] - org) / (double)dl[a]) + 1 - off + 1;
+          i0 = std::max(i0, 1); i1 = std::min(i1, N[a]);
+          b[a] = i0; b[3 + a] = i1;
+          if (i0 > i1) empty = true;
+        }
+        if (!empty) box_union(sd_box[grp], b);
+      }
+    }
+  }
+  // dense (Nx,Ny,Nz_local) copy of a per-voxel material array (tests, host-side consumers)
+  void material_read(int kind, int comp, void* out) override {
+    if (comp < 0 || comp > 2) throw std::string("component must be 0..2");
+    const T* src = nullptr;
+    if (kind == KHR_MAT_EPS_INV) src = m_arr[1][comp];
+    else if (kind == KHR_MAT_MU_INV) src = m_arr[0][comp];
+    else if (kind == KHR_MAT_SIGMA_D) src = sigM[1][comp];
+    else if (kind == KHR_MAT_SIGMA_B) src = sigM[0][comp];
+    else if (kind == KHR_MAT_CHI3) src = chi3;
+    else throw std::string("unknown material kind");
+    if (!src) throw std::string("khr_material_read: this material array does not exist");
+    std::vector<T> hh(msize);
+    CUDA_OK(cudaStreamSynchronize(stream));
+    CUDA_OK(cudaMemcpy(hh.data(), src, msize * sizeof(T), cudaMemcpyDeviceToHost));
+    T* o = (T*)out;
+    for (int z = 1; z <= N[2]; ++z)
+      for (int y = 1; y <= N[1]; ++y)
+        memcpy(o + (size_t)N[0] * ((size_t)(y - 1) + (size_t)N[1] * (z - 1)), hh.data() + midx(1, y, z), N[0] * sizeof(T));
   }
   void set_material_scalar(int kind, double v) override {
     if (kind == KHR_MAT_EPS_INV) m_scalar[1] = (T)v;
@@ -1715,6 +1905,21 @@ int32_t khr_set_grid_spacing(khr_ctx* ctx, int32_t axis, const void* spacing, in
   NEED_CTX
   if (axis < 0 || axis > 2 || !spacing) return khr::fail("bad argument");
   KHR_TRY(KHR_BOTH(set_grid_spacing(axis, spacing, len)))
+}
+int32_t khr_geometry_rasterize(khr_ctx* ctx, const khr_object* objects, int32_t nobj, int32_t kinds_mask, int32_t smoothing,
+                               const double origins[18], int64_t smoothed_out[3]) {
+  NEED_CTX
+  if (!objects || !origins) return khr::fail("bad argument");
+  KHR_TRY({
+    ctx->impl->registered_any = true;
+    ctx->impl->geometry_rasterize(objects, nobj, kinds_mask, smoothing, origins, smoothed_out);
+    if (ctx->impl_im) ctx->impl_im->geometry_rasterize(objects, nobj, kinds_mask, smoothing, origins, nullptr);
+  })
+}
+int32_t khr_material_read(khr_ctx* ctx, int32_t kind, int32_t comp, void* dense_out) {
+  NEED_CTX
+  if (!dense_out) return khr::fail("null array");
+  KHR_TRY(ctx->impl->material_read(kind, comp, dense_out))
 }
 int32_t khr_set_material_scalar(khr_ctx* ctx, int32_t kind, double value) {
   NEED_CTX

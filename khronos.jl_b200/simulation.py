@@ -139,12 +139,25 @@ class Ball:
 
 
 class Cuboid:
-    def __init__(self, center, size):
+    """GeometryPrimitives Cuboid(c, d, axes): `axes` rows are the (orthogonal) edge directions."""
+
+    def __init__(self, center, size, axes=None):
         self.center, self.size = [float(v) for v in center], [float(v) for v in size]
+        self.axes = None
+        if axes is not None:
+            a = np.asarray(axes, dtype=np.float64).reshape(3, 3)
+            self.axes = a / np.linalg.norm(a, axis=1, keepdims=True)
 
     def contains(self, X, Y, Z):
         c, s = self.center, self.size
-        return (np.abs(X - c[0]) <= s[0] / 2) & (np.abs(Y - c[1]) <= s[1] / 2) & (np.abs(Z - c[2]) <= s[2] / 2)
+        if self.axes is None:
+            return (np.abs(X - c[0]) <= s[0] / 2) & (np.abs(Y - c[1]) <= s[1] / 2) & (np.abs(Z - c[2]) <= s[2] / 2)
+        d = [X - c[0], Y - c[1], Z - c[2]]
+        ok = True
+        for k in range(3):
+            p = (self.axes[k, 0] * d[0] + self.axes[k, 1] * d[1]) + self.axes[k, 2] * d[2]
+            ok = ok & (np.abs(p) <= s[k] / 2)
+        return ok
 
 
 class Object:
@@ -262,7 +275,8 @@ class Simulation:
 
     def __init__(self, cell_size, cell_center, resolution, sources, boundaries=None, absorbers=None, geometry=None,
                  monitors=None, Courant=0.5, dtype=np.float32, device=0, rank=0, nranks=1, eps_inv=None, mu_inv=None,
-                 sigma_D=None, sigma_B=None, poles=None, boundary_conditions=None, chi3=None, grid_spacing=None):
+                 sigma_D=None, sigma_B=None, poles=None, boundary_conditions=None, chi3=None, grid_spacing=None,
+                 rasterizer="host", subpixel_smoothing=None):
         # grid_spacing: [Δx, Δy, Δz], each None (uniform) or one spacing per cell — the reference's
         # Simulation(Δx = vector, ...) (DataStructures.jl:737-739)
         self.grid = Grid(cell_size, cell_center, resolution, Courant, dtype, spacing=grid_spacing)
@@ -299,6 +313,17 @@ class Simulation:
         self.user_arrays = {"eps_inv": eps_inv, "mu_inv": mu_inv, "sigma_D": sigma_D, "sigma_B": sigma_B}
         self.user_poles = list(poles or [])  # (omega_0, gamma, sigma_array) triples
         self.user_chi3 = chi3                # dense (Nx,Ny,Nz) Kerr coefficient on the centre grid
+        # rasterizer="device": eps^-1 / mu^-1 / sigma_D / sigma_B of `geometry` are produced on the GPU
+        # (khr_geometry_rasterize), with the reference's subpixel smoothing if asked for
+        # (subpixel_smoothing = None | "volume" | "anisotropic"; DataStructures.jl:66-76, :727).
+        # rasterizer="host" is the point sampler below (no smoothing), which also serves the oracle.
+        if rasterizer not in ("host", "device"):
+            raise ValueError("rasterizer must be 'host' or 'device'")
+        if subpixel_smoothing not in (None, "volume", "anisotropic"):
+            raise ValueError("subpixel_smoothing must be None, 'volume' or 'anisotropic'")
+        if subpixel_smoothing is not None and rasterizer != "device":
+            raise ValueError("subpixel smoothing is implemented by the device rasterizer (rasterizer='device')")
+        self.rasterizer, self.subpixel_smoothing = rasterizer, subpixel_smoothing
         self.ctx = None
         self.is_prepared = False
         self.dft_monitors = []
@@ -473,6 +498,14 @@ class Simulation:
             self.sigma = [[g.compute_sigma(a, *eff(a, raw=(grp == 1 and a == 2))) for a in range(3)] for grp in range(2)]
         # geometry (Geometry.jl:450-663) + absorbers + poles
         arrays, poles = self._rasterize()
+        if self.rasterizer == "device":
+            if not self.geometry:
+                raise ValueError("rasterizer='device' needs a geometry")
+            if poles or self.user_poles or self.absorbers is not None or any(v is not None for v in self.user_arrays.values()):
+                raise _lib.KhronosError("rasterizer='device' does not combine with dispersive poles, absorbers or "
+                                        "user-supplied material arrays (those are prepared on the host)")
+            for k in ("eps_inv", "mu_inv", "sigma_D", "sigma_B"):
+                arrays[k] = None          # produced on the device in prepare_simulation
         for k, v in self.user_arrays.items():
             if v is not None:
                 arrays[k] = [np.array(x, dtype=T) for x in v]
@@ -554,6 +587,8 @@ class Simulation:
                 for a in range(3):
                     s = np.ascontiguousarray(self.sigma[grp][a])
                     _lib.check(L.khr_set_pml_sigma(ctx, grp, a, s.ctypes.data, s.size))
+        if self.rasterizer == "device":
+            self.smoothed_voxels = self._device_rasterize(ctx)
         arrays = self.material_arrays
         kinds = {"eps_inv": _lib.MAT_EPS_INV, "mu_inv": _lib.MAT_MU_INV, "sigma_D": _lib.MAT_SIGMA_D,
                  "sigma_B": _lib.MAT_SIGMA_B}
@@ -603,6 +638,64 @@ class Simulation:
             buf = (C.c_char * 128).from_buffer_copy(bytes(comm_id))
             _lib.check(L.khr_comm_init(ctx, buf, self.nranks, self.rank))
         self.is_prepared = True
+
+    def geometry_objects(self):
+        """(KhrObject array, kinds mask) for khr_geometry_rasterize: get_perm_inv / get_sigma of every
+        object (Geometry.jl:64-81), needs_perm / needs_conductivities over the scene (:317-352)."""
+        T = self.T
+        objs = (_lib.KhrObject * len(self.geometry))()
+        for q, ob in enumerate(self.geometry):
+            o, m = objs[q], ob.material
+            if isinstance(ob.shape, Ball):
+                o.kind = _lib.SHAPE_SPHERE
+                o.size[0] = ob.shape.radius
+            elif isinstance(ob.shape, Cuboid):
+                o.kind = _lib.SHAPE_CUBOID
+                for k in range(3):
+                    o.size[k] = ob.shape.size[k]
+                if ob.shape.axes is not None:
+                    for k in range(9):
+                        o.axes[k] = float(ob.shape.axes.reshape(9)[k])
+            else:
+                raise _lib.KhronosError("the device rasterizer knows Ball and Cuboid shapes")
+            for k in range(3):
+                o.center[k] = ob.shape.center[k]
+                o.eps_inv[k] = float(T(1) / T(m.epsilon))     # one(T) / T(perm)
+                o.mu_inv[k] = float(T(1) / T(m.mu))
+                o.sigma_d[k] = float(T(m.sigma_D))
+                o.sigma_b[k] = float(T(m.sigma_B))
+        mask = 0
+        if any(o.material.epsilon != 1.0 for o in self.geometry):
+            mask |= 1 << _lib.MAT_EPS_INV
+        if any(o.material.mu != 1.0 for o in self.geometry):
+            mask |= 1 << _lib.MAT_MU_INV
+        if any(o.material.sigma_D != 0.0 for o in self.geometry):
+            mask |= 1 << _lib.MAT_SIGMA_D
+        if any(o.material.sigma_B != 0.0 for o in self.geometry):
+            mask |= 1 << _lib.MAT_SIGMA_B
+        return objs, mask
+
+    def component_origins(self):
+        return np.ascontiguousarray([self.grid.component_origin(c) for c in (EX, EY, EZ, HX, HY, HZ)], dtype=np.float64)
+
+    def _device_rasterize(self, ctx):
+        objs, mask = self.geometry_objects()
+        if mask == 0:
+            return [0, 0, 0]
+        org = self.component_origins().reshape(18)
+        mode = {None: 0, "volume": 1, "anisotropic": 2}[self.subpixel_smoothing]
+        cnt = (C.c_int64 * 3)()
+        _lib.check(_lib.lib().khr_geometry_rasterize(ctx, objs, len(self.geometry), mask, mode,
+                                                     org.ctypes.data_as(C.POINTER(C.c_double)), cnt))
+        return list(cnt)
+
+    def get_material(self, kind, comp):
+        """Dense (Nx,Ny,Nz_local) copy of a device material array (kind: 'eps_inv', 'mu_inv', 'sigma_D', 'sigma_B')."""
+        k = {"eps_inv": _lib.MAT_EPS_INV, "mu_inv": _lib.MAT_MU_INV, "sigma_D": _lib.MAT_SIGMA_D,
+             "sigma_B": _lib.MAT_SIGMA_B, "chi3": _lib.MAT_CHI3}[kind]
+        out = np.empty((self.Nx, self.Ny, self.nz_local), dtype=self.T, order="F")
+        _lib.check(_lib.lib().khr_material_read(self.ctx, k, comp, out.ctypes.data))
+        return out
 
     def _source_amplitude(self, src, comp, start, dims):
         """Sources.jl:107-135 _fill_amplitude_data!: weight * amplitude * profile (Complex{Float64})."""

@@ -25,6 +25,13 @@ def oracle_from_simulation(sim):
     if getattr(sim, "complex_fields", False):
         for a in range(3):
             o.set_bloch(a, sim.bloch_k[a])
+    if getattr(sim, "rasterizer", "host") == "device":
+        # the oracle rasterises the same object list itself (its own restatement of Geometry.jl)
+        objs, mask = sim.geometry_objects()
+        rows = [[o.kind] + list(o.center) + list(o.size) + list(o.axes) + list(o.eps_inv) + list(o.mu_inv)
+                + list(o.sigma_d) + list(o.sigma_b) for o in objs]
+        mode = {None: 0, "volume": 1, "anisotropic": 2}[sim.subpixel_smoothing]
+        o.smoothed_voxels = o.rasterize(rows, mask, mode) if mask else [0, 0, 0]
     for key in ("eps_inv", "mu_inv", "sigma_D", "sigma_B"):
         arr = sim.material_arrays[key]
         if arr is not None:

@@ -1655,3 +1655,254 @@ void ko_mode_amplitudes(void* hv, int normal_axis, const int* ids4, const double
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Geometry rasterisation + subpixel smoothing, restated from
+// src/Geometry.jl:150-246 (_rasterize_object_yrange!), :450-605 (init_geometry) and :795-972
+// (_smooth_component_yrange!).  The shape predicates come from GeometryPrimitives.jl, which the
+// reference neither vendors nor pins: Sphere and Cuboid are restated from that package's published
+// definitions (`in`, `bounds`, `surfpt_nearby`, `level`; `volfrac` as the exact volume of a box cut
+// by a plane).  PARITY UNPINNED for this block: no reference test holds raster or smoothing values.
+// Arrays cover cells 1..N of each component grid (the extra staggered cell is never read by the
+// kernels), so a voxel in the last layer has no upper neighbour here.
+// ---------------------------------------------------------------------------
+namespace {
+struct GObj {
+  int kind;            // 0 Sphere, 1 Cuboid
+  double c[3], r[3], ax[9], bmin[3], bmax[3];
+  double val[4][3];    // eps_inv, mu_inv, sigma_D, sigma_B per component
+};
+
+inline bool g_contains(const GObj& o, const double* x) {
+  double d0 = x[0] - o.c[0], d1 = x[1] - o.c[1], d2 = x[2] - o.c[2];
+  if (o.kind == 0) return ((d0 * d0 + d1 * d1) + d2 * d2) <= o.r[0] * o.r[0];
+  for (int k = 0; k < 3; ++k) {
+    double p = (o.ax[3 * k] * d0 + o.ax[3 * k + 1] * d1) + o.ax[3 * k + 2] * d2;
+    if (!(std::fabs(p) <= o.r[k])) return false;
+  }
+  return true;
+}
+
+inline void g_surfpt(const GObj& o, const double* x, double* sp, double* nout) {
+  double d[3] = {x[0] - o.c[0], x[1] - o.c[1], x[2] - o.c[2]};
+  if (o.kind == 0) {
+    double nr = std::sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
+    if (nr == 0.0) { nout[0] = 1.0; nout[1] = 0.0; nout[2] = 0.0; }
+    else for (int k = 0; k < 3; ++k) nout[k] = d[k] / nr;
+    for (int k = 0; k < 3; ++k) sp[k] = o.c[k] + o.r[0] * nout[k];
+    return;
+  }
+  double dp[3], ad[3], sg[3], dl[3], shift[3] = {0, 0, 0}, nax[3] = {0, 0, 0};
+  bool isout[3], onbnd[3], all_on = true;
+  int cnt = 0;
+  for (int k = 0; k < 3; ++k) {
+    dp[k] = (o.ax[3 * k] * d[0] + o.ax[3 * k + 1] * d[1]) + o.ax[3 * k + 2] * d[2];
+    ad[k] = std::fabs(dp[k]);
+    sg[k] = std::copysign(1.0, dp[k]);
+    onbnd[k] = std::fabs(o.r[k] - ad[k]) <= 1.4901161193847656e-08 * o.r[k];
+    isout[k] = (o.r[k] < ad[k]) || onbnd[k];
+    dl[k] = o.r[k] - ad[k];
+    cnt += isout[k] ? 1 : 0;
+    all_on = all_on && (!isout[k] || onbnd[k]);
+  }
+  if (cnt == 0) {
+    int i = 0;
+    if (dl[1] < dl[i]) i = 1;
+    if (dl[2] < dl[i]) i = 2;
+    shift[i] = dl[i] * sg[i];
+    nax[i] = sg[i];
+  } else {
+    for (int k = 0; k < 3; ++k) if (isout[k]) shift[k] = dl[k] * sg[k];
+    if (all_on) { for (int k = 0; k < 3; ++k) nax[k] = onbnd[k] ? sg[k] : 0.0; }
+    else { for (int k = 0; k < 3; ++k) nax[k] = -shift[k]; }
+  }
+  for (int j = 0; j < 3; ++j) {
+    sp[j] = x[j] + ((o.ax[j] * shift[0] + o.ax[3 + j] * shift[1]) + o.ax[6 + j] * shift[2]);
+    nout[j] = (o.ax[j] * nax[0] + o.ax[3 + j] * nax[1]) + o.ax[6 + j] * nax[2];
+  }
+}
+
+inline bool g_level_nonneg(const GObj& o, const double* x) {
+  double d[3] = {x[0] - o.c[0], x[1] - o.c[1], x[2] - o.c[2]};
+  if (o.kind == 0) return 1.0 - std::sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]) / o.r[0] >= 0.0;
+  double m = 0.0;
+  for (int k = 0; k < 3; ++k) {
+    double p = (o.ax[3 * k] * d[0] + o.ax[3 * k + 1] * d[1]) + o.ax[3 * k + 2] * d[2];
+    m = std::fmax(m, std::fabs(p) / o.r[k]);
+  }
+  return 1.0 - m >= 0.0;
+}
+
+inline double g_c3(double t) { return t > 0.0 ? t * t * t : 0.0; }
+inline double g_s2(double t) { return t > 0.0 ? t * t : 0.0; }
+// fraction of the box [lo, hi] on the side of the plane (normal n through r0) opposite to n
+inline double g_volfrac(const double* lo, const double* hi, const double* n, const double* r0) {
+  double a[3], d = 0.0, amax = 0.0;
+  for (int k = 0; k < 3; ++k) {
+    double corner = n[k] >= 0.0 ? lo[k] : hi[k];
+    d += n[k] * (r0[k] - corner);
+    a[k] = std::fabs(n[k]) * (hi[k] - lo[k]);
+    amax = std::fmax(amax, a[k]);
+  }
+  if (amax == 0.0) return d >= 0.0 ? 1.0 : 0.0;
+  double b[3] = {0.0, 0.0, 0.0};
+  int m = 0;
+  for (int k = 0; k < 3; ++k) if (a[k] > 1e-6 * amax) b[m++] = a[k];
+  double tot = 0.0;
+  for (int k = 0; k < m; ++k) tot += b[k];
+  if (d <= 0.0) return 0.0;
+  if (d >= tot) return 1.0;
+  if (m == 1) return d / b[0];
+  if (m == 2) return ((g_s2(d) - g_s2(d - b[0])) - g_s2(d - b[1]) + g_s2(d - b[0] - b[1])) / (2.0 * b[0] * b[1]);
+  double s1 = (g_c3(d - b[0]) + g_c3(d - b[1])) + g_c3(d - b[2]);
+  double s2 = (g_c3(d - b[0] - b[1]) + g_c3(d - b[0] - b[2])) + g_c3(d - b[1] - b[2]);
+  return (((g_c3(d) - s1) + s2) - g_c3(d - b[0] - b[1] - b[2])) / (6.0 * b[0] * b[1] * b[2]);
+}
+
+template <class SimT>
+void rasterize_impl(SimT& S, int nobj, const double* flat, int kinds_mask, int smoothing, long* smoothed3) {
+  using T = std::remove_reference_t<decltype(S.dt)>;
+  std::vector<GObj> objs((size_t)nobj);
+  for (int q = 0; q < nobj; ++q) {
+    const double* f = flat + 28 * q;
+    GObj& o = objs[(size_t)q];
+    o.kind = (int)f[0];
+    for (int k = 0; k < 3; ++k) o.c[k] = f[1 + k];
+    if (o.kind == 0) {
+      o.r[0] = f[4]; o.r[1] = o.r[2] = 0;
+      for (int k = 0; k < 3; ++k) { o.bmin[k] = o.c[k] - o.r[0]; o.bmax[k] = o.c[k] + o.r[0]; }
+      for (int k = 0; k < 9; ++k) o.ax[k] = 0;
+    } else {
+      bool ident = true;
+      for (int k = 0; k < 9; ++k) ident = ident && f[7 + k] == 0.0;
+      for (int k = 0; k < 3; ++k) {
+        o.r[k] = f[4 + k] / 2;
+        double nr = 0;
+        for (int j = 0; j < 3; ++j) { o.ax[3 * k + j] = ident ? (j == k ? 1.0 : 0.0) : f[7 + 3 * k + j]; nr += o.ax[3 * k + j] * o.ax[3 * k + j]; }
+        nr = std::sqrt(nr);
+        for (int j = 0; j < 3; ++j) o.ax[3 * k + j] /= nr;
+      }
+      for (int i = 0; i < 3; ++i) {
+        double m = 0;
+        for (int j = 0; j < 3; ++j) m += std::fabs(o.ax[3 * j + i]) * o.r[j];
+        o.bmin[i] = o.c[i] - m; o.bmax[i] = o.c[i] + m;
+      }
+    }
+    for (int kd = 0; kd < 4; ++kd)
+      for (int k = 0; k < 3; ++k) o.val[kd][k] = (double)(T)f[16 + 3 * kd + k];
+  }
+  if (smoothed3) smoothed3[0] = smoothed3[1] = smoothed3[2] = 0;
+  for (int c = 0; c < 6; ++c) {
+    const int d = c % 3;
+    const int perm_kind = c < 3 ? 0 : 1, sig_kind = c < 3 ? 2 : 3;
+    const bool want_perm = (kinds_mask >> perm_kind) & 1, want_sig = (kinds_mask >> sig_kind) & 1;
+    if (!want_perm && !want_sig) continue;
+    double org[3];
+    S.component_origin(c, org);
+    // _precompute_coords (Geometry.jl:351-363): origin + (i - 1) * Δ, the product formed in T
+    std::vector<double> xs[3];
+    for (int a = 0; a < 3; ++a) {
+      xs[a].resize((size_t)S.N[a]);
+      for (int i = 1; i <= S.N[a]; ++i) xs[a][(size_t)i - 1] = org[a] + (double)((T)(i - 1) * S.dl[a]);
+    }
+    Arr3<T>* perm = want_perm ? (c < 3 ? &S.eps_inv_a[d] : &S.mu_inv_a[d]) : nullptr;
+    Arr3<T>* sig = want_sig ? (c < 3 ? &S.sigD[d] : &S.sigB[d]) : nullptr;
+    if (perm) { perm->alloc(S.N[0], S.N[1], S.N[2]); std::fill(perm->d.begin(), perm->d.end(), T(1)); }
+    if (sig) sig->alloc(S.N[0], S.N[1], S.N[2]);
+    if (perm && c < 3) S.eps_is_array = true;
+    if (perm && c >= 3) S.mu_is_array = true;
+    // paint last -> first so that earlier objects take priority (Geometry.jl:240-246)
+    for (int gi = nobj - 1; gi >= 0; --gi) {
+      const GObj& o = objs[(size_t)gi];
+      int lo[3], hi[3];
+      bool empty = false;
+      for (int a = 0; a < 3; ++a) {
+        // searchsortedfirst(xs, bmin) .. searchsortedlast(xs, bmax), clamped to the array
+        lo[a] = (int)(std::lower_bound(xs[a].begin(), xs[a].end(), o.bmin[a]) - xs[a].begin()) + 1;
+        hi[a] = (int)(std::upper_bound(xs[a].begin(), xs[a].end(), o.bmax[a]) - xs[a].begin());
+        lo[a] = std::max(lo[a], 1); hi[a] = std::min(hi[a], S.N[a]);
+        if (lo[a] > hi[a]) empty = true;
+      }
+      if (empty) continue;
+      for (int iz = lo[2]; iz <= hi[2]; ++iz)
+        for (int iy = lo[1]; iy <= hi[1]; ++iy)
+          for (int ix = lo[0]; ix <= hi[0]; ++ix) {
+            double pt[3] = {xs[0][(size_t)ix - 1], xs[1][(size_t)iy - 1], xs[2][(size_t)iz - 1]};
+            if (g_contains(o, pt)) {
+              if (perm) perm->at(ix - 1, iy - 1, iz - 1) = (T)o.val[perm_kind][d];
+              if (sig) sig->at(ix - 1, iy - 1, iz - 1) = (T)o.val[sig_kind][d];
+            }
+          }
+    }
+    if (!(perm && c < 3 && smoothing != 0)) continue;
+    // _smooth_component_yrange! (Geometry.jl:878-972)
+    Arr3<T> orig = *perm;
+    const T rtol = (T)1e-6;
+    const double hd[3] = {(double)S.dl[0] / 2, (double)S.dl[1] / 2, (double)S.dl[2] / 2};
+    long n_sm = 0;
+    const int nx = S.N[0], ny = S.N[1], nz = S.N[2];
+#pragma omp parallel for collapse(2) schedule(static) reduction(+ : n_sm)
+    for (int iz = 1; iz <= nz; ++iz)
+      for (int iy = 1; iy <= ny; ++iy)
+        for (int ix = 1; ix <= nx; ++ix) {
+          T ec = orig.at(ix - 1, iy - 1, iz - 1);
+          bool is_if = false;
+          T en = ec;
+          static const int off[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+          for (int q = 0; q < 6; ++q) {
+            int jx = ix + off[q][0], jy = iy + off[q][1], jz = iz + off[q][2];
+            if (!(1 <= jx && jx <= nx && 1 <= jy && jy <= ny && 1 <= jz && jz <= nz)) continue;
+            T nb = orig.at(jx - 1, jy - 1, jz - 1);
+            if (std::abs(nb - ec) > rtol * std::max(std::abs(nb), std::abs(ec))) { is_if = true; en = nb; break; }
+          }
+          if (!is_if) continue;
+          double p[3] = {xs[0][(size_t)ix - 1], xs[1][(size_t)iy - 1], xs[2][(size_t)iz - 1]};
+          double eps_c = (double)(T(1) / ec), eps_n = (double)(T(1) / en);
+          double min_d2 = std::numeric_limits<double>::max();
+          double bn[3] = {0, 0, 1}, bs[3] = {p[0], p[1], p[2]};
+          int best = -1;
+          for (int gi = 0; gi < nobj; ++gi) {
+            const GObj& o = objs[(size_t)gi];
+            double bb = 0.0;
+            for (int k = 0; k < 3; ++k) {
+              if (p[k] < o.bmin[k]) bb += (o.bmin[k] - p[k]) * (o.bmin[k] - p[k]);
+              else if (p[k] > o.bmax[k]) bb += (p[k] - o.bmax[k]) * (p[k] - o.bmax[k]);
+            }
+            if (bb >= min_d2) continue;
+            double sp[3], no[3];
+            g_surfpt(o, p, sp, no);
+            double e0 = sp[0] - p[0], e1 = sp[1] - p[1], e2 = sp[2] - p[2];
+            double d2 = (e0 * e0 + e1 * e1) + e2 * e2;
+            if (d2 < min_d2) { min_d2 = d2; best = gi; for (int k = 0; k < 3; ++k) { bn[k] = no[k]; bs[k] = sp[k]; } }
+          }
+          if (best < 0) continue;
+          double nrm = std::sqrt((bn[0] * bn[0] + bn[1] * bn[1]) + bn[2] * bn[2]);
+          double nh[3] = {0, 0, 1};
+          if (nrm > 0) for (int k = 0; k < 3; ++k) nh[k] = bn[k] / nrm;
+          double lo3[3] = {p[0] - hd[0], p[1] - hd[1], p[2] - hd[2]}, hi3[3] = {p[0] + hd[0], p[1] + hd[1], p[2] + hd[2]};
+          double f_in = g_volfrac(lo3, hi3, nh, bs);
+          double eps_shape, eps_bg;
+          if (g_level_nonneg(objs[(size_t)best], p)) { eps_shape = eps_c; eps_bg = eps_n; }
+          else { eps_shape = eps_n; eps_bg = eps_c; }
+          double eps_avg = f_in * eps_shape + (1 - f_in) * eps_bg;
+          double eps_inv_harm = f_in / eps_shape + (1 - f_in) / eps_bg;
+          double r;
+          if (smoothing == 2) { double nc2 = nh[d] * nh[d]; r = (1 - nc2) * eps_inv_harm + nc2 / eps_avg; }
+          else r = 1.0 / eps_avg;
+          perm->at(ix - 1, iy - 1, iz - 1) = (T)r;
+          n_sm += 1;
+        }
+    if (smoothed3) smoothed3[d] = n_sm;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+// objs: nobj x 28 doubles = kind, centre(3), size(3), axes(9), eps_inv(3), mu_inv(3), sigma_D(3), sigma_B(3)
+void ko_rasterize(void* hv, int nobj, const double* objs, int kinds_mask, int smoothing, long* smoothed3) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, rasterize_impl(S, nobj, objs, kinds_mask, smoothing, smoothed3));
+}
+
+}  // extern "C"

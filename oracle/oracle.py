@@ -72,6 +72,7 @@ def lib():
         L.ko_set_chi3_literal_order.argtypes = [C.c_void_p, C.c_int]
         L.ko_set_bloch.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.ko_set_grid_spacing.argtypes = [C.c_void_p, C.c_int, dp, C.c_int]
+        L.ko_rasterize.argtypes = [C.c_void_p, C.c_int, dp, C.c_int, C.c_int, C.POINTER(C.c_long)]
         L.ko_set_boundary_conditions.argtypes = [C.c_void_p, ip]
         L.ko_timestep.restype = C.c_long
         L.ko_num_threads.restype = C.c_int
@@ -374,3 +375,12 @@ class OracleSim:
         self.L.ko_mode_amplitudes(self.h, int(normal_axis), ip, ri.ctypes.data_as(dp), ap.ctypes.data_as(dp),
                                   am.ctypes.data_as(dp), pm.ctypes.data_as(dp))
         return ap[0::2] + 1j * ap[1::2], am[0::2] + 1j * am[1::2], pm
+
+    def rasterize(self, objects, kinds_mask, smoothing=0):
+        """init_geometry rasterisation + _apply_subpixel_smoothing! (Geometry.jl:150-246, 450-605, 795-972).
+        objects: rows of 28 numbers (kind, centre, size, axes(9), eps_inv(3), mu_inv(3), sigma_D(3), sigma_B(3)).
+        Returns the number of smoothed interface voxels per E component."""
+        o, op = _d(np.asarray(objects, dtype=np.float64).reshape(-1, 28))
+        cnt = (C.c_long * 3)()
+        self.L.ko_rasterize(self.h, o.shape[0], op, int(kinds_mask), int(smoothing), cnt)
+        return list(cnt)

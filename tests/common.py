@@ -21,7 +21,7 @@ class Pair:
     def __init__(self, cell, res, pml, dtype=np.float32, courant=0.5, sources=(), monitors=(), eps_inv=None,
                  mu_inv=None, sigma_D=None, sigma_B=None, poles=(), absorbers=None, center=(0.0, 0.0, 0.0),
                  build_gpu=True, rank=0, nranks=1, comm_id=None, device=0, geometry=None,
-                 boundary_conditions=None, chi3=None, grid_spacing=None):
+                 boundary_conditions=None, chi3=None, grid_spacing=None, rasterizer="host", subpixel_smoothing=None):
         self.dtype = dtype
         bnd = None if pml is None else [[p, p] if np.isscalar(p) else list(p) for p in pml]
         ksrc = [kb.UniformSource(tp, comp, c, s) for (comp, c, s, tp) in sources]
@@ -30,13 +30,15 @@ class Pair:
         self.k = kb.Simulation(cell, list(center), res, ksrc, boundaries=bnd, monitors=kmon, Courant=courant,
                                dtype=dtype, eps_inv=eps_inv, mu_inv=mu_inv, sigma_D=sigma_D, sigma_B=sigma_B,
                                poles=list(poles), absorbers=absorbers, rank=rank, nranks=nranks, device=device,
-                               geometry=geometry, boundary_conditions=boundary_conditions, chi3=chi3, grid_spacing=grid_spacing)
+                               geometry=geometry, boundary_conditions=boundary_conditions, chi3=chi3, grid_spacing=grid_spacing,
+                               rasterizer=rasterizer, subpixel_smoothing=subpixel_smoothing)
         self.grid = self.k.grid
         # the oracle always simulates the whole domain (single chunk)
         whole = self.k if nranks == 1 else kb.Simulation(
             cell, list(center), res, ksrc, boundaries=bnd, monitors=kmon, Courant=courant, dtype=dtype, eps_inv=eps_inv,
             mu_inv=mu_inv, sigma_D=sigma_D, sigma_B=sigma_B, poles=list(poles), absorbers=absorbers, geometry=geometry,
-            boundary_conditions=boundary_conditions, chi3=chi3, grid_spacing=grid_spacing)
+            boundary_conditions=boundary_conditions, chi3=chi3, grid_spacing=grid_spacing,
+            rasterizer=rasterizer, subpixel_smoothing=subpixel_smoothing)
         self.o, self.omon = oracle_from_simulation(whole)
         self.build_gpu = build_gpu
         if build_gpu:
