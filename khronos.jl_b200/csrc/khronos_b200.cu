@@ -481,9 +481,11 @@ struct Impl : Base {
             const int cmin = a == 2 ? std::max(1 - off, 0) : 1;
             const int cmax = a == 2 ? std::min(g.n[2] - off, N[2] + 1) : N[a];
             const double dd = (double)dl[a];
-            int i0 = (int)std::floor((o.bmin[a] - gg.origin[a]) / dd) + 1 - off - 2;
-            int i1 = (int)std::ceil((o.bmax[a] - gg.origin[a]) / dd) + 1 - off + 2;
-            i0 = std::max(i0, cmin); i1 = std::min(i1, cmax);
+            // estimate in double (objects like a 1e9-wide background box overflow an int), then clamp
+            const double e0 = std::floor((o.bmin[a] - gg.origin[a]) / dd) + 1 - off - 2;
+            const double e1 = std::ceil((o.bmax[a] - gg.origin[a]) / dd) + 1 - off + 2;
+            int i0 = (int)std::min(std::max(e0, (double)cmin), (double)cmax + 1);
+            int i1 = (int)std::max(std::min(e1, (double)cmax), (double)cmin - 1);
             while (i0 <= i1 && !(gcoord(gg.origin[a], i0 + off, dl[a]) >= o.bmin[a])) ++i0;
             while (i1 >= i0 && !(gcoord(gg.origin[a], i1 + off, dl[a]) <= o.bmax[a])) --i1;
             lo[a] = i0; hi[a] = i1;
@@ -552,9 +554,10 @@ struct Impl : Base {
           const int off = a == 2 ? g.z_start - 1 : 0;
           // all six component grids lie within half a cell of the centre grid: pad by one cell
           const double org = origins18[3 * (grp == 1 ? 0 : 3) + a];
-          int i0 = (int)std::floor((o.bmin[a] - org) / (double)dl[a]) + 1 - off - 1;
-          int i1 = (int)std::ceil((o.bmax[a] - org) / (double)dl[a]) + 1 - off + 1;
-          i0 = std::max(i0, 1); i1 = std::min(i1, N[a]);
+          const double e0 = std::floor((o.bmin[a] - org) / (double)dl[a]) + 1 - off - 1;
+          const double e1 = std::ceil((o.bmax[a] - org) / (double)dl[a]) + 1 - off + 1;
+          int i0 = (int)std::min(std::max(e0, 1.0), (double)N[a] + 1);
+          int i1 = (int)std::max(std::min(e1, (double)N[a]), 0.0);
           b[a] = i0; b[3 + a] = i1;
           if (i0 > i1) empty = true;
         }

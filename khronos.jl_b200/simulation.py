@@ -354,10 +354,11 @@ class Simulation:
         poles = []
         if not self.geometry:
             return arrays, poles
-        need_eps = any(o.material.epsilon != 1.0 for o in self.geometry)
-        need_mu = any(o.material.mu != 1.0 for o in self.geometry)
-        need_sd = any(o.material.sigma_D != 0.0 for o in self.geometry)
-        need_sb = any(o.material.sigma_B != 0.0 for o in self.geometry)
+        host = self.rasterizer == "host"     # the device rasterizer produces these four kinds itself
+        need_eps = host and any(o.material.epsilon != 1.0 for o in self.geometry)
+        need_mu = host and any(o.material.mu != 1.0 for o in self.geometry)
+        need_sd = host and any(o.material.sigma_D != 0.0 for o in self.geometry)
+        need_sb = host and any(o.material.sigma_B != 0.0 for o in self.geometry)
         shape = tuple(g.N)
 
         def paint(comp0, attr, inverse):

@@ -102,7 +102,7 @@ def uled(res=40, lorentz=True):
                 sources=srcs, monitors=mons, geometry=geom)
 
 
-def metalens(nx=512, ny=512, nz=128, res=32, pml_cells=15, pillars=8):
+def metalens(nx=512, ny=512, nz=128, res=32, pml_cells=15, pillars=8, rotate=False):
     """Slab-decomposed metalens-like domain: substrate half-space + pillar array, plane source,
     focal-plane DFT. The benchmark size is 2048x2048x512 per GPU; smaller sizes are parity cases."""
     cell = [nx / res, ny / res, nz / res]
@@ -115,7 +115,11 @@ def metalens(nx=512, ny=512, nz=128, res=32, pml_cells=15, pillars=8):
         for j in range(pillars):
             w = pitch * rng.uniform(0.3, 0.7)
             c = [-cell[0] / 2 + pitch * (i + 1), -cell[1] / 2 + cell[1] / (pillars + 1) * (j + 1), zsub + 0.3]
-            geom.append(Object(Cuboid(c, [w, w, 0.6]), Material(epsilon=5.76)))
+            axes = None
+            if rotate:  # benchmark/metalens.jl rotates every pillar about z
+                th = rng.uniform(0, math.pi)
+                axes = [[math.cos(th), math.sin(th), 0.0], [-math.sin(th), math.cos(th), 0.0], [0.0, 0.0, 1.0]]
+            geom.append(Object(Cuboid(c, [w, w, 0.6], axes=axes), Material(epsilon=5.76)))
     geom.append(Object(Cuboid([0, 0, zsub - cell[2]], [1e9, 1e9, 2 * cell[2]]), Material(epsilon=2.13)))
     cw = ContinuousWaveSource(1.0 / 0.64)
     inf = float("inf")
@@ -132,7 +136,8 @@ def metalens(nx=512, ny=512, nz=128, res=32, pml_cells=15, pillars=8):
 WORKLOADS = {"dipole": dipole, "waveguide_mode": waveguide_mode, "sphere": sphere, "uled": uled, "metalens": metalens}
 
 
-def build_simulation(desc, dtype=np.float32, device=0, rank=0, nranks=1):
+def build_simulation(desc, dtype=np.float32, device=0, rank=0, nranks=1, rasterizer="host", subpixel_smoothing=None):
     return Simulation(desc["cell_size"], [0.0, 0.0, 0.0], desc["resolution"], desc["sources"], boundaries=desc["pml"],
                       geometry=desc["geometry"], monitors=desc["monitors"], Courant=desc["courant"], dtype=dtype,
-                      device=device, rank=rank, nranks=nranks)
+                      device=device, rank=rank, nranks=nranks, rasterizer=rasterizer,
+                      subpixel_smoothing=subpixel_smoothing)
