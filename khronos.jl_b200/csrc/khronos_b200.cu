@@ -260,12 +260,19 @@ struct Impl : Base {
   // phase 0 = boundary planes that feed the halo exchange, phase 1 = the rest
   // table index: 0 interior; 1 / 2 / 4 PML on x / y / z only; 7 PML on several axes;
   // 8 "full" (sources, conductivity, poles); 3, 5, 6 unused (folded into 7)
-  static constexpr int NTAB = 9, NSIDE = 6;
+  // tables MBASE + m hold the tiles of class m (interior / PML) whose per-voxel material arrays are
+  // constant over the tile: they run the MARR = 2 kernels (values in the work item, 12 registers
+  // fewer, no material loads) next to the remaining tiles of the class
+  static constexpr int MBASE = 9, NTAB = 2 * MBASE, NSIDE = 12;
+  bool split_uniform = true;
   Table tab[2][2][NTAB];
   cudaStream_t side[NSIDE] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {};
   bool axis_spec = false;  // measured slower on B200 (profiles/r01_axis_spec_pdl_ab.txt): more launches, more tails
-  static int side_of(int m) { return m == 1 ? 0 : m == 2 ? 1 : m == 4 ? 2 : m == 7 ? 3 : m == 8 ? 4 : 5; }
+  static int side_of(int mm) {
+    const int m = mm % MBASE;
+    return (m == 1 ? 0 : m == 2 ? 1 : m == 4 ? 2 : m == 7 ? 3 : m == 8 ? 4 : 5) + (mm >= MBASE ? 6 : 0);
+  }
   bool main_heaviest = false;
   // chain mode: all kernels of a step on one stream, launched with programmatic dependent launch;
   // H <-> E ordering is enforced per z chunk by device counters (step_kernels.cuh), so the tail of
@@ -323,13 +330,14 @@ struct Impl : Base {
     for (int q = 0; q < NSIDE; ++q) {
       // the PML / full kernels are the critical path of a half-step: their CTAs get the SM slots
       // first, the interior kernel (main stream, default priority) fills what is left
-      CUDA_OK(cudaStreamCreateWithPriority(&side[q], cudaStreamNonBlocking, (use_prio && q < 5) ? prio_hi : prio_lo));
+      CUDA_OK(cudaStreamCreateWithPriority(&side[q], cudaStreamNonBlocking, (use_prio && (q % 6) < 5) ? prio_hi : prio_lo));
       CUDA_OK(cudaEventCreateWithFlags(&ev_join[q], cudaEventDisableTiming));
     }
     if (const char* e = getenv("KHR_AXIS_SPEC")) axis_spec = atoi(e) != 0;
     if (const char* e = getenv("KHR_MAIN_HEAVIEST")) main_heaviest = atoi(e) != 0;
     if (const char* e = getenv("KHR_ORDER")) launch_order = atoi(e);
     if (const char* e = getenv("KHR_CHAIN")) pdl = atoi(e) != 0;
+    if (const char* e = getenv("KHR_SPLIT_UNIFORM")) split_uniform = atoi(e) != 0;
     if (pdl) multi_stream = false;
     CUDA_OK(cudaHostAlloc((void**)&h_err, sizeof(int), cudaHostAllocMapped));
     *h_err = 0;
@@ -968,9 +976,10 @@ struct Impl : Base {
       if (t.items.empty()) return;
       if (k == idx && out) {
         memset(out, 0, sizeof(*out));
-        static const char* mn[NTAB] = {"interior", "pml-x", "pml-y", "", "pml-z", "", "", "pml", "full"};
+        static const char* mn[MBASE] = {"interior", "pml-x", "pml-y", "", "pml-z", "", "", "pml", "full"};
         snprintf(out->name, sizeof(out->name), "step_kernel<%s,%s,%s,%s>%s", sizeof(T) == 4 ? "f32" : "f64",
-                 gq == 0 ? "H" : "E", mn[m], m_arr[gq][0] ? "marr" : "mscalar", ph == 0 ? "[boundary]" : "");
+                 gq == 0 ? "H" : "E", mn[m % MBASE], m >= MBASE ? "muniform" : (m_arr[gq][0] ? "marr" : "mscalar"),
+                 ph == 0 ? "[boundary]" : "");
         out->launches = t.nlaunch;
         out->total_ms = t.total_ms;
         out->cells_per_launch = t.cells;
@@ -1125,12 +1134,12 @@ struct Impl : Base {
     if (const char* e = getenv("KHR_TAIL_ZN")) tail_zn = atoi(e);
     if (const char* e = getenv("KHR_SORT_ITEMS")) sort_items = atoi(e);
     for_tables([&](Table& t, int, int, int m) {
-      if (t.items.empty() || m == 8) return;
+      if (t.items.empty() || m % MBASE == 8) return;
       const size_t n = t.items.size();
       std::vector<size_t> idx(n);
       for (size_t q = 0; q < n; ++q) idx[q] = q;
       if (sort_items) std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return t.cost[a] > t.cost[b]; });
-      const size_t slots = (size_t)148 * (m == 0 ? 3 : 2);
+      const size_t slots = (size_t)148 * (m % MBASE == 0 ? 3 : 2);
       const size_t ntail = tail_zn > 0 ? std::min(n / 3, slots) : 0;
       std::vector<WorkItem> out;
       out.reserve(n + 4 * ntail);
@@ -1175,6 +1184,37 @@ struct Impl : Base {
       }
     });
     CUDA_OK(cudaStreamSynchronize(stream));
+    // move the constant-material tiles of the interior / PML classes into their own tables
+    if (split_uniform && uniform_tiles && !nonuniform && !pdl) {
+      for (int gq = 0; gq < 2; ++gq)
+        for (int ph = 0; ph < 2; ++ph)
+          for (int m = 0; m < MBASE - 1; ++m) {   // not the "full" class
+            // only the general PML class: its MARR = 1 kernel spills at the 128-register cap, the
+            // MARR = 2 one does not (E-PML launch 0.145 -> 0.136 ms on the waveguide); the interior
+            // kernel gains nothing from a second launch (measured, profiles/r01_s4_ab_split_uniform.txt)
+            if (m != 7) continue;
+            Table& t = tab[gq][ph][m];
+            Table& u = tab[gq][ph][MBASE + m];
+            if (t.items.empty()) continue;
+            std::vector<WorkItem> keep;
+            for (auto& it : t.items) ((it.flags & 2) ? u.items : keep).push_back(it);
+            if (u.items.empty()) continue;
+            // bytes model / cell counts follow the items (the model does not know about skipped loads)
+            const double per_cell = t.cells ? t.alg_bytes / (double)t.cells : 0.0;
+            int64_t ucells = 0;
+            for (auto& it : u.items) ucells += (int64_t)it.xw * it.yh * it.zn;
+            u.cells = ucells; u.alg_bytes = per_cell * (double)ucells;
+            t.cells -= ucells; t.alg_bytes -= u.alg_bytes;
+            t.items.swap(keep);
+            for (Table* q : {&t, &u}) {
+              if (q->items.empty()) { q->d = nullptr; continue; }
+              size_t bytes = q->items.size() * sizeof(WorkItem);
+              q->d = (WorkItem*)dalloc((bytes + sizeof(T) - 1) / sizeof(T), false);
+              CUDA_OK(cudaMemcpyAsync(q->d, q->items.data(), bytes, cudaMemcpyHostToDevice, stream));
+            }
+          }
+      CUDA_OK(cudaStreamSynchronize(stream));
+    }
     for_tables([&](Table& t, int, int, int) {
       t.uniform_items = 0;
       for (auto& it : t.items) t.uniform_items += (it.flags & 2) ? 1 : 0;
@@ -1183,7 +1223,7 @@ struct Impl : Base {
 
   // ---- stepping -------------------------------------------------------------
   template <int GROUP, int MODE, int AXM>
-  void launch_mode(const StepParams<T>& p, bool marr, int n, cudaStream_t st) {
+  void launch_mode(const StepParams<T>& p, int marr, int n, cudaStream_t st) {
     if (pdl) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)n); cfg.blockDim = dim3(CTA); cfg.dynamicSmemBytes = 0; cfg.stream = st;
@@ -1191,19 +1231,23 @@ struct Impl : Base {
       at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       at[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
-      if (marr) CUDA_OK(cudaLaunchKernelEx(&cfg, step_kernel<T, GROUP, MODE, true, AXM>, p));
-      else CUDA_OK(cudaLaunchKernelEx(&cfg, step_kernel<T, GROUP, MODE, false, AXM>, p));
+      if (marr) CUDA_OK(cudaLaunchKernelEx(&cfg, step_kernel<T, GROUP, MODE, 1, AXM>, p));
+      else CUDA_OK(cudaLaunchKernelEx(&cfg, step_kernel<T, GROUP, MODE, 0, AXM>, p));
     } else if (nonuniform) {
       // non-uniform grids use the general (AXM = 7) kernels
       if constexpr (AXM == 7) {
-        if (marr) step_kernel<T, GROUP, MODE, true, 7, true><<<n, CTA, 0, st>>>(p);
-        else step_kernel<T, GROUP, MODE, false, 7, true><<<n, CTA, 0, st>>>(p);
+        if (marr) step_kernel<T, GROUP, MODE, 1, 7, true><<<n, CTA, 0, st>>>(p);
+        else step_kernel<T, GROUP, MODE, 0, 7, true><<<n, CTA, 0, st>>>(p);
       } else {
         throw std::string("internal: axis-specialised kernels have no non-uniform variant");
       }
     } else {
-      if (marr) step_kernel<T, GROUP, MODE, true, AXM><<<n, CTA, 0, st>>>(p);
-      else step_kernel<T, GROUP, MODE, false, AXM><<<n, CTA, 0, st>>>(p);
+      if (marr == 2) {
+        if constexpr (AXM == 7 && MODE < 2) step_kernel<T, GROUP, MODE, 2, 7><<<n, CTA, 0, st>>>(p);
+        else throw std::string("internal: no tile-uniform variant of this kernel");
+      }
+      else if (marr) step_kernel<T, GROUP, MODE, 1, AXM><<<n, CTA, 0, st>>>(p);
+      else step_kernel<T, GROUP, MODE, 0, AXM><<<n, CTA, 0, st>>>(p);
     }
     ++launches;
   }
@@ -1221,16 +1265,18 @@ struct Impl : Base {
       if (!tab[GROUP][phase][m].items.empty() && tab[GROUP][phase][m].alg_bytes > best) { best = tab[GROUP][phase][m].alg_bytes; mmain = m; }
     if (!main_heaviest) mmain = 0;
     int order[NTAB], no = 0;
+    // class c = m % MBASE; the tile-uniform table of a class (m = MBASE + c) goes right before its remainder
+    auto push_class = [&](int c) { if (MBASE + c != mmain) order[no++] = MBASE + c; if (c != mmain) order[no++] = c; };
     if (launch_order == 1) {        // PML classes, interior, full last
-      for (int m = 7; m >= 1; --m) order[no++] = m;
-      order[no++] = 0; order[no++] = 8;
+      for (int c = 7; c >= 1; --c) push_class(c);
+      push_class(0); push_class(8);
     } else if (launch_order == 2) { // PML classes, full, interior
-      for (int m = 7; m >= 1; --m) order[no++] = m;
-      order[no++] = 8; order[no++] = 0;
+      for (int c = 7; c >= 1; --c) push_class(c);
+      push_class(8); push_class(0);
     } else {                        // full, PML classes, interior
-      for (int m = NTAB - 1; m >= 0; --m) if (m != mmain) order[no++] = m;
-      order[no++] = mmain;
+      for (int c = MBASE - 1; c >= 0; --c) push_class(c);
     }
+    order[no++] = mmain;
     for (int oi = 0; oi < no; ++oi) {
       const int m = order[oi];
       Table& t = tab[GROUP][phase][m];
@@ -1249,13 +1295,14 @@ struct Impl : Base {
         }
         CUDA_OK(cudaEventRecord(t.ev[t.ev_used], st));
       }
-      switch (m) {
-        case 0: launch_mode<GROUP, 0, 7>(p, marr, n, st); break;
-        case 1: launch_mode<GROUP, 1, 1>(p, marr, n, st); break;
-        case 2: launch_mode<GROUP, 1, 2>(p, marr, n, st); break;
-        case 4: launch_mode<GROUP, 1, 4>(p, marr, n, st); break;
-        case 8: launch_mode<GROUP, 2, 7>(p, marr, n, st); break;
-        default: launch_mode<GROUP, 1, 7>(p, marr, n, st); break;
+      const int mk = m >= MBASE ? 2 : (marr ? 1 : 0);
+      switch (m % MBASE) {
+        case 0: launch_mode<GROUP, 0, 7>(p, mk, n, st); break;
+        case 1: launch_mode<GROUP, 1, 1>(p, mk, n, st); break;
+        case 2: launch_mode<GROUP, 1, 2>(p, mk, n, st); break;
+        case 4: launch_mode<GROUP, 1, 4>(p, mk, n, st); break;
+        case 8: launch_mode<GROUP, 2, 7>(p, mk, n, st); break;
+        default: launch_mode<GROUP, 1, 7>(p, mk, n, st); break;
       }
       if (profiling) {
         CUDA_OK(cudaEventRecord(t.ev[t.ev_used + 1], st));

@@ -243,7 +243,9 @@ __device__ __forceinline__ void cascade(const T (&k)[4], const Co<T> (&cn)[4], c
 // The half-step kernel.
 //   GROUP 0: H from curl E (idx_curl = +1); GROUP 1: E from curl H (idx_curl = -1)
 //   MODE 0: pure interior; 1: + PML cascade; 2: + sigma_D/B, sources, ADE poles
-//   MARR   : per-voxel m^-1 arrays (eps^-1 or mu^-1) instead of a scalar
+//   MARR   : 0 scalar m^-1; 1 per-voxel m^-1 arrays (eps^-1 or mu^-1); 2 per-voxel arrays that are
+//            constant over every tile of the launch (the planner puts such tiles in their own table):
+//            the three values ride in the work item, no loads, no vector registers
 // The row width (lanes along x) is a per-item power of two, 8/16/32.
 // ----------------------------------------------------------------------------
 template <class T, int MODE, int AXM>
@@ -268,7 +270,7 @@ constexpr int min_ctas() {
 //            a single-axis PML tile carries one W and one U array and nothing else.
 //   NU     : non-uniform grid — the curl uses inv(Δx[ix]), inv(Δy[iy]), inv(Δz[iz]) of the updated cell
 //            (get_inv_dx(Δ::AbstractVector, i), Helpers.jl:283-291) instead of three scalars
-template <class T, int GROUP, int MODE, bool MARR, int AXM = 7, bool NU = false>
+template <class T, int GROUP, int MODE, int MARR, int AXM = 7, bool NU = false>
 __global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(const __grid_constant__ StepParams<T> p) {
   constexpr int IC = (GROUP == 0) ? 1 : -1;
   constexpr bool GENERAL = MODE >= 1;   // PML cascade
@@ -352,7 +354,8 @@ __global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(c
   czn.s = T(0); czn.om = T(1); czn.ip = T(1);
   if constexpr (GENERAL && PZA) { czn.s = p.sg[2][it.z0 - 1]; czn.om = p.om[2][it.z0 - 1]; czn.ip = p.ip[2][it.z0 - 1]; }
   const int z_end = it.z0 + it.zn;
-  const bool m_uniform = MARR && (it.flags & 2) != 0;  // block-uniform
+  const bool m_uniform = MARR == 1 && (it.flags & 2) != 0;  // block-uniform
+  const T mu0 = (T)it.mu[0], mu1 = (T)it.mu[1], mu2 = (T)it.mu[2];   // MARR == 2
   const bool yedge = (GROUP == 0) ? (row == it.yh - 1) : (row == 0);  // row whose y neighbour belongs to another CTA
 
   // everything plane zp will load from HBM, requested into L2 ahead of time
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(c
     if (edge) { pf_l2(Ay + nb + (GROUP == 0 ? 4 : -1)); pf_l2(Az + nb + (GROUP == 0 ? 4 : -1)); }
     pf_l2(p.F[0] + nb); pf_l2(p.F[1] + nb); pf_l2(p.F[2] + nb);
     const long long nm = p.mplane * (long long)(zp - 1) + mo;
-    if constexpr (MARR) {
+    if constexpr (MARR == 1) {
       if (!m_uniform) { pf_l2(p.m_arr[0] + nm); pf_l2(p.m_arr[1] + nm); pf_l2(p.m_arr[2] + nm); }
     }
     if constexpr (GENERAL) {
@@ -501,7 +504,7 @@ __global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(c
         az_x = Az[base + (GROUP == 0 ? 4 : -1)];
       }
       fx = ld4(Fx); fy = ld4(Fy); fz = ld4(Fz);
-      if constexpr (MARR) {
+      if constexpr (MARR == 1) {
         if (m_uniform) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) { m0.v[e] = (T)it.mu[0]; m1.v[e] = (T)it.mu[1]; m2.v[e] = (T)it.mu[2]; }
@@ -512,9 +515,9 @@ __global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(c
     } else {
       ax0 = ay0 = az0 = ax_z = ay_z = az_y = ax_y = zero4<T>();
     }
-#define KHR_M0(e) (MARR ? m0.v[e] : p.m_inv)
-#define KHR_M1(e) (MARR ? m1.v[e] : p.m_inv)
-#define KHR_M2(e) (MARR ? m2.v[e] : p.m_inv)
+#define KHR_M0(e) (MARR == 1 ? m0.v[e] : (MARR == 2 ? mu0 : p.m_inv))
+#define KHR_M1(e) (MARR == 1 ? m1.v[e] : (MARR == 2 ? mu1 : p.m_inv))
+#define KHR_M2(e) (MARR == 1 ? m2.v[e] : (MARR == 2 ? mu2 : p.m_inv))
     // x neighbour by shuffle inside the LX-lane row
     {
       T sy, sz;

@@ -68,6 +68,8 @@ MODES = [
     dict(KHR_AXIS_SPEC=1),
     dict(KHR_AXIS_SPEC=1, KHR_CHAIN=1),
     dict(KHR_UNIFORM_TILES=0),
+    dict(KHR_SPLIT_UNIFORM=0),
+    dict(KHR_SPLIT_UNIFORM=0, KHR_AXIS_SPEC=1),
     dict(KHR_MULTI_STREAM=0),
     dict(KHR_ZSEG=5, KHR_ZSEG_FULL=1),
     dict(KHR_TAIL_ZN=2, KHR_SORT_ITEMS=1),
