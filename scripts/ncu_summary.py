@@ -25,12 +25,13 @@ UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 
 
 def bench_name(kname):
-    m = re.search(r"step_kernel<(float|double), (?:\(int\))?(\d), (?:\(int\))?(\d), (?:\(bool\))?(\d), (?:\(int\))?(\d)>", kname)
+    m = re.search(r"step_kernel<(float|double), (?:\(int\))?(\d), (?:\(int\))?(\d), (?:\(int\)|\(bool\))?(\d), (?:\(int\))?(\d)"
+                  r"(?:, (?:\(bool\))?(\d))?>", kname)
     if not m:
         return None
     t, g, mode, marr, axm = m.group(1), int(m.group(2)), int(m.group(3)), int(m.group(4)), int(m.group(5))
     mn = {0: "interior", 2: "full"}.get(mode) or {1: "pml-x", 2: "pml-y", 4: "pml-z"}.get(axm, "pml")
-    return "step_kernel<%s,%s,%s,%s>" % ("f32" if t == "float" else "f64", "HE"[g], mn, "marr" if marr else "mscalar")
+    return "step_kernel<%s,%s,%s,%s>" % ("f32" if t == "float" else "f64", "HE"[g], mn, ("mscalar", "marr", "muniform")[marr])
 
 
 def main():
