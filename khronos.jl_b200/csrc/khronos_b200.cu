@@ -265,6 +265,10 @@ struct Impl : Base {
   // fewer, no material loads) next to the remaining tiles of the class
   static constexpr int MBASE = 9, NTAB = 2 * MBASE, NSIDE = 12;
   bool split_uniform = true;
+  // sweep mode (KHR_SWEEP=1): one grid per time step with the interior + PML tiles of both half-steps
+  // in z-chunk-major order (sweep_kernel, step_kernels.cuh); needs the chain mode's counters
+  bool sweep = false;
+  Table sweep_tab;
   Table tab[2][2][NTAB];
   cudaStream_t side[NSIDE] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {};
@@ -338,6 +342,8 @@ struct Impl : Base {
     if (const char* e = getenv("KHR_ORDER")) launch_order = atoi(e);
     if (const char* e = getenv("KHR_CHAIN")) pdl = atoi(e) != 0;
     if (const char* e = getenv("KHR_SPLIT_UNIFORM")) split_uniform = atoi(e) != 0;
+    if (const char* e = getenv("KHR_SWEEP")) sweep = atoi(e) != 0;
+    if (sweep) { pdl = true; multi_stream = false; }
     if (pdl) multi_stream = false;
     CUDA_OK(cudaHostAlloc((void**)&h_err, sizeof(int), cudaHostAllocMapped));
     *h_err = 0;
@@ -724,6 +730,8 @@ struct Impl : Base {
     // the wrap kernels are plain launches between the chain kernels: keep stream semantics simple
     if (any_periodic() || in_pair || nonuniform) pdl = false;
     if (nonuniform) axis_spec = false;
+    if (!pdl || g.nranks > 1) sweep = false;
+    if (sweep) axis_spec = false;
     if (in_pair && g.nranks > 1) throw std::string("complex fields (Bloch boundaries) are single-GPU for now: nranks must be 1");
     if (in_pair && chi3) throw std::string("chi3 with complex fields is not supported (|E|^2 couples the real and imaginary parts)");
     // per-axis PML cell sets from both groups' profiles
@@ -952,21 +960,26 @@ struct Impl : Base {
         for (int m = 0; m < NTAB; ++m) f(tab[gq][ph][m], gq, ph, m);
   }
   void collect_profile() {
-    for_tables([&](Table& t, int, int, int) {
+    auto one = [&](Table& t) {
       for (size_t q = 0; q + 1 < t.ev_used; q += 2) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, t.ev[q], t.ev[q + 1]) == cudaSuccess) { t.total_ms += ms; t.nlaunch += 1; }
         else cudaGetLastError();
       }
       t.ev_used = 0;
-    });
+    };
+    for_tables([&](Table& t, int, int, int) { one(t); });
+    one(sweep_tab);
   }
   void set_profiling(int on) override {
     sync_all();
     collect_profile();
     profiling = on != 0;
     serial_prof = on == 3;   // mode 3: one stream, so that every kernel's event pair times it alone
-    if (on == 2 || on == 3) for_tables([&](Table& t, int, int, int) { t.total_ms = 0; t.nlaunch = 0; });
+    if (on == 2 || on == 3) {
+      for_tables([&](Table& t, int, int, int) { t.total_ms = 0; t.nlaunch = 0; });
+      sweep_tab.total_ms = 0; sweep_tab.nlaunch = 0;
+    }
   }
   int kernel_stat(int idx, khr_kernel_stat* out) override {
     sync_all();
@@ -989,6 +1002,20 @@ struct Impl : Base {
       }
       ++k;
     });
+    if (sweep && !sweep_tab.items.empty()) {
+      if (k == idx && out) {
+        memset(out, 0, sizeof(*out));
+        snprintf(out->name, sizeof(out->name), "sweep_kernel<%s,H+E,interior+pml,%s/%s>", sizeof(T) == 4 ? "f32" : "f64",
+                 m_arr[0][0] ? "marr" : "mscalar", m_arr[1][0] ? "marr" : "mscalar");
+        out->launches = sweep_tab.nlaunch;
+        out->total_ms = sweep_tab.total_ms;
+        out->cells_per_launch = sweep_tab.cells;
+        out->alg_bytes_per_launch = sweep_tab.alg_bytes;
+        out->ctas = (int64_t)sweep_tab.items.size();
+        out->uniform_ctas = sweep_tab.uniform_items;
+      }
+      ++k;
+    }
     return k;
   }
 
@@ -1219,6 +1246,33 @@ struct Impl : Base {
       t.uniform_items = 0;
       for (auto& it : t.items) t.uniform_items += (it.flags & 2) ? 1 : 0;
     });
+    if (sweep) {
+      // chunk-major: H tiles of chunk c (PML first: they are the longer ones), then its E tiles
+      sweep_tab = Table();
+      int sweep_lag = 0;
+      if (const char* e = getenv("KHR_SWEEP_LAG")) sweep_lag = std::max(0, atoi(e));
+      std::vector<std::pair<long long, WorkItem>> all;
+      for (int gq = 0; gq < 2; ++gq)
+        for (int m : {7, 0}) {
+          Table& t = tab[gq][1][m];
+          for (size_t q = 0; q < t.items.size(); ++q) {
+            WorkItem it = t.items[q];
+            it.flags |= (gq << 8) | ((m == 7 ? 1 : 0) << 9);
+            // E tiles of chunk c go `lag` chunks behind the H tiles (lag 0: right after H(c))
+            const long long key = ((((long long)it.chunk + (gq == 1 ? sweep_lag : 0)) * 2 + gq) * 2 + (m == 7 ? 0 : 1)) * (1ll << 32) + (long long)q;
+            all.push_back({key, it});
+          }
+          sweep_tab.cells += t.cells; sweep_tab.alg_bytes += t.alg_bytes; sweep_tab.uniform_items += t.uniform_items;
+        }
+      std::sort(all.begin(), all.end(), [](const std::pair<long long, WorkItem>& a, const std::pair<long long, WorkItem>& b) { return a.first < b.first; });
+      for (auto& kv : all) sweep_tab.items.push_back(kv.second);
+      if (!sweep_tab.items.empty()) {
+        size_t bytes = sweep_tab.items.size() * sizeof(WorkItem);
+        sweep_tab.d = (WorkItem*)dalloc((bytes + sizeof(T) - 1) / sizeof(T), false);
+        CUDA_OK(cudaMemcpyAsync(sweep_tab.d, sweep_tab.items.data(), bytes, cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+      }
+    }
   }
 
   // ---- stepping -------------------------------------------------------------
@@ -1495,6 +1549,64 @@ struct Impl : Base {
     CUDA_OK(cudaStreamWaitEvent(im->stream, ev_pair_b, 0));
   }
 
+  // one time step in sweep mode: [H tiles that need the full kernel] [sweep grid] [E tiles that need the
+  // full kernel], all on one stream with programmatic dependent launch; ordering by the chunk counters
+  template <int MH, int ME>
+  void launch_sweep(const StepParams<T>& ph, const StepParams<T>& pe) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)sweep_tab.items.size()); cfg.blockDim = dim3(CTA); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CUDA_OK(cudaLaunchKernelEx(&cfg, sweep_kernel<T, MH, ME>, ph, pe, (const WorkItem*)sweep_tab.d));
+    ++launches;
+  }
+  void timed(Table& t, bool begin) {
+    if (!profiling) return;
+    if (begin) {
+      if (t.ev_used + 2 > t.ev.size())
+        for (int q = 0; q < 2; ++q) { cudaEvent_t e; CUDA_OK(cudaEventCreate(&e)); t.ev.push_back(e); }
+      CUDA_OK(cudaEventRecord(t.ev[t.ev_used], stream));
+    } else {
+      CUDA_OK(cudaEventRecord(t.ev[t.ev_used + 1], stream));
+      t.ev_used += 2;
+    }
+  }
+  void sweep_step(double t, double th) {
+    StepParams<T> ph, pe;
+    fill_params(ph, 0, t);
+    epochs[0] += 1;
+    fill_params(pe, 1, th);
+    const bool mh = m_arr[0][0] != nullptr, me = m_arr[1][0] != nullptr;
+    if ((mh && (!m_arr[0][1] || !m_arr[0][2])) || (me && (!m_arr[1][1] || !m_arr[1][2])))
+      throw std::string("per-voxel material needs all three components");
+    Table& hf = tab[0][1][8];
+    if (!hf.items.empty()) {
+      ph.items = hf.d;
+      timed(hf, true);
+      launch_mode<0, 2, 7>(ph, mh ? 1 : 0, (int)hf.items.size(), stream);
+      timed(hf, false);
+    }
+    if (!sweep_tab.items.empty()) {
+      timed(sweep_tab, true);
+      if (mh && me) launch_sweep<1, 1>(ph, pe);
+      else if (mh) launch_sweep<1, 0>(ph, pe);
+      else if (me) launch_sweep<0, 1>(ph, pe);
+      else launch_sweep<0, 0>(ph, pe);
+      timed(sweep_tab, false);
+    }
+    Table& ef = tab[1][1][8];
+    if (!ef.items.empty()) {
+      pe.items = ef.d;
+      timed(ef, true);
+      launch_mode<1, 2, 7>(pe, me ? 1 : 0, (int)ef.items.size(), stream);
+      timed(ef, false);
+    }
+    CUDA_OK(cudaGetLastError());
+    for (auto& pl : poles) pl.cur = 1 - pl.cur;
+    epochs[1] += 1;
+  }
   void step_h() override {
     need_final();
     double t = time_now();
@@ -1558,10 +1670,17 @@ struct Impl : Base {
       double t = time_now();
       double th = t + (double)(dt / T(2));
       update_sources_active(t);
-      half_step_all(0, t);
-      dft_update(0, t);
-      half_step_all(1, th);
-      dft_update(1, th);
+      if (sweep) {
+        // the H fields are not touched by the E update, so their DFT may follow the whole step
+        sweep_step(t, th);
+        dft_update(0, t);
+        dft_update(1, th);
+      } else {
+        half_step_all(0, t);
+        dft_update(0, t);
+        half_step_all(1, th);
+        dft_update(1, th);
+      }
       timestep += 1;
       if (im) im->timestep = timestep;
     }

@@ -271,7 +271,7 @@ constexpr int min_ctas() {
 //   NU     : non-uniform grid — the curl uses inv(Δx[ix]), inv(Δy[iy]), inv(Δz[iz]) of the updated cell
 //            (get_inv_dx(Δ::AbstractVector, i), Helpers.jl:283-291) instead of three scalars
 template <class T, int GROUP, int MODE, int MARR, int AXM = 7, bool NU = false>
-__global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(const __grid_constant__ StepParams<T> p) {
+__device__ __forceinline__ void step_body(const StepParams<T>& p, const WorkItem& it_in) {
   constexpr int IC = (GROUP == 0) ? 1 : -1;
   constexpr bool GENERAL = MODE >= 1;   // PML cascade
   constexpr bool EXTRAS = MODE == 2;    // + sources, sigma_D/B, ADE poles
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(c
   // chain mode: the next kernel of the stream may start as soon as every CTA of this one is
   // resident; data dependencies are handled by the chunk counters below (no-op otherwise)
   asm volatile("griddepcontrol.launch_dependents;");
-  const WorkItem it = p.items[blockIdx.x];
+  const WorkItem it = it_in;
   const int lxl = it.lx_log2;
   const int LX = 1 << lxl;
   const int lane_x = threadIdx.x & (LX - 1);
@@ -772,6 +772,34 @@ __global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(c
       atomicAdd(p.done_mine + it.chunk, 1ull);
     }
   }
+}
+
+template <class T, int GROUP, int MODE, int MARR, int AXM = 7, bool NU = false>
+__global__ void __launch_bounds__(CTA, (min_ctas<T, MODE, AXM>())) step_kernel(const __grid_constant__ StepParams<T> p) {
+  step_body<T, GROUP, MODE, MARR, AXM, NU>(p, p.items[blockIdx.x]);
+}
+
+// ----------------------------------------------------------------------------
+// Sweep mode: ONE grid per time step holds the interior and PML tiles of BOTH half-steps in
+// z-chunk-major order — H(chunk 0), E(chunk 0), H(chunk 1), E(chunk 1), ... — so that the E tiles
+// of a chunk run right after its H tiles, while the H planes just written and the E planes just
+// read are still in the 126 MB L2: the E half-step then takes its curl operand and its own field
+// from L2 instead of HBM, and only one grid-wide drain per step remains.  Ordering is the chain
+// mode's: an E tile waits (device counters) for the H tiles of chunks c-1, c of this step, an H
+// tile for the E tiles of chunks c, c+1 of the previous step; every dependency points to a tile
+// with a lower block index or an earlier launch, so in-order block dispatch guarantees progress.
+// WorkItem::flags bit 8 = field group, bit 9 = PML tile.
+// ----------------------------------------------------------------------------
+template <class T, int MH, int ME>
+__global__ void __launch_bounds__(CTA, (min_ctas<T, 1, 7>())) sweep_kernel(const __grid_constant__ StepParams<T> ph,
+                                                                         const __grid_constant__ StepParams<T> pe,
+                                                                         const WorkItem* __restrict__ items) {
+  const WorkItem it = items[blockIdx.x];
+  const int sel = (it.flags >> 8) & 3;   // block-uniform
+  if (sel == 0) step_body<T, 0, 0, MH>(ph, it);
+  else if (sel == 2) step_body<T, 0, 1, MH>(ph, it);
+  else if (sel == 1) step_body<T, 1, 0, ME>(pe, it);
+  else step_body<T, 1, 1, ME>(pe, it);
 }
 
 // ----------------------------------------------------------------------------

@@ -64,6 +64,8 @@ def _run_gpu(nsteps, dtype=np.float32, **envkw):
 
 MODES = [
     dict(KHR_CHAIN=1),
+    dict(KHR_SWEEP=1),
+    dict(KHR_SWEEP=1, KHR_ZSEG=3),
     dict(KHR_CHAIN=1, KHR_ZSEG=3),
     dict(KHR_AXIS_SPEC=1),
     dict(KHR_AXIS_SPEC=1, KHR_CHAIN=1),
