@@ -1182,6 +1182,20 @@ struct Impl : Base {
       t.items.swap(out);
       t.cost.clear();
     });
+    // Zigzag (KHR_ZIGZAG=1, off): the H launches walk the z chunks upwards, the E launches downwards, so
+    // that a half-step starts on the planes the previous half-step touched last — still in the 126 MB
+    // L2 — instead of on the ones it touched first.  Only the order of the tiles inside the E tables
+    // changes (by chunk, descending; order inside a chunk kept).  Measured: no gain (waveguide 49.6 ->
+    // 49.2, sphere 61.5 -> 61.3 Gcells/s, profiles/r01_s4_ab_zigzag.txt).
+    {
+      int zigzag = 0;
+      if (const char* e = getenv("KHR_ZIGZAG")) zigzag = atoi(e);
+      if (zigzag && !pdl)
+        for_tables([&](Table& t, int gq, int, int) {
+          if (gq != 1 || t.items.size() < 2) return;
+          std::stable_sort(t.items.begin(), t.items.end(), [](const WorkItem& a, const WorkItem& b) { return a.chunk > b.chunk; });
+        });
+    }
     // items per (group, z chunk) after any splitting: the targets of the dependency counters
     for (int gq = 0; gq < 2; ++gq) std::fill(chunk_cnt[gq].begin(), chunk_cnt[gq].end(), 0ull);
     for_tables([&](Table& t, int gq, int, int) {

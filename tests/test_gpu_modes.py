@@ -70,6 +70,7 @@ MODES = [
     dict(KHR_AXIS_SPEC=1),
     dict(KHR_AXIS_SPEC=1, KHR_CHAIN=1),
     dict(KHR_UNIFORM_TILES=0),
+    dict(KHR_ZIGZAG=1),
     dict(KHR_SPLIT_UNIFORM=0),
     dict(KHR_SPLIT_UNIFORM=0, KHR_AXIS_SPEC=1),
     dict(KHR_MULTI_STREAM=0),
