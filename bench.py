@@ -277,6 +277,11 @@ def main_ours(args):
                 roof["traffic"] = json.load(open(tfile)).get(dom["name"])
             except Exception:
                 pass
+        if roof["traffic"]:
+            # the same launch against the DRAM bytes ncu counted for it (the kernels eliminate B/D and
+            # skip constant-material loads, so they move less than the reference's algorithmic count)
+            roof["traffic_achieved"] = roof["traffic"] / (avg_ms * 1e-3) / 1e9
+            roof["traffic_frac"] = roof["traffic_achieved"] / peak
     cpu = None
     if n_gpus == 1 and not args.no_cpu:
         _, cpu, _, _ = cpu_run(args.workload, 6, 1, budget_s=15.0)

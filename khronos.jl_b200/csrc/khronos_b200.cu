@@ -2054,7 +2054,7 @@ struct khr_ctx {
 extern "C" {
 
 const char* khr_last_error(void) { return khr::g_err.c_str(); }
-int32_t khr_version(void) { return 100; }
+int32_t khr_version(void) { return 110; }
 
 int32_t khr_ctx_create(int32_t device, const khr_grid_desc* grid, khr_ctx** out) {
   if (!grid || !out) return khr::fail("null argument");
