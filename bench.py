@@ -274,7 +274,13 @@ def main_ours(args):
         tfile = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
         if os.path.exists(tfile):
             try:
-                roof["traffic"] = json.load(open(tfile)).get(dom["name"])
+                tj = json.load(open(tfile))
+                roof["traffic"] = tj.get(dom["name"])
+                if roof["traffic"] is None and dom["name"].endswith(",muniform>"):
+                    # capture taken before the constant-material PML tiles got their own table: same tiles
+                    # (all but a handful), same loads skipped, launched then as part of the ",marr>" table
+                    roof["traffic"] = tj.get(dom["name"].replace(",muniform>", ",marr>"))
+                    roof["traffic_note"] = "ncu capture of the same tiles inside the former <...,marr> launch"
             except Exception:
                 pass
         if roof["traffic"]:

@@ -370,6 +370,15 @@ struct Impl : Base {
     if (h_err) cudaFreeHost(h_err);
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     cudaEventDestroy(ev_boundary); cudaEventDestroy(ev_comm); cudaEventDestroy(ev_t0); cudaEventDestroy(ev_t1);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_pair_a) cudaEventDestroy(ev_pair_a);
+    if (ev_pair_b) cudaEventDestroy(ev_pair_b);
+    for (int q = 0; q < NSIDE; ++q) {
+      if (ev_join[q]) cudaEventDestroy(ev_join[q]);
+      if (side[q]) cudaStreamDestroy(side[q]);
+    }
+    for_tables([&](Table& t, int, int, int) { for (cudaEvent_t e : t.ev) cudaEventDestroy(e); t.ev.clear(); });
+    for (cudaEvent_t e : sweep_tab.ev) cudaEventDestroy(e);
     cudaStreamDestroy(stream); cudaStreamDestroy(comm_stream);
   }
 
