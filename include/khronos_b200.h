@@ -222,6 +222,17 @@ int32_t khr_near2far(khr_ctx* ctx, const int32_t monitor_ids[4], int32_t normal_
 int32_t khr_mode_overlap(khr_ctx* ctx, const int32_t monitor_ids[4], int32_t normal_axis, const double* mode_fields, int32_t n1,
                          int32_t n2, int32_t nfreq, double* out5);
 
+/* DiffractionMonitor.jl:87-165 get_diffraction_efficiencies: Poynting power of the diffraction
+ * orders |m|, |n| <= max_order per frequency from the spatial DFT of the four tangential DFT
+ * monitors of a plane (ids ordered E1, E2, H1, H2).  Only the (2 max_order + 1)^2 needed bins are
+ * formed (the reference computes the full O(N^2) transform, fft2_manual :185-197).  L1, L2 =
+ * md.cell_size along the two tangential axes, kinc1/2 = the tangential components of k_inc.
+ * power / propagating: [nfreq][2M+1][2M+1] (n fastest, m = -M..M); evanescent orders, which the
+ * reference skips, have propagating = 0 and power = 0.  The common tangential extent of the four
+ * monitors is transformed (the reference mixes per-field extents, :126-140). */
+int32_t khr_diffraction(khr_ctx* ctx, const int32_t monitor_ids[4], int32_t normal_axis, int32_t max_order, double L1, double L2,
+                        double kinc1, double kinc2, const double* freqs, int32_t nfreq, double* power, int32_t* propagating);
+
 int32_t khr_sync(khr_ctx* ctx);
 int32_t khr_get_stream(khr_ctx* ctx, void** cuda_stream);
 

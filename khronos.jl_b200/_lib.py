@@ -87,6 +87,8 @@ _SIGNATURES = {
     "khr_near2far": (_I, [_P, C.POINTER(_I), _I, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double),
                           C.POINTER(C.c_double), _I, C.POINTER(C.c_double), _I, C.POINTER(C.c_double)]),
     "khr_mode_overlap": (_I, [_P, C.POINTER(_I), _I, C.POINTER(C.c_double), _I, _I, _I, C.POINTER(C.c_double)]),
+    "khr_diffraction": (_I, [_P, C.POINTER(_I), _I, _I, C.c_double, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double), _I,
+                             C.POINTER(C.c_double), C.POINTER(_I)]),
     "khr_step": (_I, [_P, _I]),
     "khr_step_h": (_I, [_P]),
     "khr_step_e": (_I, [_P]),

@@ -117,6 +117,8 @@ struct Base {
   virtual void near2far(const int32_t* ids4, int normal_axis, double normal_sign, double eps, double mu, const double* base12,
                         const double* freqs, int nfreq, const double* obs, int nobs, double* out) = 0;
   virtual void mode_overlap(const int32_t* ids4, int normal_axis, const double* mode, int n1, int n2, int nfreq, double* out5) = 0;
+  virtual void diffraction(const int32_t* ids4, int normal_axis, int max_order, double L1, double L2, double kinc1, double kinc2,
+                           const double* freqs, int nfreq, double* power, int32_t* propagating) = 0;
   virtual void sync() = 0;
   virtual void census(int64_t* c) = 0;
   virtual void set_profiling(int on) = 0;
@@ -1985,6 +1987,31 @@ struct Impl : Base {
     CUDA_OK(cudaMemcpyAsync(out5, d_out, sizeof(double) * 5 * nfreq, cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
   }
+  // DiffractionMonitor.jl:87-165: power of the diffraction orders |m|, |n| <= max_order per frequency
+  void diffraction(const int32_t* ids4, int normal_axis, int max_order, double L1, double L2, double kinc1, double kinc2,
+                   const double* freqs, int nfreq, double* power, int32_t* propagating) override {
+    DiffArgs<T> a;
+    a.s = surface_args("khr_diffraction", ids4, normal_axis, nfreq);
+    if (max_order < 0 || max_order > 64) throw std::string("khr_diffraction: max_order must be 0..64");
+    if (!(L1 > 0) || !(L2 > 0)) throw std::string("khr_diffraction: cell sizes must be positive");
+    if (nfreq > 65535) throw std::string("khr_diffraction: too many frequencies");
+    const int nord = 2 * max_order + 1;
+    const size_t nout = (size_t)nfreq * nord * nord;
+    if (a.s.n1 < 1 || a.s.n2 < 1) { for (size_t k = 0; k < nout; ++k) { power[k] = 0.0; propagating[k] = 0; } return; }
+    a.max_order = max_order; a.L1 = L1; a.L2 = L2; a.kinc1 = kinc1; a.kinc2 = kinc2;
+    double* buf = scratch_f64(nout + nout / 2 + 2 + (size_t)nfreq);
+    double* d_out = buf;
+    int* d_prop = (int*)(d_out + nout);
+    double* d_fr = d_out + nout + nout / 2 + 2;
+    CUDA_OK(cudaMemcpyAsync(d_fr, freqs, sizeof(double) * nfreq, cudaMemcpyHostToDevice, stream));
+    a.freqs = d_fr;
+    diffraction_kernel<T><<<dim3((unsigned)(nord * nord), (unsigned)nfreq), 256, 0, stream>>>(a, d_out, d_prop);
+    CUDA_OK(cudaGetLastError());
+    launches += 1;
+    CUDA_OK(cudaMemcpyAsync(power, d_out, sizeof(double) * nout, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaMemcpyAsync(propagating, d_prop, sizeof(int) * nout, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+  }
   double* d_norm = nullptr;
   double monitor_norm(int id) override {
     if (id < 0 || id >= (int)monitors.size()) throw std::string("bad monitor id");
@@ -2284,6 +2311,12 @@ int32_t khr_mode_overlap(khr_ctx* ctx, const int32_t monitor_ids[4], int32_t nor
   NEED_CTX
   if (!monitor_ids || !mode_fields || !out5 || nfreq < 1) return khr::fail("bad argument");
   KHR_TRY(ctx->impl->mode_overlap(monitor_ids, normal_axis, mode_fields, n1, n2, nfreq, out5))
+}
+int32_t khr_diffraction(khr_ctx* ctx, const int32_t monitor_ids[4], int32_t normal_axis, int32_t max_order, double L1, double L2,
+                        double kinc1, double kinc2, const double* freqs, int32_t nfreq, double* power, int32_t* propagating) {
+  NEED_CTX
+  if (!monitor_ids || !freqs || !power || !propagating || nfreq < 1) return khr::fail("bad argument");
+  KHR_TRY(ctx->impl->diffraction(monitor_ids, normal_axis, max_order, L1, L2, kinc1, kinc2, freqs, nfreq, power, propagating))
 }
 int32_t khr_sync(khr_ctx* ctx) {
   NEED_CTX

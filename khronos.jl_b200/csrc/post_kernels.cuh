@@ -210,4 +210,63 @@ __global__ void mode_overlap_finish_kernel(const double* __restrict__ partial, i
   out[t] = s;
 }
 
+// ----------------------------------------------------------------------------
+// Diffraction orders (DiffractionMonitor.jl:87-165 get_diffraction_efficiencies): the reference forms
+// the full O(N^2) spatial DFT of the four tangential fields (fft2_manual, :185-197) and then reads
+// (2 M + 1)^2 of its bins; here one CTA computes one needed bin (order (m, n), frequency) of all
+// four fields directly:  X[k1, k2] = sum_j x[j1, j2] exp(-2 pi i (k1 j1 / n1 + k2 j2 / n2)),
+// accumulated in ComplexF64 and rounded to Complex{T} like the reference's result array, then
+//   power = real(Et1 conj(Ht2) - Et2 conj(Ht1)) / (n1 n2)^2   for propagating orders
+// (k0^2 - kx^2 - ky^2 > 0), 0 otherwise.  out: [nf][2M+1][2M+1] (n fastest); prop: same shape, 1 = propagating.
+// ----------------------------------------------------------------------------
+template <class T>
+struct DiffArgs {
+  FluxArgs<T> s;
+  int max_order;
+  double L1, L2, kinc1, kinc2;
+  const double* freqs;
+};
+
+template <class T>
+__global__ void __launch_bounds__(256) diffraction_kernel(const __grid_constant__ DiffArgs<T> a, double* __restrict__ out,
+                                                          int* __restrict__ prop) {
+  const int nord = 2 * a.max_order + 1;
+  const int m = (int)(blockIdx.x / nord) - a.max_order, n = (int)(blockIdx.x % nord) - a.max_order;
+  const int kf = blockIdx.y;
+  const int n1 = a.s.n1, n2 = a.s.n2;
+  const int k1 = ((m % n1) + n1) % n1, k2 = ((n % n2) + n2) % n2;    // mod(m, n1), mod(n, n2)
+  const size_t o = ((size_t)kf * nord + (size_t)(m + a.max_order)) * nord + (size_t)(n + a.max_order);
+  const double k0 = 6.283185307179586 * a.freqs[kf];
+  const double kx = a.kinc1 + 6.283185307179586 * m / a.L1, ky = a.kinc2 + 6.283185307179586 * n / a.L2;
+  const double kz_sq = k0 * k0 - kx * kx - ky * ky;
+  if (kz_sq <= 0) {   // evanescent order: skipped by the reference (block-uniform)
+    if (threadIdx.x == 0) { out[o] = 0.0; prop[o] = 0; }
+    return;
+  }
+  double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long ncell = (long long)n1 * n2;
+  for (long long q = threadIdx.x; q < ncell; q += blockDim.x) {
+    const int j1 = (int)(q % n1), j2 = (int)(q / n1);
+    const double phase = -6.283185307179586 * ((double)k1 * j1 / n1 + (double)k2 * j2 / n2);
+    double sn, cs;
+    sincos(phase, &sn, &cs);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      T re, im;
+      flux_val(a.s, c, j1, j2, kf, re, im);
+      const cplx p = cmul(cplx{(double)re, (double)im}, cplx{cs, sn});
+      v[2 * c] += p.re; v[2 * c + 1] += p.im;
+    }
+  }
+  block_sum<8>(v);
+  if (threadIdx.x == 0) {
+    const double nf = 1.0 / ((double)n1 * n2);
+    cplx f[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) f[c] = cplx{(double)(T)v[2 * c] * nf, (double)(T)v[2 * c + 1] * nf};   // Complex{T} bin, * norm_factor
+    out[o] = csub(cmul(f[0], cconj(f[3])), cmul(f[1], cconj(f[2]))).re;
+    prop[o] = 1;
+  }
+}
+
 }  // namespace khr

@@ -252,6 +252,11 @@ class Near2FarMonitor(FluxMonitor):
         self.medium_eps, self.medium_mu = float(medium_eps), float(medium_mu)
 
 
+class DiffractionMonitor(FluxMonitor):
+    """DiffractionMonitor (init_diffraction_monitor, DiffractionMonitor.jl:18-80): four tangential DFT
+    monitors on a plane, decomposed into diffraction orders afterwards."""
+
+
 class ModeMonitor(FluxMonitor):
     """ModeMonitor (DataStructures.jl:512-519): four tangential DFT monitors on a plane; the mode
     profiles themselves come from the caller (the mode solver is outside the hot path)."""
@@ -956,6 +961,28 @@ class Simulation:
                 power[it, ip] = 0.5 * (abs(e_th) ** 2 + abs(e_ph) ** 2) / Z
                 idx += 1
         return power
+
+    def get_diffraction_efficiencies(self, fm, max_order=5, k_inc=(0.0, 0.0, 0.0)):
+        """DiffractionMonitor.jl:87-165: {(m, n): power per frequency} for the orders that propagate at
+        some frequency (evanescent entries stay 0, as in the reference), evaluated on the device."""
+        t1, t2 = fm.tangential
+        nf, nord = len(fm.frequencies), 2 * int(max_order) + 1
+        ids = (C.c_int32 * 4)(*[m.id for m in fm.monitors])
+        freqs = np.asarray([float(f) for f in fm.frequencies], dtype=np.float64)
+        power = np.zeros(nf * nord * nord, dtype=np.float64)
+        prop = np.zeros(nf * nord * nord, dtype=np.int32)
+        L = [float(v) for v in self.grid.cell_size]
+        _lib.check(_lib.lib().khr_diffraction(self.ctx, ids, fm.normal, int(max_order), L[t1], L[t2], float(k_inc[t1]),
+                                              float(k_inc[t2]), freqs.ctypes.data_as(C.POINTER(C.c_double)), nf,
+                                              power.ctypes.data_as(C.POINTER(C.c_double)),
+                                              prop.ctypes.data_as(C.POINTER(C.c_int32))))
+        power, prop = power.reshape(nf, nord, nord), prop.reshape(nf, nord, nord)
+        out = {}
+        for im in range(nord):
+            for i_n in range(nord):
+                if prop[:, im, i_n].any():
+                    out[(im - max_order, i_n - max_order)] = power[:, im, i_n].copy()
+        return out
 
     def compute_mode_amplitudes(self, fm, mode_fields):
         """ModeMonitor.jl:345-515 compute_mode_amplitudes with the surface sums on the device

@@ -1906,3 +1906,49 @@ void ko_rasterize(void* hv, int nobj, const double* objs, int kinds_mask, int sm
 }
 
 }  // extern "C"
+
+// get_diffraction_efficiencies (src/Monitors/DiffractionMonitor.jl:87-165) with fft2_manual (:185-197)
+// evaluated only at the bins that are read.  The common tangential extent of the four monitors is
+// transformed.  power / prop: [nf][2M+1][2M+1] (n fastest); evanescent orders: prop 0, power 0.
+template <class SimT>
+static void diffraction_impl(const SimT& S, int normal_axis, const int* ids4, int max_order, double L1, double L2, double kinc1,
+                             double kinc2, const double* freqs, double* power, int* prop) {
+  using T = std::remove_const_t<std::remove_reference_t<decltype(S.dt)>>;
+  const double pi = 3.141592653589793;
+  Surface<SimT> sf(S, ids4, normal_axis);
+  const int n1 = sf.n1, n2 = sf.n2, nord = 2 * max_order + 1;
+  for (int kf = 0; kf < sf.nf; ++kf) {
+    const double k0 = 2 * pi * freqs[kf];
+    const double norm_factor = 1.0 / ((double)n1 * n2);
+#pragma omp parallel for collapse(2) schedule(dynamic)
+    for (int m = -max_order; m <= max_order; ++m)
+      for (int n = -max_order; n <= max_order; ++n) {
+        const size_t o = ((size_t)kf * nord + (size_t)(m + max_order)) * nord + (size_t)(n + max_order);
+        const int k1 = ((m % n1) + n1) % n1, k2 = ((n % n2) + n2) % n2;
+        const double kx_m = kinc1 + 2 * pi * m / L1, ky_n = kinc2 + 2 * pi * n / L2;
+        const double kz_sq = k0 * k0 - kx_m * kx_m - ky_n * ky_n;
+        if (kz_sq <= 0) { power[o] = 0.0; prop[o] = 0; continue; }
+        cd bin[4];
+        for (int c = 0; c < 4; ++c) {
+          cd s(0, 0);
+          for (int j2 = 0; j2 < n2; ++j2)
+            for (int j1 = 0; j1 < n1; ++j1) {
+              double phase = -2 * pi * ((double)(k1 * j1) / n1 + (double)(k2 * j2) / n2);
+              s += sf.val(c, j1, j2, kf) * std::exp(cd(0.0, 1.0) * phase);
+            }
+          // result array is Complex{real(T)}; then * norm_factor in ComplexF64
+          bin[c] = cd((double)(T)s.real(), (double)(T)s.imag()) * norm_factor;
+        }
+        power[o] = std::real(bin[0] * std::conj(bin[3]) - bin[1] * std::conj(bin[2]));
+        prop[o] = 1;
+      }
+  }
+}
+
+extern "C" {
+void ko_diffraction(void* hv, int normal_axis, const int* ids4, int max_order, double L1, double L2, double kinc1, double kinc2,
+                    const double* freqs, double* power, int* prop) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, diffraction_impl(S, normal_axis, ids4, max_order, L1, L2, kinc1, kinc2, freqs, power, prop));
+}
+}  // extern "C"

@@ -85,6 +85,7 @@ def lib():
         L.ko_flux.argtypes = [C.c_void_p, C.c_int, ip, dp]
         L.ko_near2far.argtypes = [C.c_void_p, C.c_int, ip, C.c_double, C.c_double, C.c_double, dp, dp, dp, C.c_int, dp]
         L.ko_mode_amplitudes.argtypes = [C.c_void_p, C.c_int, ip, dp, dp, dp, dp]
+        L.ko_diffraction.argtypes = [C.c_void_p, C.c_int, ip, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp, ip]
         _LIB = L
     return _LIB
 
@@ -384,3 +385,14 @@ class OracleSim:
         cnt = (C.c_long * 3)()
         self.L.ko_rasterize(self.h, o.shape[0], op, int(kinds_mask), int(smoothing), cnt)
         return list(cnt)
+
+    def diffraction(self, normal_axis, ids4, max_order, L1, L2, freqs, kinc1=0.0, kinc2=0.0):
+        """get_diffraction_efficiencies (DiffractionMonitor.jl:87-165): (power, propagating), each (nf, 2M+1, 2M+1)."""
+        i4, ip = _i(ids4)
+        f, fp = _d(freqs)
+        nord = 2 * int(max_order) + 1
+        power = np.zeros(len(f) * nord * nord)
+        prop = np.zeros(len(f) * nord * nord, dtype=np.int32)
+        self.L.ko_diffraction(self.h, int(normal_axis), ip, int(max_order), float(L1), float(L2), float(kinc1), float(kinc2), fp,
+                              power.ctypes.data_as(C.POINTER(C.c_double)), prop.ctypes.data_as(C.POINTER(C.c_int)))
+        return power.reshape(len(f), nord, nord), prop.reshape(len(f), nord, nord)

@@ -133,3 +133,21 @@ def test_mode_overlap_matches_oracle(normal, dtype):
     assert np.allclose(ap1.real, 1.0, atol=1e-5 if dtype is np.float32 else 1e-12), ap1
     with pytest.raises(kb.KhronosError):
         p.k.compute_mode_amplitudes(fm, mode[:, :-1])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_diffraction_orders_match_oracle(dtype):
+    """khr_diffraction (DiffractionMonitor.jl:87-165) on a binary grating with periodic x/y: same
+    propagating set and the same order powers as the oracle's restatement."""
+    from test_post_oracle import _grating
+    p, fm = _grating(dtype, build_gpu=True)
+    p.step(500)
+    got = p.k.get_diffraction_efficiencies(fm, max_order=3)
+    power, prop = p.o.diffraction(2, p.omon, 3, float(p.grid.cell_size[0]), float(p.grid.cell_size[1]),
+                                  [float(f) for f in fm.frequencies])
+    want = {(m - 3, n - 3): power[:, m, n] for m in range(7) for n in range(7) if prop[:, m, n].any()}
+    assert set(got) == set(want) and len(got) == 5
+    scale = max(np.abs(v).max() for v in want.values())
+    tol = 2e-5 if dtype is np.float32 else 1e-11
+    for k in want:
+        assert np.max(np.abs(got[k] - want[k])) < tol * scale, (k, got[k], want[k])

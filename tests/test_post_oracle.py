@@ -104,3 +104,42 @@ def test_oracle_kerr_correction():
     e_lin = np.array([D[c][i] for c in range(3)])     # vacuum, no sources at this voxel: E_lin = D
     want = e_lin / (1.0 + 5.0 * ((e_lin[0] * e_lin[0] + e_lin[1] * e_lin[1]) + e_lin[2] * e_lin[2]))
     assert np.allclose([E[c][i] for c in range(3)], want, rtol=1e-14, atol=0)
+
+
+def _grating(dtype=np.float64, build_gpu=False):
+    """Binary grating, period 1.6 along x (the cell), uniform along y, PML in z; Ey/Ex sheet source below,
+    diffraction plane above."""
+    bc = [[kb.Periodic(), kb.Periodic()], [kb.Periodic(), kb.Periodic()], [kb.PML(), kb.PML()]]
+    geom = [kb.Object(kb.Cuboid([0.2, 0, -0.2], [0.7, 50.0, 0.4]), kb.Material(epsilon=4.0)),
+            kb.Object(kb.Cuboid([0, 0, -0.9], [50.0, 50.0, 1.0]), kb.Material(epsilon=2.25))]
+    fm = kb.DiffractionMonitor([0, 0, 0.9], [1.6, 0.4, 0], [1.0, 1.5])
+    mons = [(m.component, m.center, m.size, m.frequencies, 1) for m in fm.monitors]
+    p = Pair([1.6, 0.4, 3.2], 20, [0.0, 0.0, 0.6], dtype, geometry=geom, boundary_conditions=bc, build_gpu=build_gpu,
+             sources=[(kb.EY, [0, 0, -0.7], [5.0, 5.0, 0], CW), (kb.EX, [0, 0, -0.7], [5.0, 5.0, 0], kb.ContinuousWaveSource(1.5))],
+             monitors=mons)
+    fm.monitors = p.kmon
+    return p, fm
+
+
+def test_oracle_diffraction_orders():
+    """Propagating orders only (|m| <= L f), none along the uniform y axis, and Parseval: the bins of
+    the spatial DFT add up to the plane's mean Poynting flux, so the propagating orders carry the flux
+    recorded 0.9 um above the grating up to the evanescent tail."""
+    p, fm = _grating()
+    p.o.step(700)
+    power, prop = p.o.diffraction(2, p.omon, 3, 1.6, 0.4, fm.frequencies)
+    assert prop.shape == (2, 7, 7)
+    for kf, f in enumerate(fm.frequencies):
+        for m in range(-3, 4):
+            for n in range(-3, 4):
+                want = (2 * np.pi * f) ** 2 - (2 * np.pi * m / 1.6) ** 2 - (2 * np.pi * n / 0.4) ** 2 > 0
+                assert bool(prop[kf, m + 3, n + 3]) == want
+        assert prop[kf, :, 3].sum() == (3 if f == 1.0 else 5)        # m = -1..1 at f = 1, -2..2 at f = 1.5
+    flux = p.o.flux(2, p.omon)
+    n1 = min(a.shape[0] for a in (p.o.get_dft(i) for i in p.omon))
+    n2 = min(a.shape[1] for a in (p.o.get_dft(i) for i in p.omon))
+    dA = p.grid.dl[0] * p.grid.dl[1]
+    for kf in range(2):
+        tot = power[kf].sum()
+        assert tot > 0 and abs(tot - flux[kf] / (n1 * n2 * float(dA))) < 2e-2 * abs(tot), (tot, flux[kf] / (n1 * n2 * float(dA)))
+    assert power[1, 3 + 1, 3] > 1e-3 * power[1, 3, 3]               # the grating really diffracts
