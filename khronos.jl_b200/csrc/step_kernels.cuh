@@ -414,10 +414,10 @@ __device__ __forceinline__ void step_body(const StepParams<T>& p, const WorkItem
       pf_l2(Ax + cb); pf_l2(Ay + cb);
       prefetch_plane(it.z0);
     }
-    if (threadIdx.x == 0) {
-      const int c_lo = it.chunk + (GROUP == 0 ? 0 : -1), c_hi = it.chunk + (GROUP == 0 ? 1 : 0);
-      for (int c = c_lo; c <= c_hi; ++c) {
-        if (c < 0 || c >= p.nchunk) continue;
+    if (threadIdx.x < 2) {
+      // the two chunk counters are polled by two lanes at once (one L2 round trip instead of two)
+      const int c = it.chunk + (GROUP == 0 ? 0 : -1) + (int)threadIdx.x;
+      if (c >= 0 && c < p.nchunk) {
         const unsigned long long target = p.epoch_other * p.cnt_other[c];
         unsigned spins = 0;
         while (ld_acquire_u64(p.done_other + c) < target) {
