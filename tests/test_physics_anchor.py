@@ -26,7 +26,7 @@ N_SLAB, THICK = 2.0, 0.5
 FREQS = np.linspace(1.0 / 1.5, 1.0 / 0.6, 21)
 
 
-def _build(with_slab, dtype, res=40, smoothing="staircase-aligned"):
+def _build(with_slab, dtype, res=40, smoothing="staircase-aligned", material=None):
     cell_xy, buffer, pml = 0.1, 1.5, 1.0
     cell_z = THICK + 2 * buffer + 2 * pml
     fwidth = 2 * np.pi * 0.5 * (1.0 / 0.6 - 1.0 / 1.5)
@@ -44,7 +44,7 @@ def _build(with_slab, dtype, res=40, smoothing="staircase-aligned"):
     # is shifted by half a cell so that its faces fall between two Ex nodes and exactly
     # THICK * res nodes carry eps, i.e. the rasterised slab is THICK thick.
     geom = [kb.Object(kb.Cuboid([0, 0, 0.5 / res], [cell_xy + 1.0, cell_xy + 1.0, THICK]),
-                      kb.Material(epsilon=N_SLAB ** 2))]
+                      material or kb.Material(epsilon=N_SLAB ** 2))]
     kw = {}
     if smoothing != "staircase-aligned":
         # the slab where the example puts it (faces exactly on Ex nodes: the point sampler makes it one
@@ -69,8 +69,8 @@ T_ANALYTIC = np.array([_fresnel_slab_transmission(f) for f in FREQS])
 NSTEPS = 4800  # t = 60: the pulse (cutoff 1.6) and its slab echoes (|r|^2 = 1/9 per bounce) have left
 
 
-def _oracle_flux(with_slab, dtype, smoothing="staircase-aligned"):
-    sim, fm = _build(with_slab, dtype, smoothing=smoothing)
+def _oracle_flux(with_slab, dtype, smoothing="staircase-aligned", material=None):
+    sim, fm = _build(with_slab, dtype, smoothing=smoothing, material=material)
     o, mids = oracle_from_simulation(sim)
     o.step(NSTEPS)
     return o.flux(fm.normal, mids)
@@ -86,6 +86,56 @@ def test_oracle_slab_transmission_matches_fresnel(dtype):
     assert err < 0.06, err
 
 
+def _slab_T(freq, eps):
+    """Transmission of a slab of (complex) permittivity eps, time convention exp(-i w t)."""
+    n = np.sqrt(np.asarray(eps, dtype=complex))
+    n = np.where(n.imag < 0, -n, n)
+    r12, t12, t21 = (1 - n) / (1 + n), 2 / (1 + n), 2 * n / (1 + n)
+    ph = n * 2 * np.pi * freq * THICK
+    return np.abs(t12 * t21 * np.exp(1j * ph) / (1 - r12 * r12 * np.exp(2j * ph))) ** 2
+
+
+# The ADE update of the reference (Susceptibility.jl:60-85, Dispersive.jl:25-88) is, in the continuum,
+#   Lorentz: P'' + G P' + W0^2 P = W0^2 sigma E,  W0 = 2 pi omega_0, G = 2 pi gamma
+#   Drude:   P'' + G P' = G sigma E
+# i.e. chi(f) = sigma f0^2 / (f0^2 - f^2 - i f gamma) and chi(w) = G sigma / (-w^2 - i w G).
+DISPERSIVE = {
+    "lorentz": (kb.Material(epsilon=2.0, susceptibilities=[kb.LorentzianSusceptibility(1.2, 0.2, 1.5)]),
+                2.0 + 1.5 * 1.2 ** 2 / (1.2 ** 2 - FREQS ** 2 - 1j * FREQS * 0.2)),
+    "drude": (kb.Material(epsilon=1.5, susceptibilities=[kb.DrudeSusceptibility(0.5, 3.0)]),
+              1.5 + (2 * np.pi * 0.5) * 3.0 / (-(2 * np.pi * FREQS) ** 2 - 1j * (2 * np.pi * FREQS) * (2 * np.pi * 0.5))),
+}
+
+
+@pytest.mark.parametrize("kind", ["lorentz", "drude"])
+def test_oracle_dispersive_slab_matches_analytic(kind):
+    """Pins the ADE restatement (coefficients, E-then-P ordering, the chi1 correction folded into
+    eps^-1, Geometry.jl:1236-1353) against closed-form physics: transmission of a Lorentz slab
+    through its resonance (absorption band T ~ 0 included) and of a Drude slab."""
+    mat, eps = DISPERSIVE[kind]
+    T = _oracle_flux(True, np.float64, material=mat) / _oracle_flux(False, np.float64)
+    err = np.max(np.abs(T - _slab_T(FREQS, eps)))
+    assert err < 0.015, (kind, err)      # measured: Lorentz 0.006, Drude 0.002
+
+
+def test_oracle_conductive_slab_matches_analytic():
+    """Pins the material-conductivity stages (Helpers.jl:141-154, 273-279: D <- ((1 - s) D + K) / (1 + s),
+    s = dt sigma_D / 2, i.e. dD/dt + sigma_D D = curl H): a slab with eps_eff = eps (1 + i sigma_D / w),
+    and one with mu_eff = mu (1 + i sigma_B / w), against the closed-form slab transmission."""
+    w = 2 * np.pi * FREQS
+    empty = _oracle_flux(False, np.float64)
+    for sd in (0.5, 2.0):
+        T = _oracle_flux(True, np.float64, material=kb.Material(epsilon=2.5, sigma_D=sd)) / empty
+        assert np.max(np.abs(T - _slab_T(FREQS, 2.5 * (1 + 1j * sd / w)))) < 0.02, sd      # measured 0.009 / 0.006
+    T = _oracle_flux(True, np.float64, material=kb.Material(epsilon=2.5, mu=1.5, sigma_B=0.7)) / empty
+    eps, mu = 2.5, 1.5 * (1 + 1j * 0.7 / w)
+    n, Z = np.sqrt(eps * mu + 0j), np.sqrt(mu / eps)
+    r12, t12, t21, ph = (Z - 1) / (Z + 1), 2 * Z / (Z + 1), 2 / (Z + 1), n * w * THICK
+    Ta = np.abs(t12 * t21 * np.exp(1j * ph) / (1 - r12 * r12 * np.exp(2j * ph))) ** 2
+    # (the H nodes sit half a cell off the Ex nodes the slab was aligned to: a looser mark)
+    assert np.max(np.abs(T - Ta)) < 0.03                                                    # measured 0.017
+
+
 def test_oracle_subpixel_smoothing_restores_the_slab():
     """With the slab faces on grid nodes the staircased raster is one cell too thick (max error 0.22);
     the reference's VolumeAveraging smoothing (Geometry.jl:795-972, restated in the oracle) brings the
@@ -95,6 +145,23 @@ def test_oracle_subpixel_smoothing_restores_the_slab():
     empty = _oracle_flux(False, np.float64)
     err = {m: np.max(np.abs(_oracle_flux(True, np.float64, smoothing=m) / empty - T_ANALYTIC)) for m in (None, "volume", "anisotropic")}
     assert err[None] > 0.15 and err["volume"] < 0.04 and err["anisotropic"] < 0.09, err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["lorentz", "drude"])
+def test_gpu_dispersive_slab_matches_analytic_and_oracle(kind):
+    mat, eps = DISPERSIVE[kind]
+    flux = []
+    for with_slab in (False, True):
+        sim, fm = _build(with_slab, np.float64, material=mat)
+        sim.prepare_simulation()
+        sim.step(NSTEPS)
+        flux.append(sim.get_flux(fm))
+        sim.close()
+    T = flux[1] / flux[0]
+    assert np.max(np.abs(T - _slab_T(FREQS, eps))) < 0.015
+    T_oracle = _oracle_flux(True, np.float64, material=mat) / _oracle_flux(False, np.float64)
+    assert np.max(np.abs(T - T_oracle)) < 1e-9
 
 
 @pytest.mark.gpu
