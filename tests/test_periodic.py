@@ -200,3 +200,32 @@ def test_gpu_complex_field_restrictions():
     with pytest.raises(kb.KhronosError, match="chi3"):
         Pair([2.0, 1.6, 2.4], 10, [0.0, 0.4, 0.4], np.float32, boundary_conditions=bc, chi3=chi3,
              sources=[(kb.EZ, [0, 0, 0], [0, 0, 0], CW)])
+
+
+@pytest.mark.parametrize("k", [2.0, -1.2])
+def test_oracle_bloch_band_frequencies_of_vacuum(k):
+    """Physics anchor for Bloch(k): a vacuum cell of period L = 1 with f(x + L) = f(x) exp(i k L) supports
+    plane waves with k_x = k + 2 pi m, i.e. resonances at f = |k + 2 pi m| / (2 pi).  A pulsed sheet source
+    rings them up; the two lowest must appear in the spectrum of a point DFT monitor.  Pins the phase as
+    exp(i k L) with k in radians per unit length (Chunking.jl:1745-1747) and the complex-field update."""
+    import oracle as ko
+    from bridge import oracle_from_simulation
+    nthreads = ko.num_threads()
+    ko.set_num_threads(2)            # 40 x 4 x 4 cells
+    try:
+        bc = [[kb.Bloch(k), kb.Bloch(k)], [kb.Periodic(), kb.Periodic()], [kb.Periodic(), kb.Periodic()]]
+        freqs = np.linspace(0.05, 1.2, 461)
+        src = kb.UniformSource(kb.GaussianPulseSource(fcen=0.5, fwidth=1.5), kb.EY, [0.13, 0, 0], [0, 5, 5])
+        mon = kb.DFTMonitor(kb.EY, [-0.21, 0, 0], [0, 0, 0], list(freqs), decimation=2)
+        sim = kb.Simulation([1.0, 0.1, 0.1], [0, 0, 0], 40, [src], boundaries=[[0, 0]] * 3, boundary_conditions=bc,
+                            monitors=[mon], dtype=np.float64)
+        o, m = oracle_from_simulation(sim)
+        o.step(24000)                # t = 300: line width ~ 1 / 300
+        s = np.abs(o.get_dft(m[0]).reshape(-1, len(freqs))).sum(0)
+    finally:
+        ko.set_num_threads(nthreads)
+    for f_exp in (abs(k) / (2 * np.pi), (2 * np.pi - abs(k)) / (2 * np.pi)):
+        win = np.abs(freqs - f_exp) < 0.03
+        f_peak = freqs[win][np.argmax(s[win])]
+        assert abs(f_peak - f_exp) < 0.004, (k, f_exp, f_peak)
+        assert s[win].max() > 8 * np.median(s), (k, f_exp)
