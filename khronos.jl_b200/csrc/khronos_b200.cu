@@ -2271,6 +2271,7 @@ int32_t khr_field_read_imag(khr_ctx* ctx, int32_t comp, void* dense_out) {
 int32_t khr_field_write(khr_ctx* ctx, int32_t comp, const void* dense_in) {
   NEED_CTX
   if (comp < 0 || comp > 5 || !dense_in) return khr::fail("bad argument");
+  if (ctx->impl_im) return khr::fail("khr_field_write: not supported for complex fields (the imaginary part would keep its old state); use khr_reset_fields");
   KHR_TRY(ctx->impl->field_write(comp, dense_in))
 }
 int32_t khr_field_view(khr_ctx* ctx, int32_t comp, void** dev_ptr, int64_t stride[3], int64_t* offset) {
