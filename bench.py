@@ -96,6 +96,10 @@ def make_desc(name, nranks, sample_scale=1.0):
         return d
     if name == "metalens":
         return w.metalens(nx=1024, ny=1024, nz=256 * nranks, res=32)
+    if name == "metalens_full":
+        # BASELINE.json configs[4]: 2048 x 2048 x 512 per GPU, ~20k rotated pillars (benchmark/metalens.jl);
+        # only sensible with --rasterizer device (the numpy point sampler visits every voxel per object)
+        return w.metalens(nx=2048, ny=2048, nz=512 * nranks, res=32, pillars=144, rotate=True)
     raise SystemExit("unknown workload " + name)
 
 
@@ -179,7 +183,8 @@ def main_ours(args):
 
     desc = make_desc(args.workload, n_gpus)
     dtype = np.float32 if args.dtype == "f32" else np.float64
-    sim = w.build_simulation(desc, dtype, device=local_rank, rank=rank, nranks=n_gpus)
+    sim = w.build_simulation(desc, dtype, device=local_rank, rank=rank, nranks=n_gpus, rasterizer=args.rasterizer,
+                             subpixel_smoothing=args.smoothing)
     t_prep = time.perf_counter()
     sim.prepare_simulation(comm_id=comm_id)
     t_prep = time.perf_counter() - t_prep
@@ -255,7 +260,7 @@ def main_ours(args):
         return
     peak, peak_src = peaks()
     census = sim.voxel_census()
-    per_voxel_eps = sim.material_arrays["eps_inv"] is not None
+    per_voxel_eps = sim.material_arrays["eps_inv"] is not None or args.rasterizer == "device"
     wbytes = np.dtype(dtype).itemsize
     bpc = bytes_per_cell_model(census, per_voxel_eps, wbytes)
     # dominant kernel = largest total CUDA-event time over the K steps of the serialised pass
@@ -299,7 +304,7 @@ def main_ours(args):
                        "dft_monitors": len(sim.dft_monitors), "dft_decimation": sim.dft_monitors[0].decimation if sim.dft_monitors else None,
                        "voxel_census_0123_pml_axes": census, "device_bytes": sim.device_bytes(),
                        "l2": "working set %.0f MB > 126 MB L2, no flush needed" % (sim.device_bytes() / 1e6),
-                       "prepare_s": t_prep},
+                       "prepare_s": t_prep, "rasterizer": args.rasterizer, "subpixel_smoothing": args.smoothing},
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "Mcells/s", "h2d_bytes_per_step": h2d / e2e_steps,
                     "d2h_bytes_per_step": (d2h + out_bytes) / e2e_steps,
@@ -319,6 +324,8 @@ if __name__ == "__main__":
     ap.add_argument("--workload", default="waveguide_mode")
     ap.add_argument("--dtype", default="f32")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--rasterizer", default="host", choices=["host", "device"])
+    ap.add_argument("--smoothing", default=None, choices=["volume", "anisotropic"])
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
     if a.impl == "reference":
