@@ -178,3 +178,38 @@ def test_gpu_slab_transmission_matches_fresnel_and_oracle(dtype):
     assert np.max(np.abs(T - T_ANALYTIC)) < 0.06
     T_oracle = _oracle_flux(True, dtype) / _oracle_flux(False, dtype)
     assert np.max(np.abs(T - T_oracle)) < (1e-9 if dtype is np.float64 else 1e-3), np.max(np.abs(T - T_oracle))
+
+
+def test_oracle_kerr_self_phase_modulation():
+    """Physics anchor for the chi3 branch (Dispersive.jl:127-148, E <- E / (1 + chi3 |E|^2) applied to the
+    E rebuilt from D every step, i.e. eps_eff = eps (1 + chi3 E^2)): a CW plane wave of steady-state
+    amplitude E0 crossing a Kerr layer of thickness d in vacuum picks up the self-phase-modulation shift
+    k d (sqrt(1 + 3/4 chi3 E0^2) - 1) — the 3/4 is the fundamental of cos^3.  DFT increments between two
+    late times give the steady-state phasors (the accumulators are linear in time)."""
+    res, d, buf, pml, cell_xy = 40, 2.0, 1.5, 1.0, 0.1
+    cell_z = d + 2 * buf + 2 * pml
+
+    def run(chi3val, n1=8000, n2=4000):
+        src = kb.UniformSource(kb.ContinuousWaveSource(1.0), kb.EX, [0, 0, -d / 2 - buf / 2], [cell_xy + 1, cell_xy + 1, 0])
+        mons = [kb.DFTMonitor(kb.EX, [0, 0, z], [0, 0, 0], [1.0], decimation=2) for z in (d / 2 + buf / 2, 0.0)]
+        zc = (np.arange(int(cell_z * res)) + 0.5) / res - cell_z / 2
+        chi = None if chi3val is None else np.where(np.abs(zc) <= d / 2, chi3val, 0.0)[None, None, :] * np.ones((4, 4, 1))
+        sim = kb.Simulation([cell_xy, cell_xy, cell_z], [0, 0, 0], res, [src], boundaries=[[0, 0], [0, 0], [pml, pml]],
+                            boundary_conditions=[[kb.Periodic(), kb.Periodic()], [kb.Periodic(), kb.Periodic()],
+                                                 [kb.PML(), kb.PML()]], monitors=mons, dtype=np.float64, chi3=chi)
+        o, m = oracle_from_simulation(sim)
+        o.step(n1)
+        a = [complex(o.get_dft(i).flat[0]) for i in m]
+        o.step(n2)
+        b = [complex(o.get_dft(i).flat[0]) for i in m]
+        window = (n2 / 2) * float(sim.grid.dt)            # decimation 2
+        return [(y - x) / window for x, y in zip(a, b)]
+
+    lin = run(None)
+    E0 = 2 * abs(lin[1])                                  # phasor of E0 cos(wt) is E0 / 2
+    x = 0.01                                              # chi3 E0^2
+    kerr = run(x / E0 ** 2)
+    dphi = np.angle(kerr[0] / lin[0])
+    want = 2 * np.pi * d * (np.sqrt(1 + 0.75 * x) - 1)
+    assert abs(dphi / want - 1.0) < 0.03, (dphi, want)    # measured 0.0474 vs 0.0470
+    assert abs(abs(kerr[0] / lin[0]) - 1.0) < 0.01        # lossless, index-matched: no amplitude change
