@@ -1067,6 +1067,48 @@ class Simulation:
             pass
 
 
+def stop_when_dft_decayed(tolerance=1e-6, minimum_runtime=0.0, maximum_runtime=float("inf")):
+    """Simulation.jl:411-485 stop_when_dft_decayed: a stop predicate for `run(until_after_sources=...)`.
+    Each DFT monitor tracks the step-to-step change of its norm (dft_fields_norm, `khr_monitor_norms`:
+    one device reduction for all stale monitors, cached between DFT updates) relative to the largest
+    change it has seen; the run stops when every monitor that has seen signal reports
+    rel_change <= tolerance.  Restated literally, including its behaviour with decimated monitors:
+    on a step without a DFT update the norm does not change, so rel_change = 0 there."""
+    if minimum_runtime > maximum_runtime:
+        raise ValueError("Minimum runtime (%s) cannot be greater than maximum runtime (%s)." % (minimum_runtime, maximum_runtime))
+    state = {}
+
+    def _stop(sim):
+        t = sim.round_time()
+        if t < minimum_runtime:
+            return False
+        if t > maximum_runtime:
+            return True
+        all_converged, n_active = True, 0
+        for i, current in enumerate(sim.monitor_norms()):
+            if current == 0.0:
+                continue
+            if i not in state:
+                state[i] = (current, 0.0)
+                all_converged = False
+                continue
+            prev, maxchange = state[i]
+            change = abs(current - prev)
+            maxchange = max(maxchange, change)
+            state[i] = (current, maxchange)
+            if maxchange == 0.0:
+                all_converged = False
+                continue
+            n_active += 1
+            if change / maxchange > tolerance:
+                all_converged = False
+        if n_active == 0:
+            return False
+        return all_converged
+
+    return _stop
+
+
 def run(sim, until=None, until_after_sources=None):
     """Khronos.run(sim; until=..., until_after_sources=...)."""
     return sim.run(until=until, until_after_sources=until_after_sources)

@@ -274,3 +274,46 @@ def test_auto_decimation_rule():
                         monitors=[kb.DFTMonitor(kb.EZ, [0, 0, 0], [1, 1, 0], [1.0]), kb.DFTMonitor(kb.EX, [0, 0, 0], [1, 1, 0], [1.0], 3)])
     sim.host_prepare()
     assert [m.decimation for m in sim.dft_monitors] == [16, 3]
+
+
+def test_stop_when_dft_decayed_predicate():
+    """Simulation.jl:411-485 restated in the host mirror: per-monitor change relative to the largest
+    change seen; monitors without signal are ignored; minimum / maximum runtime."""
+    import khronos_b200 as kb
+
+    class Stub:
+        def __init__(self, series, dt=1.0):
+            self.series, self.i, self.dt = series, -1, dt
+
+        def advance(self):
+            self.i += 1
+
+        def round_time(self):
+            return self.i * self.dt
+
+        def monitor_norms(self):
+            return [s[min(self.i, len(s) - 1)] for s in self.series]
+
+    def run(stub, stop, nmax=100):
+        for _ in range(nmax):
+            stub.advance()
+            if stop(stub):
+                return stub.i
+        return None
+
+    # a monitor that rings up and settles, one that never sees signal
+    a = [0.0, 1.0, 3.0, 4.0, 4.5, 4.75, 4.76, 4.76000001, 4.76000001]
+    assert run(Stub([a, [0.0] * 9]), kb.stop_when_dft_decayed(tolerance=1e-6)) == 7     # |4.76000001 - 4.76| / 2 <= 1e-6
+    assert run(Stub([a, [0.0] * 9]), kb.stop_when_dft_decayed(tolerance=1e-12)) == 8    # no change at all
+    # literal quirk: checks start at minimum_runtime; a monitor that stopped changing before that never
+    # shows a change, is never "active", and only maximum_runtime ends the run
+    assert run(Stub([a]), kb.stop_when_dft_decayed(tolerance=1e-6, minimum_runtime=20.0)) is None
+    assert run(Stub([a]), kb.stop_when_dft_decayed(tolerance=1e-6, minimum_runtime=20.0, maximum_runtime=30.0)) == 31
+    assert run(Stub([a]), kb.stop_when_dft_decayed(tolerance=1e-6, minimum_runtime=3.0)) == 7
+    assert run(Stub([[0.0] * 5]), kb.stop_when_dft_decayed(), nmax=30) is None          # never any signal
+    assert run(Stub([[0.0, 1.0, 2.0, 4.0, 8.0, 16.0, 32.0, 64.0]]), kb.stop_when_dft_decayed(maximum_runtime=5.0), nmax=7) == 6
+    # two monitors: the slower one decides
+    b = [0.0, 0.0, 0.0, 1.0, 2.0, 2.5, 2.75, 2.875, 2.875, 2.875]
+    assert run(Stub([a, b]), kb.stop_when_dft_decayed(tolerance=1e-6)) == 8
+    with pytest.raises(ValueError):
+        kb.stop_when_dft_decayed(minimum_runtime=2.0, maximum_runtime=1.0)
