@@ -984,6 +984,36 @@ class Simulation:
                     out[(im - max_order, i_n - max_order)] = power[:, im, i_n].copy()
         return out
 
+    @staticmethod
+    def compute_LEE(power, theta, phi, cone_half_angle=math.pi / 2):
+        """Near2Far.jl:1082-1124 compute_LEE: power inside a cone over the hemispherical power,
+        trapezoidal weights with the sin(theta) Jacobian."""
+        power = np.asarray(power, dtype=np.float64)
+        nt, npz = len(theta), len(phi)
+        dth = np.diff(theta) if nt > 1 else np.array([0.0])
+        dph = np.diff(phi) if npz > 1 else np.array([0.0])
+        p_total = p_cone = 0.0
+        for ip in range(npz):
+            if ip == 0:
+                wp = dph[0] / 2 if len(dph) > 0 else 2 * math.pi
+            elif ip == npz - 1:
+                wp = dph[-1] / 2
+            else:
+                wp = (dph[ip - 1] + dph[ip]) / 2
+            for it in range(nt):
+                if it == 0:
+                    wt = dth[0] / 2 if len(dth) > 0 else math.pi / 2
+                elif it == nt - 1:
+                    wt = dth[-1] / 2
+                else:
+                    wt = (dth[it - 1] + dth[it]) / 2
+                integrand = power[it, ip] * math.sin(theta[it]) * wt * wp
+                if theta[it] <= math.pi / 2:
+                    p_total += integrand
+                if theta[it] <= cone_half_angle:
+                    p_cone += integrand
+        return p_cone / p_total if p_total > 0 else 0.0
+
     def compute_mode_amplitudes(self, fm, mode_fields):
         """ModeMonitor.jl:345-515 compute_mode_amplitudes with the surface sums on the device
         (`khr_mode_overlap`).  mode_fields: complex (4, n1, n2, nf) = mode e1, e2, h1, h2 already

@@ -1952,3 +1952,20 @@ void ko_diffraction(void* hv, int normal_axis, const int* ids4, int max_order, d
   DISPATCH(h, diffraction_impl(S, normal_axis, ids4, max_order, L1, L2, kinc1, kinc2, freqs, power, prop));
 }
 }  // extern "C"
+
+extern "C" {
+// green3d! (src/Monitors/Near2Far.jl:40-96) for every observation point, summed over a list of point
+// currents: src = nsrc x (x, y, z, c0, re f0, im f0); out = nobs x 6 complex.  Lets the tests replay
+// the reference's own green3d! test-sets (test/test_near2far.jl:10-170).
+void ko_green3d_many(int nobs, const double* obs, int nsrc, const double* src, double freq, double eps, double mu, double* out) {
+#pragma omp parallel for schedule(static)
+  for (int io = 0; io < nobs; ++io) {
+    cd EH[6] = {0, 0, 0, 0, 0, 0};
+    for (int q = 0; q < nsrc; ++q) {
+      const double* s = src + 6 * q;
+      green3d(EH, obs + 3 * io, freq, eps, mu, s, (int)s[3], cd(s[4], s[5]));
+    }
+    for (int j = 0; j < 6; ++j) { out[12 * io + 2 * j] = EH[j].real(); out[12 * io + 2 * j + 1] = EH[j].imag(); }
+  }
+}
+}  // extern "C"

@@ -85,6 +85,7 @@ def lib():
         L.ko_flux.argtypes = [C.c_void_p, C.c_int, ip, dp]
         L.ko_near2far.argtypes = [C.c_void_p, C.c_int, ip, C.c_double, C.c_double, C.c_double, dp, dp, dp, C.c_int, dp]
         L.ko_mode_amplitudes.argtypes = [C.c_void_p, C.c_int, ip, dp, dp, dp, dp]
+        L.ko_green3d_many.argtypes = [C.c_int, dp, C.c_int, dp, C.c_double, C.c_double, C.c_double, dp]
         L.ko_diffraction.argtypes = [C.c_void_p, C.c_int, ip, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp, ip]
         _LIB = L
     return _LIB
@@ -144,6 +145,19 @@ def halo_ranges(src6, dst6, axis, src_upper, dst_lower):
     lib().ko_halo_ranges(sp, dp_, int(axis), int(src_upper), int(dst_lower),
                          sr.ctypes.data_as(C.POINTER(C.c_int)), dr.ctypes.data_as(C.POINTER(C.c_int)))
     return sr, dr
+
+
+def green3d(obs, sources, freq, eps=1.0, mu=1.0):
+    """green3d! (Near2Far.jl:40-96) summed over point currents.  obs: (nobs, 3); sources: rows
+    (x, y, z, c0, f0) with c0 = 1..3 electric Jx,Jy,Jz, 4..6 magnetic, f0 complex.  Returns (nobs, 6) complex."""
+    o, op = _d(np.asarray(obs, dtype=np.float64).reshape(-1, 3))
+    rows = np.array([[r[0], r[1], r[2], float(r[3]), complex(r[4]).real, complex(r[4]).imag] for r in sources], dtype=np.float64)
+    s, sp = _d(rows)
+    out = np.zeros(12 * o.shape[0])
+    lib().ko_green3d_many(o.shape[0], op, s.shape[0], sp, float(freq), float(eps), float(mu),
+                          out.ctypes.data_as(C.POINTER(C.c_double)))
+    z = out[0::2] + 1j * out[1::2]
+    return z.reshape(o.shape[0], 6)
 
 
 class OracleSim:

@@ -129,3 +129,31 @@ def test_gpu_rasterizer_argument_errors():
     with pytest.raises(kb.KhronosError, match="device"):
         kb.Simulation([4, 4, 4], [0, 0, 0], 10, [], geometry=_scene(), rasterizer="device",
                       absorbers=[[kb.Absorber(4), None], None, None]).host_prepare()
+
+
+def test_reference_subpixel_testset_on_sphere():
+    """"Subpixel smoothing on sphere" (test/test_subpixel.jl:38-153) replayed on the oracle's restatement:
+    eps = 12 ball of radius 1 over an eps = 1 background cuboid, 4^3 cell at resolution 10."""
+    geom = [kb.Object(kb.Ball([0, 0, 0], 1.0), kb.Material(epsilon=12.0)),
+            kb.Object(kb.Cuboid([0, 0, 0], [100.0, 100.0, 100.0]), kb.Material(epsilon=1.0))]
+    src = [kb.UniformSource(CW, kb.EZ, [0, 0, 0], [0, 0, 0])]
+
+    def arrays(mode):
+        sim = kb.Simulation([4.0, 4.0, 4.0], [0, 0, 0], 10, src, boundaries=[[1.0, 1.0]] * 3, geometry=geom,
+                            dtype=np.float32, rasterizer="device", subpixel_smoothing=mode)
+        return _oracle_arrays(sim)[1]["eps_inv"]
+
+    inv_s, inv_b = np.float32(1.0 / 12.0), np.float32(1.0)
+    near = lambda v, w: np.isclose(v, w, rtol=1e-4, atol=0)
+    none = arrays(None)
+    assert np.all(near(none[0], inv_s) | near(none[0], inv_b))                      # binary values
+    for mode in ("volume", "anisotropic"):
+        e = arrays(mode)
+        inter = ~near(e[0], inv_s) & ~near(e[0], inv_b)
+        assert inter.sum() > 0                                                      # intermediate values at interfaces
+        c = e[0].shape[0] // 2 - 1
+        assert near(e[0][c, c, c], inv_s) and near(e[0][0, 0, 0], inv_b)            # interior / exterior unchanged
+        assert np.all((e[0] >= inv_s - 1e-5) & (e[0] <= inv_b + 1e-5))              # bounded
+        if mode == "anisotropic":                                                   # components differ at the interface
+            diff = inter & (~near(e[0], e[1]) | ~near(e[0], e[2]))
+            assert diff.sum() > 0

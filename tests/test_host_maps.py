@@ -317,3 +317,53 @@ def test_stop_when_dft_decayed_predicate():
     assert run(Stub([a, b]), kb.stop_when_dft_decayed(tolerance=1e-6)) == 8
     with pytest.raises(ValueError):
         kb.stop_when_dft_decayed(minimum_runtime=2.0, maximum_runtime=1.0)
+
+
+def test_reference_drude_chi1_stability_testset():
+    """"Drude ADE eigenvalue stability (chi1 correction)" (test/test_dispersive.jl:74-160) replayed with the
+    oracle's ADE coefficients (Susceptibility.jl:74-85) and the chi1 value the host mirror folds into
+    eps^-1 (Geometry.jl:1236-1353): with the correction every eigenvalue of the update matrix stays on
+    or inside the unit circle, without it the silver-like Drude medium of uled.jl is unstable."""
+    import oracle as ko
+    nm = 1e-3
+    freq0 = 1.0 / (450 * nm)
+    chi_target = (0.028 + 2.88j) ** 2 - 1.0
+    w0 = 2 * np.pi * freq0
+    Gamma_ang = -w0 * chi_target.imag / chi_target.real
+    gamma_meep = Gamma_ang / (2 * np.pi)
+    sigma_drude = -chi_target.real * (w0 ** 2 + Gamma_ang ** 2) / Gamma_ang
+    dx = 1.0 / 40
+    dt = 0.5 * dx / np.sqrt(3.0)
+    Co = dt / dx
+    c = ko.ade_coefficients(0.0, gamma_meep, dt)
+    assert c["is_drude"]
+    g1, g1i = c["gamma1"], c["gamma1_inv"]
+    assert np.isclose(g1, 1 - gamma_meep * np.pi * dt) and np.isclose(g1i, 1 / (1 + gamma_meep * np.pi * dt))
+    assert np.isclose(c["drude_coeff"], gamma_meep * 2 * np.pi * dt ** 2)
+    d = c["drude_coeff"] * sigma_drude
+    chi1 = g1i * d / 2                    # what simulation.py folds into eps_inv: g1i * (gamma 2 pi dt^2) / 2 * sigma
+
+    def max_eig(eps_eff, S_list):
+        worst = 0.0
+        for S in S_list:
+            M = np.array([[1 - (S ** 2 + g1i * d) / eps_eff, 1j * S / eps_eff, -g1 * g1i / eps_eff, g1 * g1i / eps_eff],
+                          [1j * S, 1, 0, 0], [g1i * d, 0, 2 * g1i, -g1i * g1], [0, 0, 1, 0]], dtype=complex)
+            worst = max(worst, np.abs(np.linalg.eigvals(M)).max())
+        return worst
+
+    S_1d = [2 * Co * np.sin(kf * np.pi / 2) for kf in np.linspace(0.01, 1.0, 200)]
+    assert max_eig(1 + chi1, S_1d) <= 1.0 + 1e-12
+    assert max_eig(1 + chi1, [np.sqrt(3.0)]) <= 1.0 + 1e-12      # 3-D worst case as the reference writes it
+    assert max_eig(1.0, S_1d) > 1.0                               # unstable without the correction
+
+
+def test_reference_susceptibility_formulas_are_the_anchor_formulas():
+    """"Susceptibility evaluation" (test/test_dispersive.jl:40-58): the reference's chi(w) for Lorentz and
+    Drude media — the closed forms tests/test_physics_anchor.py holds the time-stepper to."""
+    import test_physics_anchor as t
+    f = t.FREQS
+    w = 2 * np.pi * f
+    lor = 2.0 + 1.5 * (2 * np.pi * 1.2) ** 2 / ((2 * np.pi * 1.2) ** 2 - w ** 2 - 1j * w * (2 * np.pi * 0.2))
+    dru = 1.5 + (-3.0 * (2 * np.pi * 0.5) / (w ** 2 + 1j * w * (2 * np.pi * 0.5)))
+    assert np.allclose(lor, t.DISPERSIVE["lorentz"][1], rtol=1e-13)
+    assert np.allclose(dru, t.DISPERSIVE["drude"][1], rtol=1e-13)

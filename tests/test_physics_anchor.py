@@ -98,7 +98,9 @@ def _slab_T(freq, eps):
 # The ADE update of the reference (Susceptibility.jl:60-85, Dispersive.jl:25-88) is, in the continuum,
 #   Lorentz: P'' + G P' + W0^2 P = W0^2 sigma E,  W0 = 2 pi omega_0, G = 2 pi gamma
 #   Drude:   P'' + G P' = G sigma E
-# i.e. chi(f) = sigma f0^2 / (f0^2 - f^2 - i f gamma) and chi(w) = G sigma / (-w^2 - i w G).
+# i.e. chi(f) = sigma f0^2 / (f0^2 - f^2 - i f gamma) and chi(w) = G sigma / (-w^2 - i w G) — the very
+# formulas of the reference's eval_susceptibility (test/test_dispersive.jl:40-58; checked in
+# tests/test_host_maps.py::test_reference_susceptibility_formulas_are_the_anchor_formulas).
 DISPERSIVE = {
     "lorentz": (kb.Material(epsilon=2.0, susceptibilities=[kb.LorentzianSusceptibility(1.2, 0.2, 1.5)]),
                 2.0 + 1.5 * 1.2 ** 2 / (1.2 ** 2 - FREQS ** 2 - 1j * FREQS * 0.2)),

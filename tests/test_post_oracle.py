@@ -180,3 +180,64 @@ def test_near2far_power_equals_flux_through_the_box():
     P_far = (Sr.mean(1) * 2 * np.pi * wq).sum() * R * R
     assert flux > 0 and abs(P_far / flux - 1.0) < 0.12, (P_far, flux)
     assert abs(P_far / flux_as_is - 1.0) > 1.0          # the y faces cancel the x faces without the sign
+
+
+# ---- the reference's own near-to-far test-sets (test/test_near2far.jl), replayed on the oracle's green3d ----
+def test_reference_green3d_testsets():
+    import oracle as ko
+    # "Green's function 3D" (:10-23): non-zero output
+    EH = ko.green3d([[1.0, 0.0, 0.0]], [[0.0, 0.0, 0.0, 1, 1.0]], 1.0)
+    assert np.any(np.abs(EH) > 0)
+    # "Green's function reciprocity" (:25-44): Ex of Jx is symmetric under exchanging source and observer
+    x1, x0 = [2.0, 1.0, 0.5], [0.0, 0.0, 0.0]
+    fwd = ko.green3d([x1], [x0 + [1, 1.0]], 1.0)[0, 0]
+    bwd = ko.green3d([x0], [x1 + [1, 1.0]], 1.0)[0, 0]
+    assert abs(fwd - bwd) <= 1e-10 * abs(bwd)
+    # "far-field 1/r decay" (:46-69)
+    d = np.ones(3) / np.sqrt(3.0)
+    E1 = ko.green3d([1e4 * d], [[0, 0, 0, 3, 1.0]], 1.0)[0, 0:3]
+    E2 = ko.green3d([2e4 * d], [[0, 0, 0, 3, 1.0]], 1.0)[0, 0:3]
+    assert abs(np.linalg.norm(E2) / np.linalg.norm(E1) - 0.5) <= 1e-3 * 0.5
+
+
+def test_reference_near2far_analytical_roundtrip():
+    """"Near2far analytical roundtrip (Jz dipole -> sin^2 theta)" (test/test_near2far.jl:71-170): exact near
+    field of a Jz dipole on a z plane, equivalent currents, projection, compute_far_field_power; the
+    phi-averaged power must follow sin^2(theta) for theta <= 45 deg with RMS error < 0.15."""
+    import oracle as ko
+    z0, r_obs, n_grid, L_ext = 2.0, 1e6, 81, 20.0
+    xs = np.linspace(-L_ext / 2, L_ext / 2, n_grid)
+    dA = (xs[1] - xs[0]) ** 2
+    surf = np.array([[x, y, z0] for y in xs for x in xs])
+    nf = ko.green3d(surf, [[0.0, 0.0, 0.0, 3, 1.0]], 1.0)                  # Ex, Ey, Ez, Hx, Hy, Hz on the plane
+    assert np.abs(nf[:, 0]).max() > 0 and np.abs(nf[:, 4]).max() > 0
+    ex, ey, hx, hy = nf[:, 0], nf[:, 1], nf[:, 3], nf[:, 4]
+    ns = 1.0
+    sources = []
+    for q, (px, py, pz) in enumerate(surf):
+        sources += [[px, py, pz, 1, ns * hy[q] * dA], [px, py, pz, 2, -ns * hx[q] * dA],
+                    [px, py, pz, 4, -ns * ey[q] * dA], [px, py, pz, 5, ns * ex[q] * dA]]
+    theta = np.linspace(5.0, 45.0, 9) * np.pi / 180
+    phi = np.linspace(0.0, 2 * np.pi - 2 * np.pi / 12, 12)
+    obs = np.array([[r_obs * np.sin(t) * np.cos(p), r_obs * np.sin(t) * np.sin(p), r_obs * np.cos(t)] for p in phi for t in theta])
+    EH = ko.green3d(obs, sources, 1.0)
+    power = kb.Simulation.compute_far_field_power(EH[:, :, None], theta, phi)
+    pw = power.mean(axis=1)
+    rms = np.sqrt(np.mean((pw / pw.max() - np.sin(theta) ** 2 / np.max(np.sin(theta) ** 2)) ** 2))
+    assert rms < 0.15, rms
+
+
+def test_reference_far_field_power_and_lee_testsets():
+    """"Far-field power computation" and "LEE computation" (test/test_near2far.jl:172-210) on the host mirror."""
+    theta = np.linspace(0, np.pi / 2, 10)
+    phi = np.linspace(0, 2 * np.pi, 21)[:-1]
+    EH = np.zeros((200, 6, 1), dtype=complex)
+    EH[:, 0, 0] = 1.0
+    power = kb.Simulation.compute_far_field_power(EH, theta, phi)
+    assert power.shape == (10, 20) and np.all(power >= 0)
+    theta = np.linspace(0, np.pi / 2, 100)
+    phi = np.linspace(0, 2 * np.pi, 101)[:-1]
+    ones = np.ones((100, 100))
+    alpha = np.deg2rad(30.0)
+    assert abs(kb.Simulation.compute_LEE(ones, theta, phi, cone_half_angle=alpha) / (1 - np.cos(alpha)) - 1) < 0.05
+    assert abs(kb.Simulation.compute_LEE(ones, theta, phi, cone_half_angle=np.pi / 2) - 1.0) < 0.01
