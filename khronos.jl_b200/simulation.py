@@ -36,8 +36,8 @@ class ContinuousWaveSource:
     def params(self, T):
         return [float(T(self.fcen)), 0.0, 0.0, 0.0]
 
-    def f_max(self):
-        return self.fcen
+    def f_max(self, T=np.float64):
+        return float(T(self.fcen))     # the profile stores fcen as backend_number (TimeSources.jl:52-58)
 
     def cutoff(self):
         return None
@@ -49,6 +49,7 @@ class GaussianPulseSource:
     kind = _lib.TIME_GAUSSIAN
 
     def __init__(self, fcen, fwidth, start_time=0.0, cutoff_scale=5.0):
+        self.ctor_args = (float(fcen), float(fwidth), float(start_time), float(cutoff_scale))
         width = 1.0 / fwidth
         cutoff = width * cutoff_scale + start_time
         self.fwidth = math.sqrt(-2.0 * math.log(1e-7)) / (width * math.pi)
@@ -62,8 +63,8 @@ class GaussianPulseSource:
     def params(self, T):
         return [float(T(self.fcen)), float(T(self.width)), float(T(self.peak_time)), float(T(self.cutoff_))]
 
-    def f_max(self):
-        return self.fcen + self.fwidth / 2
+    def f_max(self, T=np.float64):
+        return float(T(self.fcen)) + float(T(self.fwidth)) / 2   # Monitors.jl:43-45 on the T-typed fields
 
     def cutoff(self):
         return self.cutoff_
@@ -80,8 +81,8 @@ class CustomSource:
     def params(self, T):
         return [float(T(self.fcen)), float(T(self.fwidth)), 0.0, float(T(self.end_time))]
 
-    def f_max(self):
-        return self.fcen + self.fwidth / 2
+    def f_max(self, T=np.float64):
+        return float(T(self.fcen)) + float(T(self.fwidth)) / 2
 
     def cutoff(self):
         return self.end_time
@@ -209,6 +210,7 @@ class DFTMonitor:
         self.center = [float(v) for v in center]
         self.size = [float(v) for v in size]
         self.frequencies = [float(f) for f in frequencies]
+        self.user_decimation = int(decimation)   # as given; `decimation` may be raised by auto_decimate!
         self.decimation = int(decimation)
         self.id = None
         self.start = self.end = None
@@ -344,7 +346,8 @@ class Simulation:
         out = []
         for a in range(3):
             if self.grid.dlv[a] is None:
-                out.append(o[a] + np.arange(self.grid.N[a], dtype=np.float64) * float(self.grid.dl[a]))
+                # origin + (i - 1) * Δ with the Int * T product formed in T (Geometry.jl:351-375)
+                out.append(o[a] + (np.arange(self.grid.N[a]).astype(self.T) * self.T(self.grid.dl[a])).astype(np.float64))
             else:  # _build_coords(Δ::AbstractVector, ...) (Geometry.jl:377-395): origin + sum(Δ[1:i-1])
                 cum = np.concatenate([[0.0], np.cumsum(self.grid.dlv[a].astype(np.float64))[:-1]])
                 out.append(o[a] + cum)
@@ -371,12 +374,13 @@ class Simulation:
             for d in range(3):
                 xs, ys, zs = self._coords(comp0 + d)
                 X, Y, Z = np.meshgrid(xs, ys, zs, indexing="ij", sparse=True)
-                a = np.full(shape, 1.0 if inverse else 0.0, dtype=np.float64)
+                a = np.full(shape, T(1) if inverse else T(0), dtype=T)
                 for obj in reversed(self.geometry):  # earlier objects take priority (Geometry.jl:241)
                     m = obj.shape.contains(X, Y, Z)
                     v = getattr(obj.material, attr)
-                    a[np.broadcast_to(m, shape)] = (1.0 / v) if inverse else v
-                out.append(a.astype(T))
+                    # get_perm_inv = one(T) / T(perm), get_sigma = T(sigma) (Geometry.jl:62-79)
+                    a[np.broadcast_to(m, shape)] = (T(1) / T(v)) if inverse else T(v)
+                out.append(a)
             return out
 
         if need_eps:
@@ -408,15 +412,16 @@ class Simulation:
         xs, ys, zs = self._coords(EX)
         X, Y, Z = np.meshgrid(xs, ys, zs, indexing="ij", sparse=True)
         for key in uniq:
-            sg = np.zeros(shape, dtype=np.float64)
+            # _rasterize_pole_sigma! (Geometry.jl:1082-1125): last object first; an object that does not
+            # carry this pole is skipped (it does NOT clear what a lower-priority object painted); the
+            # first matching susceptibility of an object wins
+            sg = np.zeros(shape, dtype=T)
             for obj in reversed(self.geometry):
-                m = np.broadcast_to(obj.shape.contains(X, Y, Z), shape)
-                val = 0.0
-                for s in obj.material.susceptibilities:
-                    if (s.omega_0, s.gamma) == key:
-                        val = s.sigma
-                sg[m] = val
-            poles.append((key[0], key[1], sg.astype(T)))
+                match = [s for s in obj.material.susceptibilities if (s.omega_0, s.gamma) == key]
+                if not match:
+                    continue
+                sg[np.broadcast_to(obj.shape.contains(X, Y, Z), shape)] = T(match[0].sigma)
+            poles.append((key[0], key[1], sg))
         return arrays, poles
 
     def _zero_pole_sigma_in_pml(self, sigma):
@@ -731,17 +736,19 @@ class Simulation:
         return amp
 
     def _auto_decimate(self):
-        """Monitors.jl:33-78 auto_decimate!."""
+        """Monitors.jl:33-78 auto_decimate!: monitors the user left at decimation 1 get D_max."""
+        for m in self.dft_monitors:
+            m.decimation = m.user_decimation
         f_max = 0.0
         for s in self.sources:
-            f_max = max(f_max, s.time_profile.f_max())
+            f_max = max(f_max, s.time_profile.f_max(self.T))
         if f_max <= 0:
             return
         d_max = max(1, int(math.floor(1.0 / (2.0 * f_max * float(self.grid.dt)))))
         if d_max <= 1:
             return
         for m in self.dft_monitors:
-            if m.decimation == 1:
+            if m.user_decimation == 1:
                 m.decimation = d_max
 
     # --------------------------------------------------------------- step

@@ -1907,6 +1907,284 @@ void ko_rasterize(void* hv, int nobj, const double* objs, int kinds_mask, int sm
 
 }  // extern "C"
 
+// ---------------------------------------------------------------------------
+// The oracle's OWN derivation of the hot-path inputs from the user-level description
+// (so that the parity tests do not hand the oracle what the product computed):
+//   * source boxes and interpolation weights  (src/Sources/Sources.jl:43-135)
+//   * the GaussianPulseSource constructor      (src/Sources/TimeSources.jl:89-112)
+//   * dispersive poles: unique poles, sigma rasterisation, PML zeroing, chi1 fold
+//                                              (src/Geometry.jl:1059-1353 init_polarization!)
+//   * the Kerr coefficient array               (src/Geometry.jl:610-635)
+//   * auto-decimation                          (src/Monitors/Monitors.jl:33-78)
+// Absorber ramps (ko_add_absorber) and the geometry raster (ko_rasterize) were already derived here.
+// ---------------------------------------------------------------------------
+namespace {
+inline void parse_objects(const double* flat, int nobj, std::vector<GObj>& objs) {
+  objs.resize((size_t)nobj);
+  for (int q = 0; q < nobj; ++q) {
+    const double* f = flat + 28 * q;
+    GObj& o = objs[(size_t)q];
+    o.kind = (int)f[0];
+    for (int k = 0; k < 3; ++k) o.c[k] = f[1 + k];
+    if (o.kind == 0) {
+      o.r[0] = f[4]; o.r[1] = o.r[2] = 0;
+      for (int k = 0; k < 3; ++k) { o.bmin[k] = o.c[k] - o.r[0]; o.bmax[k] = o.c[k] + o.r[0]; }
+      for (int k = 0; k < 9; ++k) o.ax[k] = 0;
+    } else {
+      bool ident = true;
+      for (int k = 0; k < 9; ++k) ident = ident && f[7 + k] == 0.0;
+      for (int k = 0; k < 3; ++k) {
+        o.r[k] = f[4 + k] / 2;
+        double nr = 0;
+        for (int j = 0; j < 3; ++j) { o.ax[3 * k + j] = ident ? (j == k ? 1.0 : 0.0) : f[7 + 3 * k + j]; nr += o.ax[3 * k + j] * o.ax[3 * k + j]; }
+        nr = std::sqrt(nr);
+        for (int j = 0; j < 3; ++j) o.ax[3 * k + j] /= nr;
+      }
+      for (int i = 0; i < 3; ++i) {
+        double m = 0;
+        for (int j = 0; j < 3; ++j) m += std::fabs(o.ax[3 * j + i]) * o.r[j];
+        o.bmin[i] = o.c[i] - m; o.bmax[i] = o.c[i] + m;
+      }
+    }
+  }
+}
+
+// paint `val` over the voxels of one object on a component grid (bounds pruning + `point in shape`,
+// the loop shared by _rasterize_pole_sigma! and the chi3 painting)
+template <class SimT, class TT>
+void paint_object(const SimT& S, const GObj& o, const std::vector<double>* xs, Arr3<TT>& arr, TT val) {
+  int lo[3], hi[3];
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = (int)(std::lower_bound(xs[a].begin(), xs[a].end(), o.bmin[a]) - xs[a].begin()) + 1;
+    hi[a] = (int)(std::upper_bound(xs[a].begin(), xs[a].end(), o.bmax[a]) - xs[a].begin());
+    lo[a] = std::max(lo[a], 1); hi[a] = std::min(hi[a], S.N[a]);
+    if (lo[a] > hi[a]) return;
+  }
+  for (int iz = lo[2]; iz <= hi[2]; ++iz)
+    for (int iy = lo[1]; iy <= hi[1]; ++iy)
+      for (int ix = lo[0]; ix <= hi[0]; ++ix) {
+        double pt[3] = {xs[0][(size_t)ix - 1], xs[1][(size_t)iy - 1], xs[2][(size_t)iz - 1]};
+        if (g_contains(o, pt)) arr.at(ix - 1, iy - 1, iz - 1) = val;
+      }
+}
+
+// coordinates of cells 1..N of a component grid: origin + (i - 1) * Δ with the product formed in T
+// (_precompute_coords / _build_coords, Geometry.jl:351-375; vector Δ: cumulative sums, :377-395)
+template <class SimT>
+void comp_coords(const SimT& S, int comp, std::vector<double>* xs) {
+  using T = std::remove_const_t<std::remove_reference_t<decltype(S.dt)>>;
+  double org[3];
+  S.component_origin(comp, org);
+  for (int a = 0; a < 3; ++a) {
+    xs[a].resize((size_t)S.N[a]);
+    if (S.dlv[a].empty()) {
+      for (int i = 1; i <= S.N[a]; ++i) xs[a][(size_t)i - 1] = org[a] + (double)((T)(i - 1) * S.dl[a]);
+    } else {
+      double cum = 0.0;
+      for (int i = 1; i <= S.N[a]; ++i) { xs[a][(size_t)i - 1] = org[a] + cum; cum += (double)S.dlv[a][(size_t)i - 1]; }
+    }
+  }
+}
+
+// _collect_unique_poles + _rasterize_pole_sigma! (Geometry.jl:1059-1125): objects that do not carry
+// the pole are SKIPPED (they do not clear a lower-priority object's sigma), the first matching
+// susceptibility of an object wins, painting runs last -> first
+template <class SimT>
+int poles_from_geometry(SimT& S, int nobj, const double* flat, const int* nsus, const double* sus3) {
+  using T = std::remove_reference_t<decltype(S.dt)>;
+  std::vector<GObj> objs;
+  parse_objects(flat, nobj, objs);
+  std::vector<int> first((size_t)nobj + 1, 0);
+  for (int q = 0; q < nobj; ++q) first[(size_t)q + 1] = first[(size_t)q] + nsus[q];
+  std::vector<std::pair<double, double>> keys;
+  for (int q = 0; q < nobj; ++q)
+    for (int k = first[(size_t)q]; k < first[(size_t)q + 1]; ++k) {
+      std::pair<double, double> key(sus3[3 * k], sus3[3 * k + 1]);
+      if (std::find(keys.begin(), keys.end(), key) == keys.end()) keys.push_back(key);
+    }
+  std::vector<double> xs[3];
+  comp_coords(S, 0 /* Ex grid */, xs);
+  for (auto& key : keys) {
+    Pole<T> p;
+    p.c = ade_coefficients(key.first, key.second, (double)S.dt);
+    p.sigma.alloc(S.N[0], S.N[1], S.N[2]);
+    for (int gi = nobj - 1; gi >= 0; --gi) {
+      bool found = false;
+      T val = T(0);
+      for (int k = first[(size_t)gi]; k < first[(size_t)gi + 1]; ++k)
+        if (sus3[3 * k] == key.first && sus3[3 * k + 1] == key.second) { val = (T)sus3[3 * k + 2]; found = true; break; }
+      if (!found) continue;
+      paint_object(S, objs[(size_t)gi], xs, p.sigma, val);
+    }
+    S.poles.push_back(std::move(p));
+  }
+  return (int)keys.size();
+}
+
+// init_polarization! after the rasterisation (Geometry.jl:1180-1353): sigma zeroed inside the PML,
+// chi1 = sum_k T(gamma1_inv * C_k / 2) * sigma_k, eps_inv <- eps_inv / (1 + eps_inv * chi1)
+template <class SimT>
+void finish_poles(SimT& S) {
+  using T = std::remove_reference_t<decltype(S.dt)>;
+  if (S.poles.empty()) return;
+  std::vector<double> xs[3];
+  comp_coords(S, 0, xs);
+  if (S.has_boundaries) {
+    for (auto& p : S.poles)
+      for (int iz = 0; iz < S.N[2]; ++iz)
+        for (int iy = 0; iy < S.N[1]; ++iy)
+          for (int ix = 0; ix < S.N[0]; ++ix) {
+            if (p.sigma.at(ix, iy, iz) == T(0)) continue;
+            const int id[3] = {ix, iy, iz};
+            bool in_pml = false;
+            for (int a = 0; a < 3 && !in_pml; ++a) {
+              const T half = S.cell_size[a] / T(2);
+              const double lo = S.cell_center[a] - (double)half, hi = S.cell_center[a] + (double)half;
+              const T pl = S.pml[a][0], pr = S.pml[a][1];
+              const double x = xs[a][(size_t)id[a]];
+              if ((pl > T(0) && x < lo + (double)pl) || (pr > T(0) && x > hi - (double)pr)) in_pml = true;
+            }
+            if (in_pml) p.sigma.at(ix, iy, iz) = T(0);
+          }
+  }
+  Arr3<T> chi1;
+  chi1.alloc(S.N[0], S.N[1], S.N[2]);
+  for (auto& p : S.poles) {
+    const T c = p.c.is_drude ? (T)(p.c.gamma1_inv * p.c.drude_coeff / 2) : (T)(p.c.gamma1_inv * p.c.sigma_omega0_dt_sq / 2);
+    for (size_t q = 0; q < chi1.d.size(); ++q) chi1.d[q] = chi1.d[q] + p.sigma.d[q] * c;
+  }
+  T mx = T(0);
+  for (T v : chi1.d) mx = std::max(mx, std::abs(v));
+  if (!(mx > T(0))) return;
+  if (!S.eps_is_array) {
+    for (int d = 0; d < 3; ++d) { S.eps_inv_a[d].alloc(S.N[0], S.N[1], S.N[2]); std::fill(S.eps_inv_a[d].d.begin(), S.eps_inv_a[d].d.end(), S.eps_inv); }
+    S.eps_is_array = true;
+  }
+  for (size_t q = 0; q < chi1.d.size(); ++q) {
+    const T c1 = chi1.d[q];
+    if (c1 == T(0)) continue;
+    for (int d = 0; d < 3; ++d) { T& e = S.eps_inv_a[d].d[q]; e = e / (T(1) + e * c1); }
+  }
+}
+
+// chi3 painting (Geometry.jl:610-635): centre grid, last -> first, objects without chi3 paint nothing
+template <class SimT>
+void chi3_from_geometry(SimT& S, int nobj, const double* flat, const double* chi3_vals, const int* has_chi3) {
+  using T = std::remove_reference_t<decltype(S.dt)>;
+  bool any = false;
+  for (int q = 0; q < nobj; ++q) any = any || has_chi3[q];
+  if (!any) return;
+  std::vector<GObj> objs;
+  parse_objects(flat, nobj, objs);
+  std::vector<double> xs[3];
+  comp_coords(S, 6 /* Center */, xs);
+  S.chi3.alloc(S.N[0], S.N[1], S.N[2]);
+  for (int gi = nobj - 1; gi >= 0; --gi) {
+    const T v = has_chi3[gi] ? (T)chi3_vals[gi] : T(0);
+    if (v != T(0)) paint_object(S, objs[(size_t)gi], xs, S.chi3, v);
+  }
+}
+}  // namespace
+
+extern "C" {
+
+// gv = GridVolume(sim, Volume(center, size), component); weight[ix,iy,iz] =
+// _compute_interpolation_weight_fast(point, ...) with point = origin + (i + gv_start - 2) * Float64(Δ)
+// (Sources.jl:52-56, 118-126).  w == nullptr: only the box is returned.  pts (optional):
+// dims[0] + dims[1] + dims[2] point coordinates (x list, y list, z list) for the caller's profile.
+void ko_source_weights(void* hv, int comp, const double* center, const double* size, int* start, int* dims, double* w, double* pts) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, {
+    int e[3];
+    S.grid_volume(center, size, comp, start, e);
+    for (int a = 0; a < 3; ++a) dims[a] = e[a] - start[a] + 1;
+    if (w || pts) {
+      double org[3], lo[3], hi[3], dl[3];
+      S.component_origin(comp, org);
+      for (int a = 0; a < 3; ++a) { lo[a] = center[a] - size[a] / 2; hi[a] = center[a] + size[a] / 2; dl[a] = (double)S.dl[a]; }
+      std::vector<double> px[3];
+      for (int a = 0; a < 3; ++a) {
+        px[a].resize((size_t)std::max(dims[a], 0));
+        for (int i = 1; i <= dims[a]; ++i) px[a][(size_t)i - 1] = org[a] + (double)(i + start[a] - 2) * dl[a];
+      }
+      if (pts) { size_t k = 0; for (int a = 0; a < 3; ++a) for (double v : px[a]) pts[k++] = v; }
+      if (w)
+        for (int iz = 0; iz < dims[2]; ++iz)
+          for (int iy = 0; iy < dims[1]; ++iy)
+            for (int ix = 0; ix < dims[0]; ++ix) {
+              const double p[3] = {px[0][(size_t)ix], px[1][(size_t)iy], px[2][(size_t)iz]};
+              w[(size_t)ix + (size_t)dims[0] * ((size_t)iy + (size_t)dims[1] * (size_t)iz)] = interp_weight(p, lo, hi, size, 3, dl);
+            }
+    }
+  });
+}
+
+// GaussianPulseSource(; fcen, fwidth, start_time, cutoff_scale) (TimeSources.jl:89-112), Float64
+// constructor arithmetic; out5 = fcen, fwidth (bandwidth), width, peak_time, cutoff
+void ko_gaussian_pulse(double fcen, double fwidth_in, double start_time, double cutoff_scale, double* out5) {
+  double width = 1.0 / fwidth_in;
+  double cutoff = width * cutoff_scale + start_time;
+  double fwidth = std::sqrt(-2.0 * std::log(1e-7)) / (width * 3.141592653589793);
+  while (std::exp(-cutoff * cutoff / (2 * width * width)) < 1e-100) cutoff *= 0.9;
+  double period = 1.0 / fcen;
+  double peak = std::nearbyint((cutoff / 2) / period) * period;
+  out5[0] = fcen; out5[1] = fwidth; out5[2] = width; out5[3] = peak; out5[4] = cutoff;
+}
+
+// auto_decimate! (Monitors.jl:33-78): D_max from the time profiles; kind 0 CW (fcen), 1 Gaussian /
+// 2 custom (fcen + fwidth / 2), values cast to T first (the profiles are stored as T).  Returns D_max
+// (1: leave the monitors alone).
+int ko_auto_decimation(void* hv, int nsrc, const int* kind, const double* fcen, const double* fwidth) {
+  Handle* h = (Handle*)hv;
+  int D = 1;
+  DISPATCH(h, {
+    using TT = std::remove_reference_t<decltype(S.dt)>;
+    double f_max = 0.0;
+    for (int q = 0; q < nsrc; ++q) {
+      if (kind[q] == 0) f_max = std::max(f_max, (double)(TT)fcen[q]);
+      else f_max = std::max(f_max, (double)(TT)fcen[q] + (double)(TT)fwidth[q] / 2);
+    }
+    if (f_max > 0) D = std::max(1, (int)std::floor(1.0 / (2.0 * f_max * (double)S.dt)));
+  });
+  return D;
+}
+
+// objs28 as ko_rasterize; nsus[q] susceptibilities of object q, sus3 = flat (omega_0, gamma, sigma)
+int ko_poles_from_geometry(void* hv, int nobj, const double* objs28, const int* nsus, const double* sus3) {
+  Handle* h = (Handle*)hv;
+  int n = 0;
+  DISPATCH(h, n = poles_from_geometry(S, nobj, objs28, nsus, sus3));
+  return n;
+}
+void ko_finish_poles(void* hv) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, finish_poles(S));
+}
+void ko_chi3_from_geometry(void* hv, int nobj, const double* objs28, const double* chi3_vals, const int* has_chi3) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, chi3_from_geometry(S, nobj, objs28, chi3_vals, has_chi3));
+}
+int ko_num_poles(void* hv) {
+  Handle* h = (Handle*)hv;
+  int n = 0;
+  DISPATCH(h, n = (int)S.poles.size());
+  return n;
+}
+// pole q: out2 = (omega_0 == 0 ? 1 : 0 [is_drude], gamma1_inv) is not enough to identify it, so the
+// caller keeps the order (unique poles in geometry order, then user poles); sigma: dense (Nx,Ny,Nz)
+void ko_get_pole_sigma(void* hv, int q, double* out) {
+  Handle* h = (Handle*)hv;
+  DISPATCH(h, { auto& a = S.poles[(size_t)q].sigma; for (size_t k = 0; k < a.d.size(); ++k) out[k] = (double)a.d[k]; });
+}
+int ko_get_chi3(void* hv, double* out) {
+  Handle* h = (Handle*)hv;
+  int ok = 0;
+  DISPATCH(h, { ok = S.chi3.ok() ? 1 : 0; if (ok && out) for (size_t k = 0; k < S.chi3.d.size(); ++k) out[k] = (double)S.chi3.d[k]; });
+  return ok;
+}
+
+}  // extern "C"
+
 // get_diffraction_efficiencies (src/Monitors/DiffractionMonitor.jl:87-165) with fft2_manual (:185-197)
 // evaluated only at the bins that are read.  The common tangential extent of the four monitors is
 // transformed.  power / prop: [nf][2M+1][2M+1] (n fastest); evanescent orders: prop 0, power 0.

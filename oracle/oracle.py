@@ -87,6 +87,19 @@ def lib():
         L.ko_mode_amplitudes.argtypes = [C.c_void_p, C.c_int, ip, dp, dp, dp, dp]
         L.ko_green3d_many.argtypes = [C.c_int, dp, C.c_int, dp, C.c_double, C.c_double, C.c_double, dp]
         L.ko_diffraction.argtypes = [C.c_void_p, C.c_int, ip, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp, ip]
+        L.ko_source_weights.argtypes = [C.c_void_p, C.c_int, dp, dp, ip, ip, dp, dp]
+        L.ko_gaussian_pulse.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, dp]
+        L.ko_auto_decimation.restype = C.c_int
+        L.ko_auto_decimation.argtypes = [C.c_void_p, C.c_int, ip, dp, dp]
+        L.ko_poles_from_geometry.restype = C.c_int
+        L.ko_poles_from_geometry.argtypes = [C.c_void_p, C.c_int, dp, ip, dp]
+        L.ko_finish_poles.argtypes = [C.c_void_p]
+        L.ko_chi3_from_geometry.argtypes = [C.c_void_p, C.c_int, dp, dp, ip]
+        L.ko_num_poles.restype = C.c_int
+        L.ko_num_poles.argtypes = [C.c_void_p]
+        L.ko_get_pole_sigma.argtypes = [C.c_void_p, C.c_int, dp]
+        L.ko_get_chi3.restype = C.c_int
+        L.ko_get_chi3.argtypes = [C.c_void_p, dp]
         _LIB = L
     return _LIB
 
@@ -145,6 +158,14 @@ def halo_ranges(src6, dst6, axis, src_upper, dst_lower):
     lib().ko_halo_ranges(sp, dp_, int(axis), int(src_upper), int(dst_lower),
                          sr.ctypes.data_as(C.POINTER(C.c_int)), dr.ctypes.data_as(C.POINTER(C.c_int)))
     return sr, dr
+
+
+def gaussian_pulse(fcen, fwidth, start_time=0.0, cutoff_scale=5.0):
+    """GaussianPulseSource constructor (TimeSources.jl:89-112): dict of fcen, fwidth, width, peak_time, cutoff (Float64)."""
+    out = np.zeros(5)
+    lib().ko_gaussian_pulse(float(fcen), float(fwidth), float(start_time), float(cutoff_scale),
+                            out.ctypes.data_as(C.POINTER(C.c_double)))
+    return dict(fcen=out[0], fwidth=out[1], width=out[2], peak_time=out[3], cutoff=out[4])
 
 
 def green3d(obs, sources, freq, eps=1.0, mu=1.0):
@@ -251,6 +272,64 @@ class OracleSim:
         assert a.shape == self.N
         flat = np.ascontiguousarray(a.transpose(2, 1, 0)).ravel()
         self.L.ko_add_pole(self.h, float(omega0), float(gamma), flat.ctypes.data_as(C.POINTER(C.c_double)))
+
+    def source_weights(self, comp, center, size):
+        """The oracle's own GridVolume + interpolation weights of a source volume (Sources.jl:43-135):
+        (start, dims, weights (nx,ny,nz) Float64, [xs, ys, zs] point coordinates)."""
+        c, cp = _d(center)
+        s, sp = _d(size)
+        st = np.zeros(3, dtype=np.int32)
+        dm = np.zeros(3, dtype=np.int32)
+        ipt = C.POINTER(C.c_int)
+        dpt = C.POINTER(C.c_double)
+        self.L.ko_source_weights(self.h, int(comp), cp, sp, st.ctypes.data_as(ipt), dm.ctypes.data_as(ipt), None, None)
+        w = np.zeros(int(dm[0]) * int(dm[1]) * int(dm[2]))
+        pts = np.zeros(int(dm.sum()))
+        self.L.ko_source_weights(self.h, int(comp), cp, sp, st.ctypes.data_as(ipt), dm.ctypes.data_as(ipt),
+                                 w.ctypes.data_as(dpt), pts.ctypes.data_as(dpt))
+        w = w.reshape(int(dm[2]), int(dm[1]), int(dm[0])).transpose(2, 1, 0)
+        xs, ys, zs = pts[:dm[0]], pts[dm[0]:dm[0] + dm[1]], pts[dm[0] + dm[1]:]
+        return [int(v) for v in st], [int(v) for v in dm], w, [xs, ys, zs]
+
+    def auto_decimation(self, kinds, fcens, fwidths):
+        """auto_decimate! (Monitors.jl:33-78): D_max from the sources' time profiles."""
+        k, kp = _i(kinds)
+        f, fp = _d(fcens)
+        w, wp = _d(fwidths)
+        return int(self.L.ko_auto_decimation(self.h, len(k), kp, fp, wp))
+
+    def poles_from_geometry(self, objects, sus_lists):
+        """_collect_unique_poles + _rasterize_pole_sigma! (Geometry.jl:1059-1125).  objects: rows of 28
+        numbers as for rasterize(); sus_lists[q] = [(omega_0, gamma, sigma), ...] of object q."""
+        o, op = _d(np.asarray(objects, dtype=np.float64).reshape(-1, 28))
+        ns, nsp = _i([len(x) for x in sus_lists])
+        flat = [v for x in sus_lists for t in x for v in t] or [0.0]
+        f, fp = _d(flat)
+        return int(self.L.ko_poles_from_geometry(self.h, o.shape[0], op, nsp, fp))
+
+    def finish_poles(self):
+        """Rest of init_polarization! (Geometry.jl:1180-1353): PML zeroing of sigma, chi1 fold into eps_inv."""
+        self.L.ko_finish_poles(self.h)
+
+    def chi3_from_geometry(self, objects, chi3_values):
+        """chi3 painting (Geometry.jl:610-635); chi3_values[q] = None or the Kerr coefficient of object q."""
+        o, op = _d(np.asarray(objects, dtype=np.float64).reshape(-1, 28))
+        v, vp = _d([0.0 if x is None else float(x) for x in chi3_values])
+        hs, hp = _i([0 if x is None else 1 for x in chi3_values])
+        self.L.ko_chi3_from_geometry(self.h, o.shape[0], op, vp, hp)
+
+    def num_poles(self):
+        return int(self.L.ko_num_poles(self.h))
+
+    def get_pole_sigma(self, q):
+        out = np.zeros(self.N[::-1])
+        self.L.ko_get_pole_sigma(self.h, int(q), out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out.transpose(2, 1, 0).astype(self.dtype)
+
+    def get_chi3(self):
+        out = np.zeros(self.N[::-1])
+        ok = self.L.ko_get_chi3(self.h, out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out.transpose(2, 1, 0).astype(self.dtype) if ok else None
 
     def add_source(self, comp, start, amp, time_kind, time_params):
         """amp: complex (nx,ny,nz) array; start: 1-based global start index of

@@ -367,3 +367,102 @@ def test_reference_susceptibility_formulas_are_the_anchor_formulas():
     dru = 1.5 + (-3.0 * (2 * np.pi * 0.5) / (w ** 2 + 1j * w * (2 * np.pi * 0.5)))
     assert np.allclose(lor, t.DISPERSIVE["lorentz"][1], rtol=1e-13)
     assert np.allclose(dru, t.DISPERSIVE["drude"][1], rtol=1e-13)
+
+
+# ---------------------------------------------------------------- the oracle derives its own inputs
+def _user_level_cases():
+    from khronos_b200 import workloads as w
+    cases = {
+        "waveguide": w.waveguide_mode(res=10),
+        "sphere": w.sphere(res=8, nfreq=3),
+        "uled": w.uled(res=12),
+        "metalens": w.metalens(nx=48, ny=48, nz=40, res=16, pml_cells=6, pillars=2, rotate=True),
+        "dipole": w.dipole(40),
+    }
+    return cases
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("name", ["waveguide", "sphere", "uled", "metalens", "dipole"])
+def test_oracle_derives_its_own_inputs(name, dtype):
+    """oracle/bridge.py builds the oracle from the user-level description only (source volumes and
+    amplitudes, geometry objects, susceptibilities, monitor volumes) and compares every derived input
+    with the product's host_prepare() bit for bit: GridVolume boxes, interpolation weights x profile,
+    raster, pole sigma + PML zeroing, chi1 fold, auto-decimation (Sources.jl:43-135, Geometry.jl:150-246,
+    1059-1353, Monitors.jl:33-78)."""
+    from khronos_b200 import workloads as w
+    from bridge import oracle_from_simulation
+    sim = w.build_simulation(_user_level_cases()[name], dtype)
+    o, mids = oracle_from_simulation(sim, check=True)
+    assert len(mids) == len(sim.dft_monitors)
+    if name == "uled":
+        assert o.num_poles() == 2 and np.count_nonzero(o.get_pole_sigma(0)) > 0
+        # chi1 fold: eps_inv inside the metal differs from the raster value 1/eps = 1
+        e = o.get_material_array("eps_inv", 0)
+        assert np.any((o.get_pole_sigma(0) != 0) & (e != 1))
+
+
+def test_oracle_input_check_detects_a_wrong_host_plan():
+    """Mutation test of the check itself: a perturbed amplitude / decimation / pole sigma / absorber ramp in
+    the product's plan must be reported."""
+    from khronos_b200 import workloads as w
+    from bridge import oracle_from_simulation
+    for mutate in ("amp", "dec", "pole", "box"):
+        sim = w.build_simulation(w.uled(res=12), np.float32)
+        sim.host_prepare()
+        if mutate == "amp":
+            sim.source_data[0]["amp"] = sim.source_data[0]["amp"] * np.complex64(1.0000001)
+        elif mutate == "dec":
+            sim.dft_monitors[3].decimation += 1
+        elif mutate == "pole":
+            w0, g_, s = sim.poles[0]
+            s = s.copy()
+            s[np.nonzero(s)[0][0], np.nonzero(s)[1][0], np.nonzero(s)[2][0]] *= np.float32(1.000001)
+            sim.poles[0] = (w0, g_, s)
+        else:
+            sim.dft_monitors[0].start = [sim.dft_monitors[0].start[0] + 1] + list(sim.dft_monitors[0].start[1:])
+        with pytest.raises(AssertionError):
+            oracle_from_simulation(sim, check=True)
+        for m in sim.dft_monitors:   # monitors are shared objects of the description
+            m.decimation = m.user_decimation
+
+
+def test_pole_sigma_overlapping_objects_follow_reference():
+    """Geometry.jl:1082-1125 _rasterize_pole_sigma!: an object without the pole is skipped, so a
+    higher-priority dielectric cladding does NOT clear the sigma of a lower-priority metal where they
+    overlap (eps_inv does take the cladding's value there); the first matching susceptibility wins."""
+    from bridge import oracle_from_simulation
+    drude = kb.DrudeSusceptibility(gamma=0.05, sigma=60.0)
+    dup = kb.LorentzianSusceptibility(omega_0=0.0, gamma=0.05, sigma=7.0)      # same key: ignored (first match)
+    geom = [kb.Object(kb.Cuboid([0, 0, 0.0], [1.0, 1.0, 1.0]), kb.Material(epsilon=2.0)),               # cladding first
+            kb.Object(kb.Cuboid([0, 0, 0.3], [2.0, 2.0, 0.4]), kb.Material(epsilon=1.0, susceptibilities=[drude, dup]))]
+    for dtype in (np.float32, np.float64):
+        sim = kb.Simulation([4, 4, 3], [0, 0, 0], 10, [kb.UniformSource(kb.ContinuousWaveSource(1.0), kb.EZ, [0, 0, 0], [0, 0, 0])],
+                            boundaries=[[0.5, 0.5]] * 3, geometry=geom, dtype=dtype)
+        o, _ = oracle_from_simulation(sim, check=True)
+        assert len(sim.poles) == 1
+        s = sim.poles[0][2]
+        xs, ys, zs = sim._coords(kb.EX)
+        X, Y, Z = np.meshgrid(xs, ys, zs, indexing="ij")
+        metal = (np.abs(X) <= 1.0) & (np.abs(Y) <= 1.0) & (np.abs(Z - 0.3) <= 0.2)
+        clad = (np.abs(X) <= 0.5) & (np.abs(Y) <= 0.5) & (np.abs(Z) <= 0.5)
+        assert np.all(s[metal] == dtype(60.0)) and np.all(s[~metal] == 0)
+        assert np.any(metal & clad)                      # the overlap exists and keeps its sigma
+        e = sim.material_arrays["eps_inv"][0]
+        both = metal & clad
+        # cladding eps (1/2) there, then the chi1 fold on top of it
+        assert np.all(e[both] < dtype(0.5)) and np.all(e[clad & ~metal] == dtype(0.5))
+
+
+def test_absorber_and_gaussian_source_inputs_derived_by_oracle():
+    from bridge import oracle_from_simulation
+    ab = [[kb.Absorber(8, 3), kb.Absorber(8, 2, 3.0)], None, [None, kb.Absorber(5, 3)]]
+    prof = lambda pt, comp: np.exp(-(pt[1] / 0.4) ** 2) * (1 + 0.2 * pt[2]) + 0 * pt[0]
+    srcs = [kb.UniformSource(kb.GaussianPulseSource(1.0, 0.35), kb.EY, [-0.3, 0, 0.05], [0, 1.5, 1.2], amplitude=0.7 - 0.2j, profile=prof),
+            kb.UniformSource(kb.GaussianPulseSource(1.3, 0.5, start_time=0.3), kb.HZ, [0.2, 0.1, 0], [1.0, 0, float("inf")])]
+    mons = [kb.FluxMonitor([0.5, 0, 0], [0, 1.0, 1.0], [0.9, 1.1]), kb.DFTMonitor(kb.HX, [0, 0, 0.2], [1, 1, 0], [1.0], 3)]
+    for dtype in (np.float32, np.float64):
+        sim = kb.Simulation([4, 3, 3], [0.1, 0, -0.05], 10, srcs, boundaries=[[0.0, 0.0], [0.6, 0.6], [0.5, 0.0]], absorbers=ab,
+                            monitors=mons, dtype=dtype)
+        o, mids = oracle_from_simulation(sim, check=True)
+        assert sim.material_arrays["sigma_D"] is not None and len(mids) == 5
