@@ -250,10 +250,17 @@ typedef struct khr_kernel_stat {
   int64_t launches;             /* launches timed since the last reset */
   double total_ms;              /* summed CUDA-event time of those launches */
   int64_t cells_per_launch;     /* voxels one launch updates */
-  double alg_bytes_per_launch;  /* SURVEY.md §8(d) bytes model for those voxels (one half-step) */
+  double alg_bytes_per_launch;  /* compulsory bytes of THIS implementation for those voxels (one half-step):
+                                 * 9w per voxel (+3w per-voxel material unless the tile is constant),
+                                 * +4w per PML axis of the voxel, + conductivity / ADE / Kerr arrays where present */
   int64_t ctas;                 /* thread blocks per launch */
   int64_t uniform_ctas;         /* of those, tiles with constant per-voxel material (loads skipped) */
+  double ref_model_bytes_per_launch; /* the reference's own byte model for the same voxels (SURVEY.md §8(d):
+                                 * 9w/12w + 10w/14w/18w on 1/2/3-PML-axis voxels): "bytes saved vs reference" */
 } khr_kernel_stat;
+/* multi-GPU: time the main stream spent waiting for the halo receive since the last profiling reset
+ * (CUDA events around the wait; only recorded while profiling is on), and the number of exchanges */
+int32_t khr_comm_stat_get(khr_ctx* ctx, double* wait_ms, int64_t* exchanges);
 int32_t khr_set_profiling(khr_ctx* ctx, int32_t mode);
 /* index in [0, count); pass out = NULL to query only the count */
 int32_t khr_kernel_stat_get(khr_ctx* ctx, int32_t index, khr_kernel_stat* out, int32_t* count);

@@ -56,6 +56,7 @@ class KernelStat(C.Structure):
         ("alg_bytes_per_launch", C.c_double),
         ("ctas", C.c_int64),
         ("uniform_ctas", C.c_int64),
+        ("ref_model_bytes_per_launch", C.c_double),
     ]
 
 
@@ -113,6 +114,7 @@ _SIGNATURES = {
     "khr_device_bytes": (_I, [_P, C.POINTER(C.c_int64)]),
     "khr_set_profiling": (_I, [_P, _I]),
     "khr_kernel_stat_get": (_I, [_P, _I, C.POINTER(KernelStat), C.POINTER(_I)]),
+    "khr_comm_stat_get": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

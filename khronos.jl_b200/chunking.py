@@ -182,32 +182,88 @@ def chunk_sigma_slice(sigma_global, start, n):
     return loc
 
 
-def z_slab_partition(grid, boundaries, nranks):
-    """One z slab per rank.
+# cost of one voxel per time step relative to an interior voxel, measured on B200 with this
+# library's kernels (profiles/r02_slab_cost_calibration.txt): a voxel inside the PML costs PML_COST
+# on its first PML axis and EXTRA_AXIS_COST more per further axis.  The reference's model is the
+# same idea with one factor, chunk_cost: "PML ~60% more expensive" (Chunking.jl:269-277).
+PML_COST = 2.2
+EXTRA_AXIS_COST = 0.4
 
-    The interior z interval is cut with the reference's rule
-    sub_s = s + round((k-1)·len/n), sub_e = s + round(k·len/n) − 1
-    (Chunking.jl:703-706); the z-PML cells stay with the first / last rank.
-    Returns a list of (z_start, nz) per rank, 1-based.
+
+def plane_costs(grid, boundaries, pml_cost=None, extra_axis_cost=None):
+    """Relative cost of every z plane (1-based plane k -> costs[k-1]) from the PML voxel census."""
+    pml_cost = PML_COST if pml_cost is None else pml_cost
+    extra = EXTRA_AXIS_COST if extra_axis_cost is None else extra_axis_cost
+    n = grid.N
+    frac = []          # PML cells per axis
+    zpml = [False] * n[2]
+    for a in range(3):
+        if boundaries is not None:
+            left_end, right_start = grid.pml_cells(a, boundaries[a][0], boundaries[a][1])
+        else:
+            left_end, right_start = 0, n[a] + 1
+        cnt = min(n[a], max(left_end, 0) + max(n[a] - right_start + 1, 0))
+        frac.append(cnt)
+        if a == 2:
+            for k in range(1, n[2] + 1):
+                zpml[k - 1] = k <= left_end or k >= right_start
+    px, py = frac[0], frac[1]
+    nx, ny = n[0], n[1]
+    c0 = (nx - px) * (ny - py)                 # cells of a plane with no x / y PML
+    c1 = px * (ny - py) + (nx - px) * py       # one of x / y
+    c2 = px * py                               # both
+    plain = c0 * 1.0 + c1 * pml_cost + c2 * (pml_cost + extra)
+    inz = c0 * pml_cost + c1 * (pml_cost + extra) + c2 * (pml_cost + 2 * extra)
+    return [inz if z else plain for z in zpml]
+
+
+def z_slab_partition(grid, boundaries, nranks, rule="cost", pml_cost=None, extra_axis_cost=None):
+    """One z slab per rank.  Returns a list of (z_start, nz) per rank, 1-based.
+
+    rule="cost" (default): the z axis is cut by cumulative per-plane cost so that every rank gets
+    the same work — the reference's assign_chunks_to_ranks partitions its chunks "into nranks bands
+    by cumulative cost" the same way (Distributed.jl:104-148, chunk_cost Chunking.jl:269-277); with
+    z-PML planes ~1.5x as expensive as the others, the end ranks get fewer planes.
+
+    rule="reference": the literal index rule of the distributed PML-grid planner — the interior z
+    interval is cut with sub_s = s + round((k-1)·len/n), sub_e = s + round(k·len/n) − 1
+    (Chunking.jl:703-706) and the z-PML cells stay with the first / last rank.
     """
     n = grid.N[2]
     if nranks <= 1:
         return [(1, n)]
-    if boundaries is not None:
-        left_end, right_start = grid.pml_cells(2, boundaries[2][0], boundaries[2][1])
-    else:
-        left_end, right_start = 0, n + 1
-    s, e = left_end + 1, right_start - 1
-    if e - s + 1 < nranks:   # interior too thin to give every rank a part: cut the whole axis
-        s, e = 1, n
-    total = e - s + 1
-    if total < nranks:
+    if n < nranks:
         raise ValueError("fewer z cells than ranks")
-    cuts = []
-    for k in range(1, nranks + 1):
-        sub_s = s + _jl_round((k - 1) * total / nranks)
-        sub_e = s + _jl_round(k * total / nranks) - 1
-        cuts.append([sub_s, sub_e])
-    cuts[0][0] = 1
-    cuts[-1][1] = n
-    return [(a, b - a + 1) for a, b in cuts]
+    if rule == "reference":
+        if boundaries is not None:
+            left_end, right_start = grid.pml_cells(2, boundaries[2][0], boundaries[2][1])
+        else:
+            left_end, right_start = 0, n + 1
+        s, e = left_end + 1, right_start - 1
+        if e - s + 1 < nranks:   # interior too thin to give every rank a part: cut the whole axis
+            s, e = 1, n
+        total = e - s + 1
+        cuts = []
+        for k in range(1, nranks + 1):
+            sub_s = s + _jl_round((k - 1) * total / nranks)
+            sub_e = s + _jl_round(k * total / nranks) - 1
+            cuts.append([sub_s, sub_e])
+        cuts[0][0] = 1
+        cuts[-1][1] = n
+        return [(a, b - a + 1) for a, b in cuts]
+    if rule != "cost":
+        raise ValueError("rule must be 'cost' or 'reference'")
+    costs = plane_costs(grid, boundaries, pml_cost, extra_axis_cost)
+    cum = [0.0]
+    for c in costs:
+        cum.append(cum[-1] + c)
+    total = cum[-1]
+    bounds = [0]     # planes 1..bounds[k] belong to ranks < k
+    for k in range(1, nranks):
+        target = total * k / nranks
+        lo = bounds[-1] + 1                  # at least one plane per rank ...
+        hi = n - (nranks - k)                # ... and enough planes left for the ranks above
+        best = min(range(lo, hi + 1), key=lambda j: (abs(cum[j] - target), j))
+        bounds.append(best)
+    bounds.append(n)
+    return [(bounds[k] + 1, bounds[k + 1] - bounds[k]) for k in range(nranks)]

@@ -48,6 +48,7 @@ struct NcclApi {
   int (*CommDestroy)(void*) = nullptr;
   int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
@@ -71,6 +72,7 @@ static void load_nccl() {
   g_nccl.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
   g_nccl.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))sym("ncclSend");
   g_nccl.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))sym("ncclRecv");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclAllReduce");
   g_nccl.GroupStart = (int (*)())sym("ncclGroupStart");
   g_nccl.GroupEnd = (int (*)())sym("ncclGroupEnd");
   g_nccl.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
@@ -123,6 +125,7 @@ struct Base {
   virtual void census(int64_t* c) = 0;
   virtual void set_profiling(int on) = 0;
   virtual int kernel_stat(int idx, khr_kernel_stat* out) = 0;
+  virtual void comm_stat(double* wait_ms, int64_t* exchanges) = 0;
   bool periodic[3] = {false, false, false};
   // complex fields (Bloch boundaries): this context holds the real parts, `partner` (owned by the
   // khr_ctx) the imaginary parts of every field; bloch_kl[a] = k * L of the axis
@@ -250,7 +253,8 @@ struct Impl : Base {
     // bytes model and live CUDA-event timing of this table's launches
     int64_t cells = 0;
     int64_t uniform_items = 0;  // tiles whose per-voxel material arrays are constant
-    double alg_bytes = 0;
+    double alg_bytes = 0;      // compulsory bytes of this implementation
+    double ref_bytes = 0;      // the reference's byte model
     std::vector<cudaEvent_t> ev;  // pairs
     size_t ev_used = 0;
     double total_ms = 0;
@@ -369,6 +373,7 @@ struct Impl : Base {
     cudaDeviceSynchronize();
     for (void* p : allocs) cudaFree(p);
     if (h_norms) cudaFreeHost(h_norms);
+    if (h_norm_nb) cudaFreeHost(h_norm_nb);
     if (h_err) cudaFreeHost(h_err);
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     cudaEventDestroy(ev_boundary); cudaEventDestroy(ev_comm); cudaEventDestroy(ev_t0); cudaEventDestroy(ev_t1);
@@ -381,6 +386,7 @@ struct Impl : Base {
     }
     for_tables([&](Table& t, int, int, int) { for (cudaEvent_t e : t.ev) cudaEventDestroy(e); t.ev.clear(); });
     for (cudaEvent_t e : sweep_tab.ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : halo_ev) cudaEventDestroy(e);
     cudaStreamDestroy(stream); cudaStreamDestroy(comm_stream);
   }
 
@@ -924,25 +930,34 @@ struct Impl : Base {
     return r;
   }
 
-  // Algorithmic bytes of one work item for one half-step, SURVEY.md §8(d):
-  //   interior 9w (+3w when the constitutive factor is a per-voxel array),
-  //   +10w / 14w / 18w on voxels inside 1 / 2 / 3 PML axes (T, U, W of the reference),
-  //   +1w per component where a material conductivity array is non-zero,
-  //   ADE voxels: 10w per pole + fPD write 3w + D r/w 6w + fPD read 3w.
-  double item_alg_bytes(int gq, const std::vector<int>* pmlc, int x0, int xw, int y0, int yh, int z0, int zn) const {
+  // Bytes one work item moves in one half-step, two models (w = sizeof(T)):
+  //  * own (roofline.achieved): the compulsory traffic of THIS implementation — every array the tile
+  //    touches once: 9w per voxel (3 curl operands read, 3 fields read + written), +3w for the per-voxel
+  //    constitutive arrays unless the tile is constant (flags bit 1: the loads are skipped), +4w per PML
+  //    axis of the voxel (W of that axis and U of the previous component, each read + written; B/D are
+  //    eliminated), conductivity arrays 3w (+6w C stage inside the PML) on the tiles that carry them,
+  //    ADE: 10w per pole voxel (sigma, P^n read, P^{n-1} read, P^{n+1} written) + D 6w on dispersive /
+  //    Kerr voxels (+1w chi3).  Neighbour planes / rows shared between tiles come from L2 and are not
+  //    counted, so the figure is a lower bound of the DRAM traffic (ncu: within 4 % of it).
+  //  * ref (bytes_vs_reference_model): SURVEY.md §8(d), what the reference's layout would move for the
+  //    same voxels — 9w (+3w per-voxel material), +10w / 14w / 18w on 1 / 2 / 3-PML-axis voxels,
+  //    +3w conductivity, ADE 10w per pole + fPD 3w + D 6w + fPD read 3w.
+  void item_bytes(int gq, const std::vector<int>* pmlc, const WorkItem& it, double* own, double* ref) const {
     const double w = sizeof(T);
+    const int x0 = it.x0, xw = it.xw, y0 = it.y0, yh = it.yh, z0 = it.z0, zn = it.zn;
     int64_t p1[3], p0[3];
     int lo[3] = {x0, y0, z0}, n[3] = {xw, yh, zn};
     for (int a = 0; a < 3; ++a) {
       p1[a] = pmlc[a][lo[a] + n[a] - 1] - pmlc[a][lo[a] - 1];
       p0[a] = n[a] - p1[a];
     }
-    int64_t c0 = p0[0] * p0[1] * p0[2];
-    int64_t c1 = p1[0] * p0[1] * p0[2] + p0[0] * p1[1] * p0[2] + p0[0] * p0[1] * p1[2];
-    int64_t c2 = p1[0] * p1[1] * p0[2] + p1[0] * p0[1] * p1[2] + p0[0] * p1[1] * p1[2];
-    int64_t c3 = p1[0] * p1[1] * p1[2];
-    double base = (m_arr[gq][0] ? 12.0 : 9.0) * w;
-    double b = (double)(c0 + c1 + c2 + c3) * base + (double)c1 * 10 * w + (double)c2 * 14 * w + (double)c3 * 18 * w;
+    const int64_t cells = (int64_t)xw * yh * zn;
+    const int64_t c1 = p1[0] * p0[1] * p0[2] + p0[0] * p1[1] * p0[2] + p0[0] * p0[1] * p1[2];
+    const int64_t c2 = p1[0] * p1[1] * p0[2] + p1[0] * p0[1] * p1[2] + p0[0] * p1[1] * p1[2];
+    const int64_t c3 = p1[0] * p1[1] * p1[2];
+    const bool marr = m_arr[gq][0] != nullptr;
+    double b_ref = (double)cells * (marr ? 12.0 : 9.0) * w + (double)c1 * 10 * w + (double)c2 * 14 * w + (double)c3 * 18 * w;
+    double b_own = (double)cells * ((marr && !(it.flags & 2)) ? 12.0 : 9.0) * w + (double)(c1 + 2 * c2 + 3 * c3) * 4 * w;
     auto count_mask = [&](const std::vector<uint8_t>& mk) {
       int64_t k = 0;
       if (mk.empty()) return k;
@@ -953,15 +968,36 @@ struct Impl : Base {
         }
       return k;
     };
-    if (has_sd[gq] && boxes_hit(sd_box[gq], x0, x0 + xw - 1, y0, y0 + yh - 1, z0, z0 + zn - 1))
-      b += (double)count_mask(sd_mask[gq]) * 3 * w;
+    if (has_sd[gq] && boxes_hit(sd_box[gq], x0, x0 + xw - 1, y0, y0 + yh - 1, z0, z0 + zn - 1)) {
+      b_ref += (double)count_mask(sd_mask[gq]) * 3 * w;
+      b_own += (double)cells * 3 * w + (Cst[gq][0] ? (double)(c1 + c2 + c3) * 6 * w : 0.0);
+    }
     if (gq == 1)
       for (size_t q = 0; q < poles.size(); ++q)
-        if (boxes_hit(poles[q].box, x0, x0 + xw - 1, y0, y0 + yh - 1, z0, z0 + zn - 1))
-          b += (double)count_mask(pole_mask[q]) * (10 + (q == 0 ? 12 : 0)) * w;
-    if (gq == 1 && chi3 && boxes_hit(chi3_box, x0, x0 + xw - 1, y0, y0 + yh - 1, z0, z0 + zn - 1))
-      b += (double)count_mask(chi3_mask) * 7 * w;  // chi3 read + D read/write
-    return b;
+        if (boxes_hit(poles[q].box, x0, x0 + xw - 1, y0, y0 + yh - 1, z0, z0 + zn - 1)) {
+          const int64_t k = count_mask(pole_mask[q]);
+          b_ref += (double)k * (10 + (q == 0 ? 12 : 0)) * w;
+          b_own += (double)k * (10 + (q == 0 ? 6 : 0)) * w;
+        }
+    if (gq == 1 && chi3 && boxes_hit(chi3_box, x0, x0 + xw - 1, y0, y0 + yh - 1, z0, z0 + zn - 1)) {
+      const int64_t k = count_mask(chi3_mask);
+      b_ref += (double)k * 7 * w;  // chi3 read + D read/write
+      b_own += (double)k * 7 * w;
+    }
+    *own = b_own; *ref = b_ref;
+  }
+  void account_tables(const std::vector<int>* pmlc) {
+    auto one = [&](Table& t, int gq) {
+      t.cells = 0; t.alg_bytes = 0; t.ref_bytes = 0; t.uniform_items = 0;
+      for (auto& it : t.items) {
+        double a, r;
+        item_bytes(gq, pmlc, it, &a, &r);
+        t.cells += (int64_t)it.xw * it.yh * it.zn;
+        t.alg_bytes += a; t.ref_bytes += r;
+        t.uniform_items += (it.flags & 2) ? 1 : 0;
+      }
+    };
+    for_tables([&](Table& t, int gq, int, int) { one(t, gq); });
   }
 
   template <class F>
@@ -987,9 +1023,11 @@ struct Impl : Base {
     collect_profile();
     profiling = on != 0;
     serial_prof = on == 3;   // mode 3: one stream, so that every kernel's event pair times it alone
+    collect_halo();
     if (on == 2 || on == 3) {
       for_tables([&](Table& t, int, int, int) { t.total_ms = 0; t.nlaunch = 0; });
       sweep_tab.total_ms = 0; sweep_tab.nlaunch = 0;
+      halo_wait_ms = 0; halo_exchanges = 0;
     }
   }
   int kernel_stat(int idx, khr_kernel_stat* out) override {
@@ -1008,6 +1046,7 @@ struct Impl : Base {
         out->total_ms = t.total_ms;
         out->cells_per_launch = t.cells;
         out->alg_bytes_per_launch = t.alg_bytes;
+        out->ref_model_bytes_per_launch = t.ref_bytes;
         out->ctas = (int64_t)t.items.size();
         out->uniform_ctas = t.uniform_items;
       }
@@ -1022,6 +1061,7 @@ struct Impl : Base {
         out->total_ms = sweep_tab.total_ms;
         out->cells_per_launch = sweep_tab.cells;
         out->alg_bytes_per_launch = sweep_tab.alg_bytes;
+        out->ref_model_bytes_per_launch = sweep_tab.ref_bytes;
         out->ctas = (int64_t)sweep_tab.items.size();
         out->uniform_ctas = sweep_tab.uniform_items;
       }
@@ -1149,10 +1189,9 @@ struct Impl : Base {
                     }
                     Table& tt = tab[gq][phase][mode];
                     tt.items.push_back(it);
-                    tt.cells += (int64_t)xw * yh * zc;
-                    const double ab = item_alg_bytes(gq, pmlc, x0, xw, y0, yh, zs, zc);
-                    tt.cost.push_back(ab);
-                    tt.alg_bytes += ab;
+                    double ab, rb;
+                    item_bytes(gq, pmlc, it, &ab, &rb);
+                    tt.cost.push_back(rb);   // launch-order heuristic only; the tables are accounted at the end
                   };
                   bool any_box = false;
                   for (auto& bx : boxes)
@@ -1251,12 +1290,6 @@ struct Impl : Base {
             std::vector<WorkItem> keep;
             for (auto& it : t.items) ((it.flags & 2) ? u.items : keep).push_back(it);
             if (u.items.empty()) continue;
-            // bytes model / cell counts follow the items (the model does not know about skipped loads)
-            const double per_cell = t.cells ? t.alg_bytes / (double)t.cells : 0.0;
-            int64_t ucells = 0;
-            for (auto& it : u.items) ucells += (int64_t)it.xw * it.yh * it.zn;
-            u.cells = ucells; u.alg_bytes = per_cell * (double)ucells;
-            t.cells -= ucells; t.alg_bytes -= u.alg_bytes;
             t.items.swap(keep);
             for (Table* q : {&t, &u}) {
               if (q->items.empty()) { q->d = nullptr; continue; }
@@ -1267,10 +1300,7 @@ struct Impl : Base {
           }
       CUDA_OK(cudaStreamSynchronize(stream));
     }
-    for_tables([&](Table& t, int, int, int) {
-      t.uniform_items = 0;
-      for (auto& it : t.items) t.uniform_items += (it.flags & 2) ? 1 : 0;
-    });
+    account_tables(pmlc);   // cells and both byte models per table, after classification / splitting
     if (sweep) {
       // chunk-major: H tiles of chunk c (PML first: they are the longer ones), then its E tiles
       sweep_tab = Table();
@@ -1287,7 +1317,7 @@ struct Impl : Base {
             const long long key = ((((long long)it.chunk + (gq == 1 ? sweep_lag : 0)) * 2 + gq) * 2 + (m == 7 ? 0 : 1)) * (1ll << 32) + (long long)q;
             all.push_back({key, it});
           }
-          sweep_tab.cells += t.cells; sweep_tab.alg_bytes += t.alg_bytes; sweep_tab.uniform_items += t.uniform_items;
+          sweep_tab.cells += t.cells; sweep_tab.alg_bytes += t.alg_bytes; sweep_tab.ref_bytes += t.ref_bytes; sweep_tab.uniform_items += t.uniform_items;
         }
       std::sort(all.begin(), all.end(), [](const std::pair<long long, WorkItem>& a, const std::pair<long long, WorkItem>& b) { return a.first < b.first; });
       for (auto& kv : all) sweep_tab.items.push_back(kv.second);
@@ -1496,9 +1526,39 @@ struct Impl : Base {
     NCCL_OK(g_nccl.GroupEnd());
     CUDA_OK(cudaEventRecord(ev_comm, comm_stream));
   }
+  // profiling: CUDA events on the main stream right before and after the wait for the halo receive;
+  // their distance is the time the next half-step could not start because the planes were not there yet
+  std::vector<cudaEvent_t> halo_ev;
+  size_t halo_ev_used = 0;
+  double halo_wait_ms = 0;
+  int64_t halo_exchanges = 0;
+  void collect_halo() {
+    for (size_t q = 0; q + 1 < halo_ev_used; q += 2) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, halo_ev[q], halo_ev[q + 1]) == cudaSuccess) { halo_wait_ms += ms; halo_exchanges += 1; }
+      else cudaGetLastError();
+    }
+    halo_ev_used = 0;
+  }
+  void comm_stat(double* wait_ms, int64_t* exchanges) override {
+    sync_all();
+    collect_halo();
+    if (wait_ms) *wait_ms = halo_wait_ms;
+    if (exchanges) *exchanges = halo_exchanges;
+  }
   void wait_halo() {
     if (g.nranks <= 1) return;
+    if (profiling) {
+      if (halo_ev_used + 2 > halo_ev.size())
+        for (int q = 0; q < 2; ++q) { cudaEvent_t e; CUDA_OK(cudaEventCreate(&e)); halo_ev.push_back(e); }
+      CUDA_OK(cudaEventRecord(halo_ev[halo_ev_used], stream));
+    }
     CUDA_OK(cudaStreamWaitEvent(stream, ev_comm, 0));
+    if (profiling) {
+      CUDA_OK(cudaEventRecord(halo_ev[halo_ev_used + 1], stream));
+      halo_ev_used += 2;
+      if (halo_ev_used >= 4096) { CUDA_OK(cudaStreamSynchronize(stream)); collect_halo(); }
+    }
   }
 
   // periodic axes: wrap the group's three components once its kernels are queued (the
@@ -1817,33 +1877,50 @@ struct Impl : Base {
   // all stale ones are reduced by one launch + one small device->host copy.
   std::vector<double> norm_cache;
   std::vector<char> norm_stale;
-  double* d_norms = nullptr;
+  static constexpr int NORM_BLOCKS = 148 * 4;
+  double* d_norms = nullptr;      // [n] results, then [n * NORM_BLOCKS] block partials
+  int* d_norm_nb = nullptr;
   double* h_norms = nullptr;
+  int* h_norm_nb = nullptr;
+  void norms_setup() {
+    const int n = (int)monitors.size();
+    if (d_norms || n == 0) return;
+    d_norms = (double*)dalloc((sizeof(double) * (size_t)n * (NORM_BLOCKS + 1) + sizeof(T) - 1) / sizeof(T));
+    d_norm_nb = (int*)dalloc((sizeof(int) * (size_t)n + sizeof(T) - 1) / sizeof(T));
+    CUDA_OK(cudaMallocHost((void**)&h_norms, sizeof(double) * n));
+    CUDA_OK(cudaMallocHost((void**)&h_norm_nb, sizeof(int) * n));
+    norm_cache.assign(n, 0.0);
+    norm_stale.assign(n, 1);
+  }
+  // reduce the monitors flagged in `which` (1 = reduce); results land in h_norms (sum of squares)
+  void norms_reduce(const std::vector<char>& which) {
+    const int n = (int)monitors.size();
+    for (int q = 0; q < n; ++q) {
+      h_norm_nb[q] = 0;
+      if (!which[q]) continue;
+      const long long ne = 2 * (long long)monitors[q].elems;
+      const int blocks = (int)std::min<long long>((ne + 255) / 256, NORM_BLOCKS);
+      h_norm_nb[q] = blocks;
+      if (blocks > 0) { sumsq_kernel<T><<<blocks, 256, 0, stream>>>(monitors[q].M, ne, d_norms + n + (size_t)q * NORM_BLOCKS); ++launches; }
+    }
+    CUDA_OK(cudaMemcpyAsync(d_norm_nb, h_norm_nb, sizeof(int) * n, cudaMemcpyHostToDevice, stream));
+    sumsq_finish_kernel<<<(n + 63) / 64, 64, 0, stream>>>(d_norms + n, d_norm_nb, NORM_BLOCKS, n, d_norms);
+    ++launches;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(h_norms, d_norms, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+  }
   void monitor_norms(double* out, int count) override {
     int n = (int)monitors.size();
     if (count != n) throw std::string("khr_monitor_norms: count must equal the number of monitors");
     if (n == 0) return;
-    if (!d_norms) {
-      d_norms = (double*)dalloc((sizeof(double) * (n + 1) + sizeof(T) - 1) / sizeof(T));
-      CUDA_OK(cudaMallocHost((void**)&h_norms, sizeof(double) * n));
-      norm_cache.assign(n, 0.0);
-      norm_stale.assign(n, 1);
-    }
+    norms_setup();
     bool any = false;
     for (int q = 0; q < n; ++q) any |= norm_stale[q] != 0;
     if (any) {
-      CUDA_OK(cudaMemsetAsync(d_norms, 0, sizeof(double) * n, stream));
-      for (int q = 0; q < n; ++q) {
-        if (!norm_stale[q]) continue;
-        long long ne = 2 * (long long)monitors[q].elems;
-        int blocks = (int)std::min<long long>((ne + 255) / 256, 148 * 4);
-        if (blocks > 0) { sumsq_kernel<T><<<blocks, 256, 0, stream>>>(monitors[q].M, ne, d_norms + q); ++launches; }
-      }
-      CUDA_OK(cudaGetLastError());
-      CUDA_OK(cudaMemcpyAsync(h_norms, d_norms, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
-      CUDA_OK(cudaStreamSynchronize(stream));
+      norms_reduce(norm_stale);
       for (int q = 0; q < n; ++q)
-        if (norm_stale[q]) { norm_cache[q] = std::sqrt(h_norms[q]); norm_stale[q] = 0; }
+        if (norm_stale[q]) { norm_cache[q] = monitors[q].elems ? std::sqrt(h_norms[q]) : 0.0; norm_stale[q] = 0; }
     }
     for (int q = 0; q < n; ++q) out[q] = norm_cache[q];
   }
@@ -1852,45 +1929,27 @@ struct Impl : Base {
   double* d_flux = nullptr;
   size_t d_flux_cap = 0;
   void flux(const int32_t* ids4, int normal_axis, double* out, int nfreq) override {
-    need_final();
-    if (normal_axis < 0 || normal_axis > 2) throw std::string("khr_flux: normal axis must be 0, 1 or 2");
-    FluxArgs<T> a;
-    a.normal = normal_axis;
-    a.t1 = normal_axis == 0 ? 1 : 0;
-    a.t2 = normal_axis == 2 ? 1 : 2;
-    a.n1 = a.n2 = 1 << 30;
-    for (int q = 0; q < 4; ++q) {
-      if (ids4[q] < 0 || ids4[q] >= (int)monitors.size()) throw std::string("khr_flux: bad monitor id");
-      const Monitor& m = monitors[ids4[q]];
-      if ((int)m.freqs.size() != nfreq) throw std::string("khr_flux: the four monitors must share the frequency list");
-      if ((q < 2) != (m.comp < 3)) throw std::string("khr_flux: monitors must be ordered E1, E2, H1, H2");
-      if (g.nranks > 1 && (m.s[2] < g.z_start || m.e[2] > g.z_start + N[2] - 1 + (g.rank == g.nranks - 1 ? 1 : 0)))
-        throw std::string("khr_flux: the monitor box is split across ranks; reduce the DFT arrays first "
-                          "(distributed.reduce_dft) and use the host formula");
-      a.M[q] = m.M;
-      for (int d = 0; d < 3; ++d) a.n[q][d] = m.n[d];
-      if (m.n[normal_axis] < 1) throw std::string("khr_flux: empty monitor box");
-      a.n1 = std::min(a.n1, m.n[a.t1]);
-      a.n2 = std::min(a.n2, m.n[a.t2]);
-    }
-    a.nf = nfreq;
-    a.dA = (double)dl[a.t1] * (double)dl[a.t2];
+    FluxArgs<T> a = surface_args("khr_flux", ids4, normal_axis, nfreq);
     if (a.n1 < 1 || a.n2 < 1) { for (int k = 0; k < nfreq; ++k) out[k] = 0.0; return; }
     const int nblocks = (int)std::min<long long>(((long long)a.n1 * a.n2 + 255) / 256, 256);
-    const size_t need = (size_t)nfreq * (nblocks + 1);
-    if (need > d_flux_cap) {
-      d_flux = (double*)dalloc((sizeof(double) * need + sizeof(T) - 1) / sizeof(T), false);
-      d_flux_cap = need;
-    }
-    flux_kernel<T><<<dim3((unsigned)nblocks, (unsigned)nfreq), 256, 0, stream>>>(a, d_flux + nfreq);
-    flux_finish_kernel<<<(nfreq + 63) / 64, 64, 0, stream>>>(d_flux + nfreq, nblocks, nfreq, d_flux);
+    double* buf = scratch_f64((size_t)nfreq * (nblocks + 1));
+    flux_kernel<T><<<dim3((unsigned)nblocks, (unsigned)nfreq), 256, 0, stream>>>(a, buf + nfreq);
+    flux_finish_kernel<<<(nfreq + 63) / 64, 64, 0, stream>>>(buf + nfreq, nblocks, nfreq, buf);
     CUDA_OK(cudaGetLastError());
     launches += 2;
-    CUDA_OK(cudaMemcpyAsync(out, d_flux, sizeof(double) * nfreq, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaMemcpyAsync(out, buf, sizeof(double) * nfreq, cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
   }
   // the four monitors of a plane as the surface-integral kernels see them (shared by khr_flux,
   // khr_near2far and khr_mode_overlap)
+  // Several ranks: every rank accumulates the planes it owns and keeps zeros elsewhere, so the sum
+  // over ranks IS the single-domain accumulator, bit for bit (x + 0 = x).  The four arrays are summed
+  // with ncclAllReduce into scratch copies (the accumulators themselves keep running) and every rank
+  // evaluates the surface integral on the complete arrays — the reference reduces the arrays with
+  // MPI.Reduce! before its host loops (Visualization.jl:325-331).  COLLECTIVE: all ranks must call
+  // the same surface function for the same monitors in the same order.
+  T* surf_scratch[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t surf_cap[4] = {0, 0, 0, 0};
   FluxArgs<T> surface_args(const char* who, const int32_t* ids4, int normal_axis, int nfreq) {
     need_final();
     if (normal_axis < 0 || normal_axis > 2) throw std::string(who) + ": normal axis must be 0, 1 or 2";
@@ -1904,9 +1963,6 @@ struct Impl : Base {
       const Monitor& m = monitors[ids4[q]];
       if ((int)m.freqs.size() != nfreq) throw std::string(who) + ": the four monitors must share the frequency list";
       if ((q < 2) != (m.comp < 3)) throw std::string(who) + ": monitors must be ordered E1, E2, H1, H2";
-      if (g.nranks > 1 && (m.s[2] < g.z_start || m.e[2] > g.z_start + N[2] - 1 + (g.rank == g.nranks - 1 ? 1 : 0)))
-        throw std::string(who) + ": the monitor box is split across ranks; reduce the DFT arrays first "
-                                 "(distributed.reduce_dft) and use the host formula";
       a.M[q] = m.M;
       for (int d = 0; d < 3; ++d) a.n[q][d] = m.n[d];
       if (m.n[normal_axis] < 1) throw std::string(who) + ": empty monitor box";
@@ -1915,6 +1971,20 @@ struct Impl : Base {
     }
     a.nf = nfreq;
     a.dA = (double)dl[a.t1] * (double)dl[a.t2];
+    if (g.nranks > 1) {
+      if (!comm) throw std::string(who) + ": nranks > 1 but khr_comm_init was not called";
+      CUDA_OK(cudaEventRecord(ev_boundary, stream));
+      CUDA_OK(cudaStreamWaitEvent(comm_stream, ev_boundary, 0));
+      for (int q = 0; q < 4; ++q) {
+        const Monitor& m = monitors[ids4[q]];
+        const size_t cnt = 2 * m.elems;
+        if (cnt > surf_cap[q]) { surf_scratch[q] = dalloc(cnt, false); surf_cap[q] = cnt; }
+        NCCL_OK(g_nccl.AllReduce(m.M, surf_scratch[q], cnt, sizeof(T) == 4 ? /*ncclFloat32*/ 7 : /*ncclFloat64*/ 8, /*ncclSum*/ 0, comm, comm_stream));
+        a.M[q] = surf_scratch[q];
+      }
+      CUDA_OK(cudaEventRecord(ev_comm, comm_stream));
+      CUDA_OK(cudaStreamWaitEvent(stream, ev_comm, 0));
+    }
     return a;
   }
   double* scratch_f64(size_t need) {
@@ -2012,19 +2082,13 @@ struct Impl : Base {
     CUDA_OK(cudaMemcpyAsync(propagating, d_prop, sizeof(int) * nout, cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
   }
-  double* d_norm = nullptr;
   double monitor_norm(int id) override {
     if (id < 0 || id >= (int)monitors.size()) throw std::string("bad monitor id");
-    if (!d_norm) d_norm = (double*)dalloc((sizeof(double) * 2 + sizeof(T) - 1) / sizeof(T));
-    CUDA_OK(cudaMemsetAsync(d_norm, 0, sizeof(double), stream));
-    long long n = 2 * (long long)monitors[id].elems;
-    int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
-    if (blocks > 0) sumsq_kernel<T><<<blocks, 256, 0, stream>>>(monitors[id].M, n, d_norm);
-    CUDA_OK(cudaGetLastError());
-    double h = 0;
-    CUDA_OK(cudaMemcpyAsync(&h, d_norm, sizeof(double), cudaMemcpyDeviceToHost, stream));
-    CUDA_OK(cudaStreamSynchronize(stream));
-    return std::sqrt(h);
+    norms_setup();
+    std::vector<char> which(monitors.size(), 0);
+    which[(size_t)id] = 1;
+    norms_reduce(which);
+    return monitors[(size_t)id].elems ? std::sqrt(h_norms[id]) : 0.0;
   }
   void sync() override {
     sync_all();
@@ -2343,6 +2407,10 @@ int32_t khr_set_profiling(khr_ctx* ctx, int32_t mode) {
 int32_t khr_kernel_stat_get(khr_ctx* ctx, int32_t index, khr_kernel_stat* out, int32_t* count) {
   NEED_CTX
   KHR_TRY({ int n = ctx->impl->kernel_stat(index, out); if (count) *count = n; })
+}
+int32_t khr_comm_stat_get(khr_ctx* ctx, double* wait_ms, int64_t* exchanges) {
+  NEED_CTX
+  KHR_TRY(ctx->impl->comm_stat(wait_ms, exchanges))
 }
 int32_t khr_device_bytes(khr_ctx* ctx, int64_t* bytes) {
   NEED_CTX

@@ -1018,9 +1018,11 @@ __global__ void flux_finish_kernel(const double* __restrict__ partial, int nbloc
   out[kf] = t;
 }
 
-// sum of squares (Simulation.jl:440-445 stop_when_dft_decayed reduces |M|^2 every step)
+// sum of squares (Simulation.jl:440-445 stop_when_dft_decayed reduces |M|^2 every step).
+// Deterministic like the flux reduction: fixed grid-stride assignment, one partial per block,
+// then one thread per monitor adds the partials in block order (no atomics).
 template <class T>
-__global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ a, long long n, double* __restrict__ out) {
+__global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ a, long long n, double* __restrict__ partial) {
   double s = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     double v = (double)a[i];
@@ -1033,8 +1035,17 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ a, lon
   if (threadIdx.x == 0) {
     double t = 0;
     for (int q = 0; q < 8; ++q) t += ws[q];
-    atomicAdd(out, t);
+    partial[blockIdx.x] = t;
   }
+}
+// out[m] = sum of partial[m * stride .. + nblocks[m]) in order; nblocks[m] == 0 leaves out[m] untouched
+__global__ void sumsq_finish_kernel(const double* __restrict__ partial, const int* __restrict__ nblocks, int stride, int nmon,
+                                    double* __restrict__ out) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= nmon || nblocks[m] == 0) return;
+  double t = 0;
+  for (int q = 0; q < nblocks[m]; ++q) t += partial[(size_t)m * stride + q];
+  out[m] = t;
 }
 
 }  // namespace khr

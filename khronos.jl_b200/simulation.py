@@ -283,7 +283,10 @@ class Simulation:
     def __init__(self, cell_size, cell_center, resolution, sources, boundaries=None, absorbers=None, geometry=None,
                  monitors=None, Courant=0.5, dtype=np.float32, device=0, rank=0, nranks=1, eps_inv=None, mu_inv=None,
                  sigma_D=None, sigma_B=None, poles=None, boundary_conditions=None, chi3=None, grid_spacing=None,
-                 rasterizer="host", subpixel_smoothing=None):
+                 rasterizer="host", subpixel_smoothing=None, slab_rule="cost"):
+        # slab_rule: how the z axis is cut into one slab per rank — "cost" (equal work, default) or
+        # "reference" (the literal index rule of the distributed PML-grid planner), chunking.z_slab_partition
+        self.slab_rule = slab_rule
         # grid_spacing: [Δx, Δy, Δz], each None (uniform) or one spacing per cell — the reference's
         # Simulation(Δx = vector, ...) (DataStructures.jl:737-739)
         self.grid = Grid(cell_size, cell_center, resolution, Courant, dtype, spacing=grid_spacing)
@@ -493,7 +496,7 @@ class Simulation:
         if getattr(self, "_host_ready", False):
             return
         g, T = self.grid, self.T
-        self.slabs = chunking.z_slab_partition(g, self.boundaries, self.nranks)
+        self.slabs = chunking.z_slab_partition(g, self.boundaries, self.nranks, rule=self.slab_rule)
         self.z_start, self.nz_local = self.slabs[self.rank]
         # boundaries (Boundaries.jl:99-164): sigma_B and sigma_D profiles are identical
         # sigma profiles per field group [H, E].  Periodic / PEC / PMC sides drop their PML
@@ -1066,8 +1069,15 @@ class Simulation:
             _lib.check(L.khr_kernel_stat_get(self.ctx, i, C.byref(st), None))
             out.append(dict(name=st.name.decode(), launches=st.launches, total_ms=st.total_ms,
                             cells_per_launch=st.cells_per_launch, alg_bytes_per_launch=st.alg_bytes_per_launch,
+                            ref_model_bytes_per_launch=st.ref_model_bytes_per_launch,
                             ctas=st.ctas, uniform_ctas=st.uniform_ctas))
         return out
+
+    def comm_stats(self):
+        """(ms the main stream waited for halo planes, number of exchanges) since the profiling reset."""
+        ms, n = C.c_double(), C.c_int64()
+        _lib.check(_lib.lib().khr_comm_stat_get(self.ctx, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def monitor_norm(self, monitor):
         v = C.c_double()

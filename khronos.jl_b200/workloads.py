@@ -57,25 +57,30 @@ def waveguide_mode(res=40, wg_length=10.0, z_stack=1):
                 sources=srcs, monitors=mons, geometry=geom)
 
 
-def sphere(res=64, radius=2.5, nfreq=21):
-    """512^3 at res 64: eps=3 ball, Ex+Hy plane sources, 6-face flux box x 21 frequencies."""
+def sphere(res=64, radius=2.5, nfreq=21, z_stack=1):
+    """512^3 at res 64: eps=3 ball, Ex+Hy plane sources, 6-face flux box x 21 frequencies.
+    `z_stack` repeats the cell (ball + flux box) along z: weak-scaling runs, one cell per GPU."""
     s = 2.0 + 1.0 + 2 * radius
-    z0 = -s / 2 + 1.0
+    z0 = -s * z_stack / 2 + 1.0
     inf = float("inf")
     cw = ContinuousWaveSource(1.0)
     srcs = [UniformSource(cw, EX, [0, 0, z0], [inf, inf, 0.0]), UniformSource(cw, HY, [0, 0, z0], [inf, inf, 0.0])]
     b = radius + 0.25
     freqs = list(np.linspace(0.8, 1.2, nfreq))
-    mons = []
-    for axis in range(3):
-        for sgn in (-1, 1):
-            c = [0.0, 0.0, 0.0]
-            c[axis] = sgn * b
-            sz = [2 * b] * 3
-            sz[axis] = 0.0
-            mons.append(FluxMonitor(c, sz, freqs))
-    return dict(name="sphere_res%d" % res, cell_size=[s, s, s], resolution=res, pml=[[1.0, 1.0]] * 3, courant=0.5,
-                sources=srcs, monitors=mons, geometry=[Object(Ball([0, 0, 0], radius), Material(epsilon=3.0))])
+    mons, geom = [], []
+    for q in range(z_stack):
+        zc = (-z_stack / 2 + 0.5 + q) * s
+        geom.append(Object(Ball([0, 0, zc], radius), Material(epsilon=3.0)))
+        for axis in range(3):
+            for sgn in (-1, 1):
+                c = [0.0, 0.0, zc]
+                c[axis] += sgn * b
+                sz = [2 * b] * 3
+                sz[axis] = 0.0
+                mons.append(FluxMonitor(c, sz, freqs))
+    name = "sphere_res%d" % res + ("" if z_stack == 1 else "_x%d" % z_stack)
+    return dict(name=name, cell_size=[s, s, s * z_stack], resolution=res, pml=[[1.0, 1.0]] * 3, courant=0.5,
+                sources=srcs, monitors=mons, geometry=geom)
 
 
 def uled(res=40, lorentz=True):
@@ -136,8 +141,9 @@ def metalens(nx=512, ny=512, nz=128, res=32, pml_cells=15, pillars=8, rotate=Fal
 WORKLOADS = {"dipole": dipole, "waveguide_mode": waveguide_mode, "sphere": sphere, "uled": uled, "metalens": metalens}
 
 
-def build_simulation(desc, dtype=np.float32, device=0, rank=0, nranks=1, rasterizer="host", subpixel_smoothing=None):
+def build_simulation(desc, dtype=np.float32, device=0, rank=0, nranks=1, rasterizer="host", subpixel_smoothing=None,
+                     slab_rule="cost"):
     return Simulation(desc["cell_size"], [0.0, 0.0, 0.0], desc["resolution"], desc["sources"], boundaries=desc["pml"],
                       geometry=desc["geometry"], monitors=desc["monitors"], Courant=desc["courant"], dtype=dtype,
                       device=device, rank=rank, nranks=nranks, rasterizer=rasterizer,
-                      subpixel_smoothing=subpixel_smoothing)
+                      subpixel_smoothing=subpixel_smoothing, slab_rule=slab_rule)

@@ -245,7 +245,7 @@ def test_z_slab_partition_rule():
     g = kb.Grid([4, 4, 16], [0, 0, 0], 10, 0.5, np.float32)
     pml = [[1.0, 1.0]] * 3
     for n in (1, 2, 3, 4, 8):
-        slabs = chunking.z_slab_partition(g, pml, n)
+        slabs = chunking.z_slab_partition(g, pml, n, rule="reference")
         assert len(slabs) == n and slabs[0][0] == 1
         assert sum(nz for _, nz in slabs) == g.N[2]
         for (a, na), (b, _) in zip(slabs[:-1], slabs[1:]):
@@ -254,6 +254,33 @@ def test_z_slab_partition_rule():
             # interior cuts follow the reference's rounding (Chunking.jl:703-706)
             iv = chunking.pml_grid_intervals(g, pml, n)[2]
             assert [s for s, _ in iv[1:-1]][1:] == [z for z, _ in slabs[1:]]
+
+
+def test_z_slab_partition_cost_balanced():
+    """Default rule: cuts by cumulative per-plane cost (the reference's assign_chunks_to_ranks partitions by
+    cumulative chunk_cost, Distributed.jl:104-148): every rank within 2 % of the mean work, contiguous
+    cover, fewer planes on the ranks that hold the z-PML; degenerate cases stay valid."""
+    for cell, res, pml, n in (([12, 6, 3.3 * 8], 40, [[1.0, 1.0]] * 3, 8), ([8, 8, 8 * 4], 16, [[1.0, 1.0]] * 3, 4),
+                              ([4, 4, 16], 10, [[1.0, 1.0]] * 3, 3), ([4, 4, 16], 10, [[0.0, 0.0], [0.5, 0.5], [0.0, 2.0]], 2),
+                              ([4, 4, 16], 10, None, 4)):
+        g = kb.Grid(cell, [0, 0, 0], res, 0.5, np.float32)
+        slabs = chunking.z_slab_partition(g, pml, n)
+        assert len(slabs) == n and slabs[0][0] == 1 and sum(nz for _, nz in slabs) == g.N[2]
+        for (a, na), (b, _) in zip(slabs[:-1], slabs[1:]):
+            assert a + na == b and na >= 1
+        costs = chunking.plane_costs(g, pml)
+        work = [sum(costs[a - 1:a - 1 + nz]) for a, nz in slabs]
+        tol = max(costs) / (sum(costs) / n)          # one plane of slack
+        assert max(work) / (sum(work) / n) < 1 + tol, (slabs, work)
+        if pml is not None and pml[2][0] > 0 and pml[2][1] > 0 and n > 2:
+            assert slabs[0][1] < slabs[1][1] and slabs[-1][1] < slabs[-2][1]
+            ref = chunking.z_slab_partition(g, pml, n, rule="reference")
+            wref = [sum(costs[a - 1:a - 1 + nz]) for a, nz in ref]
+            assert max(work) < max(wref)             # better balanced than the literal rule
+    g = kb.Grid([1, 1, 0.4], [0, 0, 0], 10, 0.5, np.float32)
+    assert chunking.z_slab_partition(g, None, 4) == [(1, 1), (2, 1), (3, 1), (4, 1)]
+    with pytest.raises(ValueError):
+        chunking.z_slab_partition(g, None, 5)
 
 
 def test_time_source_matches_oracle():
