@@ -316,6 +316,12 @@ def run_workload(name, args, ctx, steps, warmup, dtype=np.float32, e2e=True, sam
     # (reduced on the device, across ranks with one all-reduce) and the other DFT arrays are read at the end.
     e2e_rec = None
     if e2e:
+        # first-call work stays outside the window like any warm-up: the scratch of the flux reduction and, on
+        # several ranks, NCCL's lazy set-up of its all-reduce channels
+        for m in sim.monitors[:1]:
+            if isinstance(m, kb.FluxMonitor):
+                sim.get_flux(m)
+        sim.monitor_norms()
         barrier()
         t0 = time.perf_counter()
         h2d = d2h = 0

@@ -123,7 +123,7 @@ _LIB = None
 
 def build(force=False):
     """Compile libkhronos_b200.so in-tree with nvcc for sm_100a (no GPU needed)."""
-    srcs = [os.path.join(CSRC, f) for f in ("khronos_b200.cu", "step_kernels.cuh", "post_kernels.cuh", "geom_kernels.cuh")]
+    srcs = [os.path.join(CSRC, f) for f in ("khronos_b200.cu", "step_kernels.cuh", "pml_tma.cuh", "post_kernels.cuh", "geom_kernels.cuh")]
     srcs.append(os.path.join(_HERE, "..", "include", "khronos_b200.h"))
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if force or stale:

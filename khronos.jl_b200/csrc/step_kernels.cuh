@@ -44,10 +44,11 @@ struct WorkItem {
   int z0, zn;   // first local plane and number of planes marched
   int flags;    // bit0: tile may contain a source of this group
                 // bit1: the per-voxel constitutive arrays are constant over the tile (values in mu[])
+                // bits 4-6: axes (x, y, z) whose PML range the tile lies in
   int lx_log2;  // lanes along x = 1 << lx_log2 (3, 4 or 5); rows per CTA = 256 >> lx_log2
   double mu[3]; // tile-uniform m^-1 per component (exact: a Float32 value is representable)
   int chunk;    // z chunk of the item (unit of the H <-> E dependency counters)
-  int pad_;
+  int zmask;    // bit q: plane z0 + q lies in the z PML of either field group (pml_tma.cuh loads the z slabs there)
 };
 
 // compact index along a PML axis: cells 1..lo_w map to 0..lo_w-1, cells >= hi_base

@@ -33,11 +33,11 @@ def env(**kw):
                 os.environ[k] = v
 
 
-def _scene(dtype=np.float32):
+def _scene(dtype=np.float32, nx=72):
     """Piecewise-constant eps with one random block (uniform and non-uniform tiles), PML on all
     axes, a Drude slab, a plane source and a point source, two DFT monitors."""
     rng = np.random.default_rng(7)
-    N = (72, 44, 48)
+    N = (nx, 44, 48)
     eps = [np.full(N, 1.0, dtype=dtype) for _ in range(3)]
     for e in eps:
         e[:, :, 24:] = dtype(1.0 / 2.25)
@@ -47,11 +47,11 @@ def _scene(dtype=np.float32):
     kw = dict(sources=[(kb.EX, [0, 0, -0.9], [3.0, 2.0, 0], CW), (kb.HZ, [0.4, 0.2, 0.5], [0, 0, 0], CW)],
               monitors=[(kb.EX, [0, 0, 0.3], [5.0, 3.0, 0], [0.9, 1.0], 1), (kb.HY, [0, 0.1, 0], [4.0, 0, 3.0], [1.0], 2)],
               eps_inv=eps, poles=[(0.0, 0.3, sg)])
-    return ([7.2, 4.4, 4.8], 10, [1.0, 1.0, 1.0], dtype), kw
+    return ([nx / 10.0, 4.4, 4.8], 10, [1.0, 1.0, 1.0], dtype), kw
 
 
-def _run_gpu(nsteps, dtype=np.float32, **envkw):
-    args, kw = _scene(dtype)
+def _run_gpu(nsteps, dtype=np.float32, nx=72, **envkw):
+    args, kw = _scene(dtype, nx)
     with env(**envkw):
         p = Pair(*args, **kw)
     p.k.step(nsteps)
@@ -76,6 +76,15 @@ MODES = [
     dict(KHR_MULTI_STREAM=0),
     dict(KHR_ZSEG=5, KHR_ZSEG_FULL=1),
     dict(KHR_TAIL_ZN=2, KHR_SORT_ITEMS=1),
+    # the TMA-staged persistent PML kernel (pml_tma.cuh): same cascade, different data movement
+    dict(KHR_TMA=1),
+    dict(KHR_TMA=1, KHR_SPLIT_UNIFORM=0),
+    dict(KHR_TMA=1, KHR_UNIFORM_TILES=0),
+    dict(KHR_TMA=1, KHR_TMA_STAGES=2),
+    dict(KHR_TMA=1, KHR_ZSEG=3),
+    dict(KHR_TMA=0),
+    dict(KHR_LOCAL_CUTS=0),
+    dict(KHR_LOCAL_CUTS=0, KHR_TMA=1),
 ]
 
 
@@ -88,6 +97,17 @@ def baseline():
 def test_mode_is_bit_identical_to_default(baseline, mode):
     _, f0, d0 = baseline
     _, f1, d1 = _run_gpu(60, **mode)
+    for c in range(6):
+        assert np.array_equal(f0[c], f1[c]), ("field", c, rel_l2(f1[c], f0[c]))
+    for a, b in zip(d0, d1):
+        assert np.array_equal(a, b), ("dft", rel_l2(b, a))
+
+
+@pytest.mark.parametrize("mode", [dict(KHR_TMA=1), dict(KHR_TMA=1, KHR_SPLIT_UNIFORM=0)], ids=lambda m: ",".join("%s=%s" % kv for kv in m.items()))
+def test_tma_kernel_ragged_rows_bit_identical(mode):
+    """Nx = 70 (not a multiple of 4): the last thread of a row owns 2 valid cells (RAGGED variants)."""
+    _, f0, d0 = _run_gpu(40, nx=70, KHR_TMA=0)
+    _, f1, d1 = _run_gpu(40, nx=70, **mode)
     for c in range(6):
         assert np.array_equal(f0[c], f1[c]), ("field", c, rel_l2(f1[c], f0[c]))
     for a, b in zip(d0, d1):
