@@ -279,6 +279,13 @@ struct Impl : Base {
   Table sweep_tab;
   Table tab[2][2][NTAB];
   Table tma_tab[2];   // [group]: interior + PML tiles of phase 1 handled by the persistent TMA kernel (pml_tma.cuh)
+  // fused step (KHR_FUSE=1): both half-steps' TMA tiles in one launch, E one z chunk behind H (step_tma_kernel)
+  bool tma_fuse = false, skip_tma_launch = false;
+  int fuse_lag = 1;
+  Table fuse_tab;
+  unsigned long long* d_fuse_done = nullptr;
+  unsigned int* d_fuse_cnt = nullptr;
+  unsigned long long fuse_epoch = 0;
   cudaStream_t side[NSIDE] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {};
   bool axis_spec = false;  // measured slower on B200 (profiles/r01_axis_spec_pdl_ab.txt): more launches, more tails
@@ -354,6 +361,8 @@ struct Impl : Base {
     if (const char* e = getenv("KHR_SWEEP")) sweep = atoi(e) != 0;
     if (const char* e = getenv("KHR_TMA")) tma_policy = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("KHR_TMA_STAGES")) tma_stages_req = atoi(e);
+    if (const char* e = getenv("KHR_FUSE")) tma_fuse = atoi(e) != 0;
+    if (const char* e = getenv("KHR_FUSE_LAG")) fuse_lag = std::max(0, atoi(e));
     if (sweep) { pdl = true; multi_stream = false; }
     if (pdl) multi_stream = false;
     CUDA_OK(cudaHostAlloc((void**)&h_err, sizeof(int), cudaHostAllocMapped));
@@ -393,6 +402,7 @@ struct Impl : Base {
     for (cudaEvent_t e : sweep_tab.ev) cudaEventDestroy(e);
     for (cudaEvent_t e : halo_ev) cudaEventDestroy(e);
     for (int gq = 0; gq < 2; ++gq) for (cudaEvent_t e : tma_tab[gq].ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : fuse_tab.ev) cudaEventDestroy(e);
     cudaStreamDestroy(stream); cudaStreamDestroy(comm_stream);
   }
 
@@ -1040,7 +1050,7 @@ struct Impl : Base {
     };
     for_tables([&](Table& t, int, int, int) { one(t); });
     one(sweep_tab);
-    one(tma_tab[0]); one(tma_tab[1]);
+    one(tma_tab[0]); one(tma_tab[1]); one(fuse_tab);
   }
   void set_profiling(int on) override {
     sync_all();
@@ -1052,6 +1062,7 @@ struct Impl : Base {
       for_tables([&](Table& t, int, int, int) { t.total_ms = 0; t.nlaunch = 0; });
       sweep_tab.total_ms = 0; sweep_tab.nlaunch = 0;
       for (int gq = 0; gq < 2; ++gq) { tma_tab[gq].total_ms = 0; tma_tab[gq].nlaunch = 0; }
+      fuse_tab.total_ms = 0; fuse_tab.nlaunch = 0;
       halo_wait_ms = 0; halo_exchanges = 0;
     }
   }
@@ -1077,7 +1088,17 @@ struct Impl : Base {
       }
       ++k;
     });
-    for (int gq = 0; gq < 2; ++gq) {
+    if (tma_fuse && !fuse_tab.items.empty()) {
+      if (k == idx && out) {
+        memset(out, 0, sizeof(*out));
+        snprintf(out->name, sizeof(out->name), "step_tma_kernel<f32,H+E,interior+pml,%s/%s>", m_arr[0][0] ? "marr" : "mscalar", m_arr[1][0] ? "marr" : "mscalar");
+        out->launches = fuse_tab.nlaunch; out->total_ms = fuse_tab.total_ms; out->cells_per_launch = fuse_tab.cells;
+        out->alg_bytes_per_launch = fuse_tab.alg_bytes; out->ref_model_bytes_per_launch = fuse_tab.ref_bytes;
+        out->ctas = (int64_t)fuse_tab.items.size(); out->uniform_ctas = fuse_tab.uniform_items;
+      }
+      ++k;
+    }
+    for (int gq = 0; gq < 2 && !tma_fuse; ++gq) {
       Table& t = tma_tab[gq];
       if (t.items.empty()) continue;
       if (k == idx && out) {
@@ -1172,6 +1193,10 @@ struct Impl : Base {
       }
       // measured on B200 (profiles/r01_zseg_sweep.txt): 7-8 planes per CTA is the sweet spot
       zseg = (int)std::min<long long>(8, std::max<long long>(4, (tiles_xy * N[2] + 2367) / 2368));
+      // the persistent TMA kernel has no per-tile ramp to amortise and balances better with short tiles whose
+      // neighbours are in flight at the same time (halo rows / carried planes hit L2): 3-4 planes measured best
+      // (profiles/r02_tma_ab.txt: sphere 512^3 62.4 / 64.2 / 64.8 / 64.4 / 63.6 Gcells/s at 8 / 2 / 3 / 4 / 6)
+      if (tma_on) zseg = 4;
       if (const char* e = getenv("KHR_ZSEG")) zseg = std::max(1, atoi(e));
     }
     auto set_zmask = [&](WorkItem& it) {
@@ -1401,6 +1426,34 @@ struct Impl : Base {
       CUDA_OK(cudaStreamSynchronize(stream));
     }
     account_tables(pmlc);   // cells and both byte models per table, after classification / splitting
+    if (tma_fuse && (!tma_on || g.nranks > 1 || any_periodic() || in_pair || tma_tab[0].items.empty() || tma_tab[1].items.empty())) tma_fuse = false;
+    if (tma_fuse) {
+      fuse_tab = Table();
+      std::vector<std::pair<long long, WorkItem>> all;
+      std::vector<unsigned int> cnt((size_t)nchunk, 0u);
+      for (int gq = 0; gq < 2; ++gq) {
+        const Table& t = tma_tab[gq];
+        for (size_t q = 0; q < t.items.size(); ++q) {
+          WorkItem it = t.items[q];
+          it.flags |= gq << 8;
+          if (gq == 0) cnt[(size_t)it.chunk] += 1;
+          // E tiles of chunk c go `lag` chunks behind the H tiles of chunk c (lag >= 1: they wait for H(c-1), H(c) only)
+          all.push_back({(((long long)it.chunk + (gq == 1 ? fuse_lag : 0)) * 2 + gq) * (1ll << 32) + (long long)q, it});
+        }
+        fuse_tab.cells += t.cells; fuse_tab.alg_bytes += t.alg_bytes; fuse_tab.ref_bytes += t.ref_bytes; fuse_tab.uniform_items += t.uniform_items;
+      }
+      std::sort(all.begin(), all.end(), [](const std::pair<long long, WorkItem>& a, const std::pair<long long, WorkItem>& b) { return a.first < b.first; });
+      for (auto& kv : all) fuse_tab.items.push_back(kv.second);
+      const size_t bytes = fuse_tab.items.size() * sizeof(WorkItem);
+      fuse_tab.d = (WorkItem*)dalloc((bytes + sizeof(T) - 1) / sizeof(T), false);
+      CUDA_OK(cudaMemcpyAsync(fuse_tab.d, fuse_tab.items.data(), bytes, cudaMemcpyHostToDevice, stream));
+      fuse_tab.d_ctr = (unsigned int*)dalloc(64 / sizeof(T), true);
+      d_fuse_done = (unsigned long long*)dalloc(((size_t)nchunk * 8 + sizeof(T) - 1) / sizeof(T) + 8, true);
+      d_fuse_cnt = (unsigned int*)dalloc(((size_t)nchunk * 4 + sizeof(T) - 1) / sizeof(T) + 8, false);
+      CUDA_OK(cudaMemcpyAsync(d_fuse_cnt, cnt.data(), (size_t)nchunk * 4, cudaMemcpyHostToDevice, stream));
+      CUDA_OK(cudaStreamSynchronize(stream));
+      fuse_epoch = 0;
+    }
     if (sweep) {
       // chunk-major: H tiles of chunk c (PML first: they are the longer ones), then its E tiles
       sweep_tab = Table();
@@ -1502,8 +1555,7 @@ struct Impl : Base {
     }
   }
   template <int GROUP>
-  void launch_tma(const StepParams<T>& p, Table& t, cudaStream_t st) {
-    TmaParams<T> tp;
+  void fill_tma(const StepParams<T>& p, Table& t, TmaParams<T>& tp) {
     memset(&tp, 0, sizeof(tp));
     for (int d = 0; d < 3; ++d) {
       const int ia = GROUP == 0 ? d : 3 + d, jf = GROUP == 0 ? 3 + d : d;
@@ -1526,9 +1578,52 @@ struct Impl : Base {
     stages = std::min(stages, TMA_MAXSTAGES);
     if (tma_stages_req > 0) stages = std::min(stages, tma_stages_req);
     tp.nstages = stages;
-    if ((N[0] % 4) != 0) launch_tma_variant<GROUP, true>(tp, stages, st);
-    else launch_tma_variant<GROUP, false>(tp, stages, st);
+  }
+  template <int GROUP>
+  void launch_tma(const StepParams<T>& p, Table& t, cudaStream_t st) {
+    TmaParams<T> tp;
+    fill_tma<GROUP>(p, t, tp);
+    if ((N[0] % 4) != 0) launch_tma_variant<GROUP, true>(tp, tp.nstages, st);
+    else launch_tma_variant<GROUP, false>(tp, tp.nstages, st);
     ++launches;
+  }
+  template <bool RAGGED>
+  void launch_fused_variant(const TmaParams<T>& th_, const TmaParams<T>& te_, const TmaFuse& fu) {
+    if constexpr (sizeof(T) == 4) {
+      static bool attr_done = false;
+      if (!attr_done) {
+        CUDA_OK(cudaFuncSetAttribute(step_tma_kernel<T, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        attr_done = true;
+      }
+      const int grid = std::min(num_sms, th_.nitems);
+      step_tma_kernel<T, RAGGED><<<grid, TMA_THREADS, tma_smem_bytes(0, th_.nstages), stream>>>(th_, te_, fu);
+    } else {
+      throw std::string("internal: the TMA kernel is Float32 only");
+    }
+  }
+  // one time step with the fused kernel: [H tiles that need step_kernel] [step_tma_kernel] [E tiles that need step_kernel]
+  void fused_step(double t, double th) {
+    StepParams<T> ph, pe;
+    fill_params(ph, 0, t);
+    fill_params(pe, 1, th);
+    const bool mh = m_arr[0][0] != nullptr, me = m_arr[1][0] != nullptr;
+    skip_tma_launch = true;
+    launch_group<0>(ph, 1, mh);
+    TmaParams<T> th_, te_;
+    fill_tma<0>(ph, fuse_tab, th_);
+    fill_tma<1>(pe, fuse_tab, te_);
+    TmaFuse fu;
+    fuse_epoch += 1;
+    fu.done_h = d_fuse_done; fu.cnt_h = d_fuse_cnt; fu.epoch = fuse_epoch; fu.nchunk = nchunk; fu.err_flag = d_err;
+    timed(fuse_tab, true);
+    if ((N[0] % 4) != 0) launch_fused_variant<true>(th_, te_, fu); else launch_fused_variant<false>(th_, te_, fu);
+    ++launches;
+    timed(fuse_tab, false);
+    launch_group<1>(pe, 1, me);
+    skip_tma_launch = false;
+    CUDA_OK(cudaGetLastError());
+    for (auto& pl : poles) pl.cur = 1 - pl.cur;
+    epochs[0] += 1; epochs[1] += 1;
   }
 
   // ---- stepping -------------------------------------------------------------
@@ -1620,7 +1715,7 @@ struct Impl : Base {
       }
       if (st != stream) { CUDA_OK(cudaEventRecord(ev_join[side_of(m)], st)); used[m] = true; }
     }
-    if (phase == 1 && tma_on && !tma_tab[GROUP].items.empty()) {
+    if (phase == 1 && tma_on && !skip_tma_launch && !tma_tab[GROUP].items.empty()) {
       // the persistent half-step kernel goes last, on the main stream: the small launches above have their
       // CTAs placed first, its 148 CTAs take the SMs as they become free and claim work dynamically
       Table& t = tma_tab[GROUP];
@@ -1969,6 +2064,10 @@ struct Impl : Base {
         sweep_step(t, th);
         dft_update(0, t);
         dft_update(1, th);
+      } else if (tma_fuse) {
+        fused_step(t, th);
+        dft_update(0, t);
+        dft_update(1, th);
       } else {
         half_step_all(0, t);
         dft_update(0, t);
@@ -2005,6 +2104,8 @@ struct Impl : Base {
       if (d_done[gq]) CUDA_OK(cudaMemsetAsync(d_done[gq], 0, (size_t)nchunk * sizeof(unsigned long long), stream));
       epochs[gq] = 0;
     }
+    if (d_fuse_done) CUDA_OK(cudaMemsetAsync(d_fuse_done, 0, (size_t)nchunk * 8, stream));
+    fuse_epoch = 0;
     timestep = 0;
     sources_active = true;
   }
@@ -2302,7 +2403,7 @@ struct Impl : Base {
   void sync() override {
     sync_all();
     CUDA_OK(cudaStreamSynchronize(comm_stream));
-    if (h_err && *h_err) { *h_err = 0; throw std::string("a step kernel timed out waiting for its H/E dependency counters (chain mode)"); }
+    if (h_err && *h_err) { *h_err = 0; throw std::string("a step kernel timed out waiting for its H/E dependency counters (chain / sweep / fused mode)"); }
     if (last_ms < 0) {
       float ms = 0;
       if (cudaEventElapsedTime(&ms, ev_t0, ev_t1) == cudaSuccess) last_ms = ms;

@@ -83,6 +83,9 @@ MODES = [
     dict(KHR_TMA=1, KHR_TMA_STAGES=2),
     dict(KHR_TMA=1, KHR_ZSEG=3),
     dict(KHR_TMA=0),
+    dict(KHR_TMA=1, KHR_FUSE=1),
+    dict(KHR_TMA=1, KHR_FUSE=1, KHR_ZSEG=2),
+    dict(KHR_TMA=1, KHR_FUSE=1, KHR_ZSEG=3, KHR_FUSE_LAG=2),
     dict(KHR_LOCAL_CUTS=0),
     dict(KHR_LOCAL_CUTS=0, KHR_TMA=1),
 ]
