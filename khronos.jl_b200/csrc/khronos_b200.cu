@@ -230,6 +230,11 @@ struct Impl : Base {
     T ao_re = 0, ao_im = 0;
   };
   std::vector<Source> sources;
+  std::vector<SrcDesc<T>> h_src_ext[2];
+  SrcDesc<T>* d_src_ext[2] = {nullptr, nullptr};
+  size_t src_ext_cap[2] = {0, 0};
+  std::vector<PoleDesc<T>> h_pole_ext;
+  PoleDesc<T>* d_pole_ext = nullptr;
   T* Tsrc[2] = {nullptr, nullptr};  // flux accumulators of the source voxels per group
   size_t nslots[2] = {0, 0};
   struct Monitor {
@@ -273,6 +278,7 @@ struct Impl : Base {
   // fewer, no material loads) next to the remaining tiles of the class
   static constexpr int MBASE = 9, NTAB = 2 * MBASE, NSIDE = 12;
   bool split_uniform = true;
+  int full_split = 2;      // MODE 2 tiles: rows per CTA = tile rows / full_split, threads = 256 / full_split
   // sweep mode (KHR_SWEEP=1): one grid per time step with the interior + PML tiles of both half-steps
   // in z-chunk-major order (sweep_kernel, step_kernels.cuh); needs the chain mode's counters
   bool sweep = false;
@@ -693,7 +699,7 @@ struct Impl : Base {
   }
   int pole_register(double omega0, double gamma, const void* sigma) override {
     if (finalized) throw std::string("khr_pole_register after khr_finalize_plan");
-    if ((int)poles.size() >= MAXPOLE) throw std::string("too many ADE poles (max 4)");
+    if ((int)poles.size() >= 32) throw std::string("too many ADE poles (at most 32 per simulation)");
     // Susceptibility.jl:74-85 compute_ade_coefficients, Float64 then cast (Dispersive.jl:213-218)
     const double pi = 3.141592653589793;
     double dtd = (double)dt;
@@ -1211,8 +1217,10 @@ struct Impl : Base {
     for (int gq = 0; gq < 2; ++gq) {
       std::vector<Box>& boxes = gboxes[gq];
       int chunk = -1;
-      int zseg_full = 2;
+      int zseg_full = 3;   // measured (profiles/r02_mode2_ab.txt): 3 planes x half-height CTAs: uled 45.5 -> 46.3, waveguide 49.5 -> 50.5 Gcells/s
       if (const char* e = getenv("KHR_ZSEG_FULL")) zseg_full = std::max(1, atoi(e));
+      full_split = 2;
+      if (const char* e = getenv("KHR_FULL_SPLIT")) full_split = atoi(e) == 1 ? 1 : 2;
       bool local_cuts = true;   // x / y cuts only in the z ranges a box reaches (a point source no longer slices every plane)
       if (const char* e = getenv("KHR_LOCAL_CUTS")) local_cuts = atoi(e) != 0;
       for (auto& Z : zr) {
@@ -1240,13 +1248,14 @@ struct Impl : Base {
                   // Tiles that touch a source / conductivity / pole box run the heavy MODE 2 kernel
                   // (1 CTA per SM): they are cut into short z pieces so that a thin box still
                   // spreads over all SMs and does not become the critical path of the half-step.
-                  auto emit = [&](int zs, int zc) {
-                    WorkItem it{x0, xw, y0, yh, zs, zc, 0, 3 + lxi};
+                  auto emit = [&](int zs, int zc, int ys = -1, int yc = 0) {
+                    if (ys < 0) { ys = y0; yc = yh; }
+                    WorkItem it{x0, xw, ys, yc, zs, zc, 0, 3 + lxi};
                     it.chunk = chunk;
                     chunk_cnt[gq][(size_t)chunk] += 1;
                     bool extras = false;
                     for (auto& bx : boxes)
-                      if (boxes_hit(bx.b, x0, x0 + xw - 1, y0, y0 + yh - 1, zs, zs + zc - 1)) {
+                      if (boxes_hit(bx.b, x0, x0 + xw - 1, ys, ys + yc - 1, zs, zs + zc - 1)) {
                         extras = true;
                         if (bx.src) it.flags |= 1;
                       }
@@ -1270,8 +1279,14 @@ struct Impl : Base {
                   for (auto& bx : boxes)
                     if (boxes_hit(bx.b, x0, x0 + xw - 1, y0, y0 + yh - 1, z0, z0 + zn - 1)) any_box = true;
                   if (!any_box) emit(z0, zn);
-                  else
-                    for (int zs = z0; zs < z0 + zn; zs += zseg_full) emit(zs, std::min(zseg_full, z0 + zn - zs));
+                  else {
+                    // MODE 2 CTAs have 128 threads (half the rows of a tile): two of them fit an SM at ~250
+                    // registers, two independent load -> compute -> store chains per SM instead of one
+                    const int hrows = std::max(1, th / full_split);
+                    for (int zs = z0; zs < z0 + zn; zs += zseg_full)
+                      for (int ys = y0; ys < y0 + yh; ys += hrows)
+                        emit(zs, std::min(zseg_full, z0 + zn - zs), ys, std::min(hrows, y0 + yh - ys));
+                  }
                 }
               }
             }
@@ -1631,7 +1646,7 @@ struct Impl : Base {
   void launch_mode(const StepParams<T>& p, int marr, int n, cudaStream_t st) {
     if (pdl) {
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3((unsigned)n); cfg.blockDim = dim3(CTA); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+      cfg.gridDim = dim3((unsigned)n); cfg.blockDim = dim3(MODE == 2 ? CTA / full_split : CTA); cfg.dynamicSmemBytes = 0; cfg.stream = st;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -1641,8 +1656,8 @@ struct Impl : Base {
     } else if (nonuniform) {
       // non-uniform grids use the general (AXM = 7) kernels
       if constexpr (AXM == 7) {
-        if (marr) step_kernel<T, GROUP, MODE, 1, 7, true><<<n, CTA, 0, st>>>(p);
-        else step_kernel<T, GROUP, MODE, 0, 7, true><<<n, CTA, 0, st>>>(p);
+        if (marr) step_kernel<T, GROUP, MODE, 1, 7, true><<<n, MODE == 2 ? CTA / full_split : CTA, 0, st>>>(p);
+        else step_kernel<T, GROUP, MODE, 0, 7, true><<<n, MODE == 2 ? CTA / full_split : CTA, 0, st>>>(p);
       } else {
         throw std::string("internal: axis-specialised kernels have no non-uniform variant");
       }
@@ -1651,8 +1666,8 @@ struct Impl : Base {
         if constexpr (AXM == 7 && MODE < 2) step_kernel<T, GROUP, MODE, 2, 7><<<n, CTA, 0, st>>>(p);
         else throw std::string("internal: no tile-uniform variant of this kernel");
       }
-      else if (marr) step_kernel<T, GROUP, MODE, 1, AXM><<<n, CTA, 0, st>>>(p);
-      else step_kernel<T, GROUP, MODE, 0, AXM><<<n, CTA, 0, st>>>(p);
+      else if (marr) step_kernel<T, GROUP, MODE, 1, AXM><<<n, MODE == 2 ? CTA / full_split : CTA, 0, st>>>(p);
+      else step_kernel<T, GROUP, MODE, 0, AXM><<<n, MODE == 2 ? CTA / full_split : CTA, 0, st>>>(p);
     }
     ++launches;
   }
@@ -1756,18 +1771,33 @@ struct Impl : Base {
     p.mpx = MPX;
     p.mplane = (long long)MPX * N[1];
     p.cxp = cxp; p.cy = cy; p.cz = cz;
-    // sources of this group
+    // sources of this group: up to MAXSRC descriptors ride in the kernel parameters, more go through a device
+    // table refreshed on the stream before the launch (Sources.jl:330-340 loops over any number of sources)
     p.nsrc = 0;
+    std::vector<SrcDesc<T>>& hs = h_src_ext[gq];
+    hs.clear();
     for (auto& s : sources) {
       if ((s.comp >= 3) != (gq == 0)) continue;
-      if (p.nsrc >= MAXSRC) throw std::string("too many sources in one field group (max 8)");
-      SrcDesc<T>& d = p.src[p.nsrc++];
+      SrcDesc<T> d;
       d.amp = s.amp; d.slot = s.slot; d.comp = s.comp % 3;
       for (int a = 0; a < 3; ++a) { d.s[a] = s.s[a]; d.d[a] = s.d[a]; }
       T re = 0, im = 0;
       if (sources_active) eval_time_source(s.ts, t_src, &re, &im);
       d.an_re = re; d.an_im = im; d.ao_re = s.ao_re; d.ao_im = s.ao_im;
       s.ao_re = re; s.ao_im = im;
+      hs.push_back(d);
+    }
+    p.nsrc = (int)hs.size();
+    p.src_ext = nullptr;
+    if (p.nsrc <= MAXSRC) {
+      for (int q = 0; q < p.nsrc; ++q) p.src[q] = hs[(size_t)q];
+    } else {
+      if ((size_t)p.nsrc > src_ext_cap[gq]) {
+        src_ext_cap[gq] = (size_t)p.nsrc;
+        d_src_ext[gq] = (SrcDesc<T>*)dalloc((sizeof(SrcDesc<T>) * src_ext_cap[gq] + sizeof(T) - 1) / sizeof(T), false);
+      }
+      CUDA_OK(cudaMemcpyAsync(d_src_ext[gq], hs.data(), sizeof(SrcDesc<T>) * hs.size(), cudaMemcpyHostToDevice, stream));
+      p.src_ext = d_src_ext[gq];
     }
     p.dep_on = pdl ? 1 : 0;
     p.nchunk = nchunk;
@@ -1780,13 +1810,27 @@ struct Impl : Base {
     for (int d = 0; d < 3; ++d) p.Dst[d] = (gq == 1) ? Dst[d] : nullptr;
     p.Tsrc = Tsrc[gq];
     p.chi3 = (gq == 1) ? chi3 : nullptr;
-    if (gq == 1)
+    p.pole_ext = nullptr;
+    if (gq == 1) {
+      std::vector<PoleDesc<T>>& hp = h_pole_ext;
+      hp.clear();
       for (auto& pl : poles) {
-        PoleDesc<T>& d = p.pole[p.npole++];
+        PoleDesc<T> d;
         d.sigma = pl.sigma;
         for (int c = 0; c < 3; ++c) { d.Pc[c] = pl.P[pl.cur][c]; d.Pp[c] = pl.P[1 - pl.cur][c]; }
         d.g1i = pl.g1i; d.g1 = pl.g1; d.cp = pl.cp; d.cd = pl.cd;
+        hp.push_back(d);
       }
+      p.npole = (int)hp.size();
+      if (p.npole <= MAXPOLE) {
+        for (int q = 0; q < p.npole; ++q) p.pole[q] = hp[(size_t)q];
+      } else {
+        // P^n / P^{n-1} swap roles every step, so the table is refreshed with the launch
+        if (!d_pole_ext) d_pole_ext = (PoleDesc<T>*)dalloc((sizeof(PoleDesc<T>) * 32 + sizeof(T) - 1) / sizeof(T), false);
+        CUDA_OK(cudaMemcpyAsync(d_pole_ext, hp.data(), sizeof(PoleDesc<T>) * hp.size(), cudaMemcpyHostToDevice, stream));
+        p.pole_ext = d_pole_ext;
+      }
+    }
   }
 
   void update_sources_active(double t) {
@@ -2116,7 +2160,25 @@ struct Impl : Base {
     memcpy(u.b, id, 128);
     CUDA_OK(cudaSetDevice(device));
     NCCL_OK(g_nccl.CommInitRank(&comm, nranks, u, rank));
+    // which monitor boxes are cut by a slab boundary?  A rank that holds a strict, non-empty part of a box knows
+    // it; one max-all-reduce tells everybody.  Surface integrals over uncut boxes then need no array reduction:
+    // the owner's accumulators are the whole box, everybody else's are zero (khr_flux: sum of nf doubles).
+    mon_split.assign(monitors.size(), 0);
+    if (!monitors.empty() && finalized) {
+      std::vector<int> h(monitors.size(), 0);
+      for (size_t q = 0; q < monitors.size(); ++q)
+        h[q] = (mon_local_nz[q] > 0 && mon_local_nz[q] < monitors[q].n[2]) ? 1 : 0;
+      int* d = (int*)dalloc((sizeof(int) * h.size() + sizeof(T) - 1) / sizeof(T) + 4, false);
+      CUDA_OK(cudaMemcpyAsync(d, h.data(), sizeof(int) * h.size(), cudaMemcpyHostToDevice, comm_stream));
+      NCCL_OK(g_nccl.AllReduce(d, d, h.size(), /*ncclInt32*/ 2, /*ncclMax*/ 2, comm, comm_stream));
+      CUDA_OK(cudaMemcpyAsync(h.data(), d, sizeof(int) * h.size(), cudaMemcpyDeviceToHost, comm_stream));
+      CUDA_OK(cudaStreamSynchronize(comm_stream));
+      mon_split = h;
+      mon_split_known = true;
+    }
   }
+  std::vector<int> mon_split;
+  bool mon_split_known = false;
   void halo_exchange(int gq) override {
     post_halo(gq);
     wait_halo();
@@ -2239,19 +2301,30 @@ struct Impl : Base {
   double* d_flux = nullptr;
   size_t d_flux_cap = 0;
   void flux(const int32_t* ids4, int normal_axis, double* out, int nfreq) override {
-    FluxArgs<T> a = surface_args("khr_flux", ids4, normal_axis, nfreq);
-    if (a.n1 < 1 || a.n2 < 1) { for (int k = 0; k < nfreq; ++k) out[k] = 0.0; return; }
-    const int nblocks = (int)std::min<long long>(((long long)a.n1 * a.n2 + 255) / 256, 256);
+    bool local_only = false;
+    FluxArgs<T> a = surface_args("khr_flux", ids4, normal_axis, nfreq, &local_only);
+    const bool empty = a.n1 < 1 || a.n2 < 1;
+    if (empty && !local_only) { for (int k = 0; k < nfreq; ++k) out[k] = 0.0; return; }
+    const int nblocks = empty ? 1 : (int)std::min<long long>(((long long)a.n1 * a.n2 + 255) / 256, 256);
     double* buf = scratch_f64((size_t)nfreq * (nblocks + 1));
-    flux_kernel<T><<<dim3((unsigned)nblocks, (unsigned)nfreq), 256, 0, stream>>>(a, buf + nfreq);
-    flux_finish_kernel<<<(nfreq + 63) / 64, 64, 0, stream>>>(buf + nfreq, nblocks, nfreq, buf);
-    CUDA_OK(cudaGetLastError());
-    launches += 2;
+    if (empty) CUDA_OK(cudaMemsetAsync(buf, 0, sizeof(double) * nfreq, stream));
+    else {
+      flux_kernel<T><<<dim3((unsigned)nblocks, (unsigned)nfreq), 256, 0, stream>>>(a, buf + nfreq);
+      flux_finish_kernel<<<(nfreq + 63) / 64, 64, 0, stream>>>(buf + nfreq, nblocks, nfreq, buf);
+      CUDA_OK(cudaGetLastError());
+      launches += 2;
+    }
+    if (local_only) {
+      // the box lies inside one slab: that rank's result is the flux, everybody else computed 0 from empty accumulators
+      CUDA_OK(cudaEventRecord(ev_boundary, stream));
+      CUDA_OK(cudaStreamWaitEvent(comm_stream, ev_boundary, 0));
+      NCCL_OK(g_nccl.AllReduce(buf, buf, (size_t)nfreq, /*ncclFloat64*/ 8, /*ncclSum*/ 0, comm, comm_stream));
+      CUDA_OK(cudaEventRecord(ev_comm, comm_stream));
+      CUDA_OK(cudaStreamWaitEvent(stream, ev_comm, 0));
+    }
     CUDA_OK(cudaMemcpyAsync(out, buf, sizeof(double) * nfreq, cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
   }
-  // the four monitors of a plane as the surface-integral kernels see them (shared by khr_flux,
-  // khr_near2far and khr_mode_overlap)
   // Several ranks: every rank accumulates the planes it owns and keeps zeros elsewhere, so the sum
   // over ranks IS the single-domain accumulator, bit for bit (x + 0 = x).  The four arrays are summed
   // with ncclAllReduce into scratch copies (the accumulators themselves keep running) and every rank
@@ -2260,8 +2333,9 @@ struct Impl : Base {
   // the same surface function for the same monitors in the same order.
   T* surf_scratch[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t surf_cap[4] = {0, 0, 0, 0};
-  FluxArgs<T> surface_args(const char* who, const int32_t* ids4, int normal_axis, int nfreq) {
+  FluxArgs<T> surface_args(const char* who, const int32_t* ids4, int normal_axis, int nfreq, bool* local_only = nullptr) {
     need_final();
+    if (local_only) *local_only = false;
     if (normal_axis < 0 || normal_axis > 2) throw std::string(who) + ": normal axis must be 0, 1 or 2";
     FluxArgs<T> a;
     a.normal = normal_axis;
@@ -2281,6 +2355,11 @@ struct Impl : Base {
     }
     a.nf = nfreq;
     a.dA = (double)dl[a.t1] * (double)dl[a.t2];
+    if (g.nranks > 1 && local_only && mon_split_known) {
+      bool cut = false;
+      for (int q = 0; q < 4; ++q) cut = cut || mon_split[(size_t)ids4[q]] != 0;
+      if (!cut) { *local_only = true; return a; }    // the caller sums its result over the ranks instead
+    }
     if (g.nranks > 1) {
       if (!comm) throw std::string(who) + ": nranks > 1 but khr_comm_init was not called";
       CUDA_OK(cudaEventRecord(ev_boundary, stream));

@@ -34,8 +34,8 @@
 namespace khr {
 
 constexpr int XO = 31;        // storage x offset: cell ix lives at sx = ix + XO (cell 1 is 128 B aligned)
-constexpr int MAXSRC = 8;     // sources per field group handled in one launch
-constexpr int MAXPOLE = 4;    // ADE poles handled in one launch
+constexpr int MAXSRC = 8;     // sources per field group that travel in the kernel parameters (more: device table, StepParams::src_ext)
+constexpr int MAXPOLE = 4;    // ADE poles that travel in the kernel parameters (more: device table, StepParams::pole_ext)
 constexpr int CTA = 256;
 
 struct WorkItem {
@@ -106,9 +106,12 @@ struct StepParams {
   // sources
   int nsrc;
   SrcDesc<T> src[MAXSRC];
+  const SrcDesc<T>* src_ext;    // any number of sources (Sources.jl:330-340 loops over all of them): when nsrc > MAXSRC
+                                // the descriptors of this half-step live in a device table refreshed by the host
   // ADE
   int npole;
   PoleDesc<T> pole[MAXPOLE];
+  const PoleDesc<T>* pole_ext;  // any number of poles (Dispersive.jl:186-228): device table when npole > MAXPOLE (at most 32)
   T* Dst[3];          // D kept on dispersive / Kerr voxels (material layout), as the reference does
   const T* chi3;      // Kerr coefficient per voxel (material layout) or null; E group only
   T* Tsrc;            // B/D kept on source voxels (compact, one slot per (component, cell))
@@ -261,8 +264,11 @@ constexpr int min_ctas() {
 #ifndef KHR_MINCTA_M1S
 #define KHR_MINCTA_M1S 3   // single-axis PML tiles
 #endif
+#ifndef KHR_MINCTA_M2
+#define KHR_MINCTA_M2 1    // sources / conductivity / ADE tiles
+#endif
   constexpr bool single = (AXM == 1 || AXM == 2 || AXM == 4);
-  return sizeof(T) == 4 ? (MODE == 0 ? KHR_MINCTA_M0 : (MODE == 1 ? (single ? KHR_MINCTA_M1S : KHR_MINCTA_M1) : 1)) : 1;
+  return sizeof(T) == 4 ? (MODE == 0 ? KHR_MINCTA_M0 : (MODE == 1 ? (single ? KHR_MINCTA_M1S : KHR_MINCTA_M1) : KHR_MINCTA_M2)) : 1;
 }
 
 //   AXM    : bit mask of the axes whose sigma may be non-zero inside the work item (the planner
@@ -338,14 +344,14 @@ __device__ __forceinline__ void step_body(const StepParams<T>& p, const WorkItem
     }
   }
   // sources: which table entries can touch this tile (block-uniform mask)
-  unsigned srcmask = 0;
+  unsigned srcmask = 0;       // bit min(q, 31): sources >= 31 share the last bit and are box-tested per plane
   if constexpr (EXTRAS) {
     if (it.flags & 1) {
       for (int q = 0; q < p.nsrc; ++q) {
-        const SrcDesc<T>& s = p.src[q];
+        const SrcDesc<T>& s = p.src_ext ? p.src_ext[q] : p.src[q];
         bool hit = (s.s[0] < it.x0 + it.xw) && (s.s[0] + s.d[0] > it.x0) && (s.s[1] < it.y0 + it.yh) &&
                    (s.s[1] + s.d[1] > it.y0) && (s.s[2] < it.z0 + it.zn) && (s.s[2] + s.d[2] > it.z0);
-        if (hit) srcmask |= 1u << q;
+        if (hit) srcmask |= 1u << (q < 31 ? q : 31);
       }
     }
   }
@@ -390,9 +396,10 @@ __device__ __forceinline__ void step_body(const StepParams<T>& p, const WorkItem
       // the pole / conductivity arrays are read through sigma-dependent chains: make them L2 hits
       if constexpr (GROUP == 1) {
         for (int q = 0; q < p.npole; ++q) {
-          pf_l2(p.pole[q].sigma + nm);
+          const PoleDesc<T>& pl = p.pole_ext ? p.pole_ext[q] : p.pole[q];
+          pf_l2(pl.sigma + nm);
 #pragma unroll
-          for (int d = 0; d < 3; ++d) { pf_l2(p.pole[q].Pc[d] + nm); pf_l2(p.pole[q].Pp[d] + nm); }
+          for (int d = 0; d < 3; ++d) { pf_l2(pl.Pc[d] + nm); pf_l2(pl.Pp[d] + nm); }
         }
         if (p.chi3 != nullptr) pf_l2(p.chi3 + nm);
         if ((p.npole > 0 || p.chi3 != nullptr) && p.Dst[0] != nullptr) { pf_l2(p.Dst[0] + nm); pf_l2(p.Dst[1] + nm); pf_l2(p.Dst[2] + nm); }
@@ -572,7 +579,7 @@ __device__ __forceinline__ void step_body(const StepParams<T>& p, const WorkItem
           for (int e = 0; e < 4; ++e) { so[d][e] = T(0); sn[d][e] = T(0); sd[d][e] = T(0); }
         V4<T> c0 = zero4<T>(), c1 = zero4<T>(), c2 = zero4<T>();
         bool has_sd = false, use_c = false;
-        bool pol_on[MAXPOLE];
+        unsigned polmask = 0;      // bit q: pole q is present in one of the thread's 4 cells
         bool pol_any = false;
         bool disp[4] = {false, false, false, false};  // cell carries a pole or a Kerr coefficient: D is kept
         V4<T> c3 = zero4<T>();                         // chi3 of the 4 cells
@@ -587,8 +594,8 @@ __device__ __forceinline__ void step_body(const StepParams<T>& p, const WorkItem
           // sources (Sources.jl:355-356): S = real(a(t) * A[x])
           if (srcmask != 0) {
             for (int q = 0; q < p.nsrc; ++q) {
-              if (!((srcmask >> q) & 1u)) continue;
-              const SrcDesc<T>& s = p.src[q];
+              if (!((srcmask >> (q < 31 ? q : 31)) & 1u)) continue;
+              const SrcDesc<T>& s = p.src_ext ? p.src_ext[q] : p.src[q];
               const int ly = iy - s.s[1], lz = iz - s.s[2];
               if (ly < 0 || ly >= s.d[1] || lz < 0 || lz >= s.d[2]) continue;
 #pragma unroll
@@ -614,26 +621,23 @@ __device__ __forceinline__ void step_body(const StepParams<T>& p, const WorkItem
 #pragma unroll
               for (int e = 0; e < 4; ++e) { disp[e] |= (c3.v[e] != T(0)); chi_any |= (c3.v[e] != T(0)); }
             }
+            for (int q = 0; q < p.npole; ++q) {
+              const PoleDesc<T>& pl = p.pole_ext ? p.pole_ext[q] : p.pole[q];
+              V4<T> sg = ld4(pl.sigma + mbase);
+              if ((sg.v[0] != T(0)) || (sg.v[1] != T(0)) || (sg.v[2] != T(0)) || (sg.v[3] != T(0))) {
+                polmask |= 1u << q;
+                pol_any = true;
 #pragma unroll
-            for (int q = 0; q < MAXPOLE; ++q) {
-              pol_on[q] = false;
-              if (q < p.npole) {
-                V4<T> sg = ld4(p.pole[q].sigma + mbase);
-                pol_on[q] = (sg.v[0] != T(0)) || (sg.v[1] != T(0)) || (sg.v[2] != T(0)) || (sg.v[3] != T(0));
-                if (pol_on[q]) {
-                  pol_any = true;
+                for (int e = 0; e < 4; ++e) disp[e] |= (sg.v[e] != T(0));
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) disp[e] |= (sg.v[e] != T(0));
+                for (int d = 0; d < 3; ++d) {
+                  V4<T> pc = ld4(pl.Pc[d] + mbase), pp = ld4(pl.Pp[d] + mbase);
 #pragma unroll
-                  for (int d = 0; d < 3; ++d) {
-                    V4<T> pc = ld4(p.pole[q].Pc[d] + mbase), pp = ld4(p.pole[q].Pp[d] + mbase);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                      const T mm = (d == 0) ? KHR_M0(e) : (d == 1) ? KHR_M1(e) : KHR_M2(e);
-                      sn[d][e] -= mm * pc.v[e];
-                      so[d][e] -= mm * pp.v[e];
-                      pu[d][e] += pc.v[e];
-                    }
+                  for (int e = 0; e < 4; ++e) {
+                    const T mm = (d == 0) ? KHR_M0(e) : (d == 1) ? KHR_M1(e) : KHR_M2(e);
+                    sn[d][e] -= mm * pc.v[e];
+                    so[d][e] -= mm * pp.v[e];
+                    pu[d][e] += pc.v[e];
                   }
                 }
               }
@@ -735,10 +739,9 @@ __device__ __forceinline__ void step_body(const StepParams<T>& p, const WorkItem
           if (use_c) { st4(p.C[0] + mbase, c0); st4(p.C[1] + mbase, c1); st4(p.C[2] + mbase, c2); }
           // ADE (Dispersive.jl:25-88): P^{n+1} from P^n, P^{n-1} and the new E; written over P^{n-1}
           if constexpr (GROUP == 1) {
-#pragma unroll
-            for (int q = 0; q < MAXPOLE; ++q) {
-              if (q < p.npole && pol_on[q]) {
-                const PoleDesc<T>& pl = p.pole[q];
+            for (int q = 0; q < p.npole; ++q) {
+              if ((polmask >> q) & 1u) {
+                const PoleDesc<T>& pl = p.pole_ext ? p.pole_ext[q] : p.pole[q];
                 V4<T> sg = ld4(pl.sigma + mbase);
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {

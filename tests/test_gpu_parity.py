@@ -99,6 +99,36 @@ def test_dispersive_ade(kind):
     _check(p, 80)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_six_poles_and_twelve_sources(dtype):
+    """Any number of poles and sources, as the reference loops over all of them (Dispersive.jl:186-228,
+    Sources.jl:330-340): 6 poles (3 Drude, 3 Lorentz, partly overlapping, one touching the PML) and 12 E-group
+    + 9 H-group sources (points, lines, sheets; several hit the same tile and the same voxel) — more than the
+    4 / 8 descriptors that ride in the kernel parameters, so the device tables are exercised."""
+    N = (48, 40, 36)
+    rng = np.random.default_rng(5)
+    poles = []
+    for q in range(6):
+        sg = np.zeros(N, dtype=dtype)
+        x0, y0, z0 = 6 + 5 * q, 4 + 3 * q, 8 + 3 * q
+        sg[x0:x0 + 14, y0:y0 + 16, z0:z0 + 5] = dtype(0.4 + 0.3 * q)
+        poles.append((0.0 if q % 2 == 0 else 0.9 + 0.2 * q, 0.1 + 0.05 * q, sg))
+    srcs = []
+    for q in range(12):
+        comp = (kb.EX, kb.EY, kb.EZ)[q % 3]
+        c = [float(v) for v in rng.uniform(-1.2, 1.2, 3)]
+        size = [[0, 0, 0], [1.0, 0, 0], [0, 0.8, 0.6], [0.5, 0.5, 0]][q % 4]
+        srcs.append((comp, c, size, kb.ContinuousWaveSource(fcen=0.8 + 0.05 * q)))
+    for q in range(9):
+        comp = (kb.HX, kb.HY, kb.HZ)[q % 3]
+        c = [float(v) for v in rng.uniform(-1.0, 1.0, 3)]
+        srcs.append((comp, c, [[0, 0, 0], [0, 0.7, 0]][q % 2], kb.GaussianPulseSource(fcen=1.0 + 0.05 * q, fwidth=0.5)))
+    srcs.append((kb.EZ, srcs[0][1], [0, 0, 0], CW))      # a second source on the very same voxels as the first
+    p = Pair([4.8, 4.0, 3.6], 10, [0.6, 0.6, 0.6], dtype, poles=poles, sources=srcs,
+             monitors=[(kb.EY, [0, 0, 0.2], [3, 3, 0], [0.9, 1.1], 1), (kb.HZ, [0, 0.1, 0], [3, 0, 2.4], [1.0], 2)])
+    _check(p, 70)
+
+
 def test_random_state_single_step():
     """uniform [-1,1] initial fields (seed 1234), one step, no sources."""
     rng = np.random.default_rng(1234)
