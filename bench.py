@@ -344,6 +344,7 @@ def run_workload(name, args, ctx, steps, warmup, dtype=np.float32, e2e=True, sam
                            "get_flux (device reduction) / DFT arrays read at the end"}
     census = sim.voxel_census()
     dev_bytes = sim.device_bytes()
+    gk, gr = sim.graph_info()
     cfg = config_of(desc, sim, world, rast, smooth, dtype)
     sim.close()
     if rank != 0:
@@ -387,6 +388,8 @@ def run_workload(name, args, ctx, steps, warmup, dtype=np.float32, e2e=True, sam
            "details": {"voxel_census_0123_pml_axes": census, "device_bytes": dev_bytes, "prepare_s": t_prep,
                        "dft_decimation": decs[0] if decs else None, "dft_updates_in_window": dft_updates,
                        "warmup_requested": warmup, "warmup_run": w_al, "slabs": [list(s) for s in sim.slabs],
+                       "cuda_graph": {"kernels_per_step_graph": gk, "replays": gr,
+                                      "host_launches_per_step": 1 if gk else None},
                        "ms_per_step_serialised_with_kernel_events": ms_profiled / steps,
                        "kernels": [{k: s[k] for k in ("name", "launches", "total_ms", "ctas", "uniform_ctas", "alg_bytes_per_launch")} for s in stats]},
            "window": (t_win0, t_win1)}

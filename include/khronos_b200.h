@@ -261,6 +261,9 @@ typedef struct khr_kernel_stat {
 /* multi-GPU: time the main stream spent waiting for the halo receive since the last profiling reset
  * (CUDA events around the wait; only recorded while profiling is on), and the number of exchanges */
 int32_t khr_comm_stat_get(khr_ctx* ctx, double* wait_ms, int64_t* exchanges);
+/* khr_step can replay a CUDA graph of one time step (single GPU; the reference captures graphs of its
+ * step too, Kernels.jl:99-145) when KHR_GRAPH=1 is set: kernels in the graph (0 = no graph in use) and replays so far. */
+int32_t khr_graph_info(khr_ctx* ctx, int64_t* kernels_per_graph, int64_t* replays);
 int32_t khr_set_profiling(khr_ctx* ctx, int32_t mode);
 /* index in [0, count); pass out = NULL to query only the count */
 int32_t khr_kernel_stat_get(khr_ctx* ctx, int32_t index, khr_kernel_stat* out, int32_t* count);

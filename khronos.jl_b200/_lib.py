@@ -115,6 +115,7 @@ _SIGNATURES = {
     "khr_set_profiling": (_I, [_P, _I]),
     "khr_kernel_stat_get": (_I, [_P, _I, C.POINTER(KernelStat), C.POINTER(_I)]),
     "khr_comm_stat_get": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "khr_graph_info": (_I, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

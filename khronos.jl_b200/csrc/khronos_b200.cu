@@ -127,6 +127,7 @@ struct Base {
   virtual void set_profiling(int on) = 0;
   virtual int kernel_stat(int idx, khr_kernel_stat* out) = 0;
   virtual void comm_stat(double* wait_ms, int64_t* exchanges) = 0;
+  virtual void graph_info(int64_t* kernels_per_graph, int64_t* replays) = 0;
   bool periodic[3] = {false, false, false};
   // complex fields (Bloch boundaries): this context holds the real parts, `partner` (owned by the
   // khr_ctx) the imaginary parts of every field; bloch_kl[a] = k * L of the axis
@@ -278,6 +279,19 @@ struct Impl : Base {
   // fewer, no material loads) next to the remaining tiles of the class
   static constexpr int MBASE = 9, NTAB = 2 * MBASE, NSIDE = 12;
   bool split_uniform = true;
+  // CUDA graph of one time step (single GPU): the kernels of both half-steps on their streams are captured once;
+  // per step only the MODE 2 kernel nodes get new parameters (source amplitudes, P^n / P^{n-1} pointers) and the
+  // graph is replayed — one host launch per step instead of 6-8 launches + ~10 event operations.  The reference
+  // captures CUDA graphs of its step for the same reason (Kernels.jl:99-145).  Bit-identical; on B200 the host is
+  // not the limiter of this path (it runs several steps ahead of the device), and the replayed graph loses the
+  // stream priorities that put the PML kernels first, so it measures slower and stays opt-in.
+  bool graph_on = false, capturing = false;   // measured (profiles/r02_graph_ab.txt): replay is 3-5 % slower than the direct launches -> opt-in, KHR_GRAPH=1
+  cudaGraph_t step_graph = nullptr;
+  cudaGraphExec_t step_gexec = nullptr;
+  struct DynNode { cudaGraphNode_t node; int gq; const WorkItem* items; cudaKernelNodeParams kp; };
+  std::vector<DynNode> dyn_nodes;
+  int64_t graph_kernels = 0, graph_replays = 0;
+  int plain_steps_done = 0;
   int full_split = 2;      // MODE 2 tiles: rows per CTA = tile rows / full_split, threads = 256 / full_split
   // sweep mode (KHR_SWEEP=1): one grid per time step with the interior + PML tiles of both half-steps
   // in z-chunk-major order (sweep_kernel, step_kernels.cuh); needs the chain mode's counters
@@ -368,6 +382,7 @@ struct Impl : Base {
     if (const char* e = getenv("KHR_TMA")) tma_policy = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("KHR_TMA_STAGES")) tma_stages_req = atoi(e);
     if (const char* e = getenv("KHR_FUSE")) tma_fuse = atoi(e) != 0;
+    if (const char* e = getenv("KHR_GRAPH")) graph_on = atoi(e) != 0;
     if (const char* e = getenv("KHR_FUSE_LAG")) fuse_lag = std::max(0, atoi(e));
     if (sweep) { pdl = true; multi_stream = false; }
     if (pdl) multi_stream = false;
@@ -397,6 +412,8 @@ struct Impl : Base {
     if (h_err) cudaFreeHost(h_err);
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     cudaEventDestroy(ev_boundary); cudaEventDestroy(ev_comm); cudaEventDestroy(ev_t0); cudaEventDestroy(ev_t1);
+    if (step_gexec) cudaGraphExecDestroy(step_gexec);
+    if (step_graph) cudaGraphDestroy(step_graph);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_pair_a) cudaEventDestroy(ev_pair_a);
     if (ev_pair_b) cudaEventDestroy(ev_pair_b);
@@ -1669,6 +1686,17 @@ struct Impl : Base {
       else if (marr) step_kernel<T, GROUP, MODE, 1, AXM><<<n, MODE == 2 ? CTA / full_split : CTA, 0, st>>>(p);
       else step_kernel<T, GROUP, MODE, 0, AXM><<<n, MODE == 2 ? CTA / full_split : CTA, 0, st>>>(p);
     }
+    if (capturing && MODE == 2) {
+      // the node just added is the only dependency the next operation on this stream would get
+      cudaStreamCaptureStatus cs;
+      const cudaGraphNode_t* deps = nullptr;
+      size_t ndeps = 0;
+      CUDA_OK(cudaStreamGetCaptureInfo(st, &cs, nullptr, nullptr, &deps, &ndeps));
+      if (cs != cudaStreamCaptureStatusActive || ndeps != 1) throw std::string("internal: cannot identify the captured MODE 2 kernel node");
+      DynNode dn;
+      dn.node = deps[0]; dn.gq = GROUP; dn.items = p.items;
+      dyn_nodes.push_back(dn);
+    }
     ++launches;
   }
   // The kernels of a half-step phase are independent: the interior one runs on the main
@@ -1936,6 +1964,11 @@ struct Impl : Base {
   void half_step(int gq, double t_src) {
     StepParams<T> p;
     fill_params(p, gq, t_src);
+    half_step_launch(gq, p);
+    if (gq == 1) for (auto& pl : poles) pl.cur = 1 - pl.cur;
+    epochs[gq] += 1;
+  }
+  void half_step_launch(int gq, StepParams<T>& p) {
     bool marr = m_arr[gq][0] != nullptr;
     if (marr && (!m_arr[gq][1] || !m_arr[gq][2])) throw std::string("per-voxel material needs all three components");
     if (g.nranks > 1) {
@@ -1948,8 +1981,56 @@ struct Impl : Base {
       if (gq == 0) launch_group<0>(p, 1, marr); else launch_group<1>(p, 1, marr);
     }
     if (any_periodic() && !in_pair) wrap_periodic(gq);
-    if (gq == 1) for (auto& pl : poles) pl.cur = 1 - pl.cur;
-    epochs[gq] += 1;
+  }
+  // ---- one step as a CUDA graph ------------------------------------------------------------------------------
+  void graph_info(int64_t* kernels_per_graph, int64_t* replays) override {
+    if (kernels_per_graph) *kernels_per_graph = step_gexec ? graph_kernels : 0;
+    if (replays) *replays = graph_replays;
+  }
+  bool graph_usable() const {
+    return graph_on && !pdl && !sweep && !tma_fuse && g.nranks == 1 && !in_pair && !profiling;
+  }
+  void graph_step(double t, double th) {
+    StepParams<T> ph, pe;
+    fill_params(ph, 0, t);
+    fill_params(pe, 1, th);
+    if (!step_gexec) {
+      dyn_nodes.clear();
+      const int64_t l0 = launches;
+      capturing = true;
+      cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
+      if (e != cudaSuccess) { capturing = false; throw std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e); }
+      try {
+        half_step_launch(0, ph);
+        half_step_launch(1, pe);
+      } catch (...) {
+        capturing = false;
+        cudaGraph_t junk = nullptr;
+        cudaStreamEndCapture(stream, &junk);
+        if (junk) cudaGraphDestroy(junk);
+        throw;
+      }
+      capturing = false;
+      CUDA_OK(cudaStreamEndCapture(stream, &step_graph));
+      graph_kernels = launches - l0;
+      launches = l0;
+      CUDA_OK(cudaGraphInstantiate(&step_gexec, step_graph, 0));
+      for (auto& dn : dyn_nodes) CUDA_OK(cudaGraphKernelNodeGetParams(dn.node, &dn.kp));
+    }
+    for (auto& dn : dyn_nodes) {
+      StepParams<T> q = dn.gq == 0 ? ph : pe;
+      q.items = dn.items;
+      void* args[1] = {&q};
+      cudaKernelNodeParams kp = dn.kp;
+      kp.kernelParams = args;
+      kp.extra = nullptr;
+      CUDA_OK(cudaGraphExecKernelNodeSetParams(step_gexec, dn.node, &kp));
+    }
+    CUDA_OK(cudaGraphLaunch(step_gexec, stream));
+    launches += graph_kernels;
+    graph_replays += 1;
+    for (auto& pl : poles) pl.cur = 1 - pl.cur;
+    epochs[0] += 1; epochs[1] += 1;
   }
   // complex fields: the same half-step on the imaginary parts (own streams, no sources), then the
   // wrap-around copies of both parts with the Bloch phase on this context's stream
@@ -2112,11 +2193,17 @@ struct Impl : Base {
         fused_step(t, th);
         dft_update(0, t);
         dft_update(1, th);
+      } else if (graph_usable() && plain_steps_done >= 1) {
+        // H is not touched by the E half-step, so its DFT may follow the whole step
+        graph_step(t, th);
+        dft_update(0, t);
+        dft_update(1, th);
       } else {
         half_step_all(0, t);
         dft_update(0, t);
         half_step_all(1, th);
         dft_update(1, th);
+        plain_steps_done += 1;
       }
       timestep += 1;
       if (im) im->timestep = timestep;
@@ -2800,6 +2887,10 @@ int32_t khr_kernel_stat_get(khr_ctx* ctx, int32_t index, khr_kernel_stat* out, i
 int32_t khr_comm_stat_get(khr_ctx* ctx, double* wait_ms, int64_t* exchanges) {
   NEED_CTX
   KHR_TRY(ctx->impl->comm_stat(wait_ms, exchanges))
+}
+int32_t khr_graph_info(khr_ctx* ctx, int64_t* kernels_per_graph, int64_t* replays) {
+  NEED_CTX
+  KHR_TRY(ctx->impl->graph_info(kernels_per_graph, replays))
 }
 int32_t khr_device_bytes(khr_ctx* ctx, int64_t* bytes) {
   NEED_CTX

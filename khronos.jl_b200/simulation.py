@@ -1073,6 +1073,12 @@ class Simulation:
                             ctas=st.ctas, uniform_ctas=st.uniform_ctas))
         return out
 
+    def graph_info(self):
+        """(kernels in the CUDA graph of a step, graph replays so far); (0, 0) when no graph is in use."""
+        k, r = C.c_int64(), C.c_int64()
+        _lib.check(_lib.lib().khr_graph_info(self.ctx, C.byref(k), C.byref(r)))
+        return k.value, r.value
+
     def comm_stats(self):
         """(ms the main stream waited for halo planes, number of exchanges) since the profiling reset."""
         ms, n = C.c_double(), C.c_int64()

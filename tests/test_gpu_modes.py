@@ -86,6 +86,8 @@ MODES = [
     dict(KHR_TMA=1, KHR_FUSE=1),
     dict(KHR_TMA=1, KHR_FUSE=1, KHR_ZSEG=2),
     dict(KHR_TMA=1, KHR_FUSE=1, KHR_ZSEG=3, KHR_FUSE_LAG=2),
+    dict(KHR_GRAPH=1),
+    dict(KHR_GRAPH=1, KHR_TMA=1),
     dict(KHR_LOCAL_CUTS=0),
     dict(KHR_LOCAL_CUTS=0, KHR_TMA=1),
 ]
@@ -115,6 +117,26 @@ def test_tma_kernel_ragged_rows_bit_identical(mode):
         assert np.array_equal(f0[c], f1[c]), ("field", c, rel_l2(f1[c], f0[c]))
     for a, b in zip(d0, d1):
         assert np.array_equal(a, b), ("dft", rel_l2(b, a))
+
+
+def test_step_graph_is_used_and_counts_kernels():
+    """KHR_GRAPH=1: khr_step replays a CUDA graph after the first step (one host launch per step); stepping one call at a
+    time, as run() does, gives the same bits as one call for all steps."""
+    args, kw = _scene()
+    with env(KHR_GRAPH=1):
+        p = Pair(*args, **kw)
+    p.k.step(30)
+    p.k.sync()
+    k, r = p.k.graph_info()
+    assert k >= 4 and r == 29, (k, r)
+    f_batch = [p.k.get_field(c).copy() for c in range(6)]
+    p.k.reset_fields()
+    for _ in range(30):
+        p.k.step(1)
+    p.k.sync()
+    for c in range(6):
+        assert np.array_equal(f_batch[c], p.k.get_field(c)), c
+    p.k.close()
 
 
 def test_default_mode_matches_oracle(baseline):
