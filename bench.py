@@ -127,7 +127,7 @@ class ClockSampler:
 WORKLOAD_DEFAULTS = {
     # name: (rasterizer, subpixel smoothing)
     "sphere": ("device", "anisotropic"), "sphere256": ("device", "anisotropic"), "metalens_full": ("device", None),
-    "metalens": ("device", None),
+    "metalens": ("device", None), "periodic_bloch": ("device", None),
 }
 
 
@@ -145,6 +145,10 @@ def make_desc(name, nranks, sample_scale=1.0):
     if name.startswith("dipole"):
         n = int(name[6:] or 256)
         return w.dipole(max(16, int(round(n * sample_scale / 8)) * 8) if sample_scale != 1.0 else n)
+    if name == "periodic_bloch":
+        # benchmark/periodic_bloch.jl at a size that loads a B200: 16 x 16 holes at resolution 40 (640 x 640 x 180, complex fields)
+        n = 16 if sample_scale == 1.0 else 3
+        return w.periodic_bloch(res=max(8, int(round(40 * sample_scale))), n_cells=n)
     if name == "metalens":
         return w.metalens(nx=1024, ny=1024, nz=256 * nranks, res=32)
     if name == "metalens_full":
@@ -162,7 +166,7 @@ def config_of(desc, sim, n_gpus, rasterizer, smoothing, dtype):
     wb = np.dtype(dtype).itemsize
     fields_mb = 6.0 * (sim.Nx + 2) * (sim.Ny + 2) * (sim.Nz + 2) * wb / 1e6
     return {"workload": desc["name"], "grid": [sim.Nx, sim.Ny, sim.Nz], "parallelism": "z-slab x%d" % n_gpus,
-            "pml_cells": int(round(desc["pml"][0][0] * desc["resolution"])), "dft_monitors": len(sim.dft_monitors),
+            "pml_cells": int(round(max(p[0] for p in desc["pml"]) * desc["resolution"])), "dft_monitors": len(sim.dft_monitors),
             "rasterizer": rasterizer, "subpixel_smoothing": smoothing,
             "l2": "inputs larger than L2: the six field arrays alone are %.0f MB per step >> 126 MB, no flush needed" % fields_mb}
 

@@ -90,7 +90,7 @@ int32_t khr_set_material_array(khr_ctx* ctx, int32_t kind, int32_t comp, const v
 /* Geometry on the device: replaces the rasterisation loop of init_geometry
  * (Geometry.jl:450-605, _rasterize_object_yrange! :150-246: objects painted last to first inside
  * their bounding-box index ranges, earlier objects win) and _apply_subpixel_smoothing!
- * (:795-972) for scenes of spheres and cuboids, writing eps^-1 / mu^-1 / sigma_D / sigma_B
+ * (:795-972) for scenes of spheres, cuboids and cylinders, writing eps^-1 / mu^-1 / sigma_D / sigma_B
  * straight into the library's device arrays.  Shape predicates follow GeometryPrimitives.jl
  * (`in`, `bounds`, `surfpt_nearby`, `level`, `volfrac`; not vendored by the reference).
  *   objects      : priority order (index 0 wins), painted values already 1/eps etc. in dtype precision
@@ -99,13 +99,14 @@ int32_t khr_set_material_array(khr_ctx* ctx, int32_t kind, int32_t comp, const v
  *   origins      : get_component_origin (utils.jl:156-170) of Ex,Ey,Ez,Hx,Hy,Hz, 6 x (x,y,z)
  *   smoothed_out : interface voxels rewritten per E component (may be NULL)
  * Uniform grids only; before khr_finalize_plan. */
-enum { KHR_SHAPE_SPHERE = 0, KHR_SHAPE_CUBOID = 1 };
+enum { KHR_SHAPE_SPHERE = 0, KHR_SHAPE_CUBOID = 1, KHR_SHAPE_CYLINDER = 2 };
 typedef struct khr_object {
   int32_t kind;
   int32_t pad_;
   double center[3];
-  double size[3];     /* sphere: size[0] = radius; cuboid: full edge lengths along its axes */
-  double axes[9];     /* cuboid: rows = axis vectors (orthogonal; normalised by the library); all zero = identity */
+  double size[3];     /* sphere: size[0] = radius; cuboid: full edge lengths along its axes; cylinder: radius, height */
+  double axes[9];     /* cuboid: rows = axis vectors (orthogonal; normalised by the library); all zero = identity;
+                         cylinder: axes[0..2] = axis direction */
   double eps_inv[3], mu_inv[3], sigma_d[3], sigma_b[3];
 } khr_object;
 int32_t khr_geometry_rasterize(khr_ctx* ctx, const khr_object* objects, int32_t nobj, int32_t kinds_mask, int32_t smoothing,

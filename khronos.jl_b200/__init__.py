@@ -8,14 +8,14 @@ directory name carries a dot and cannot be imported directly).
 """
 from . import _lib, chunking, grid
 from .grid import EX, EY, EZ, HX, HY, HZ, Grid, interpolation_weight
-from .simulation import (Absorber, Ball, ContinuousWaveSource, Cuboid, CustomSource, DFTMonitor, DrudeSusceptibility,
+from .simulation import (Absorber, Ball, ContinuousWaveSource, Cuboid, Cylinder, CustomSource, DFTMonitor, DrudeSusceptibility,
                          FluxMonitor, GaussianPulseSource, LorentzianSusceptibility, Material, ModeMonitor, Near2FarMonitor, DiffractionMonitor,
                          Object, Simulation, UniformSource, run, run_benchmark, step, stop_when_dft_decayed, PML, Periodic, Bloch, PECBoundary, PMCBoundary)
 from ._lib import KhronosError, build
 from . import workloads
 
 __all__ = [
-    "Absorber", "Ball", "ContinuousWaveSource", "Cuboid", "CustomSource", "DFTMonitor", "DrudeSusceptibility",
+    "Absorber", "Ball", "ContinuousWaveSource", "Cuboid", "Cylinder", "CustomSource", "DFTMonitor", "DrudeSusceptibility",
     "FluxMonitor", "GaussianPulseSource", "LorentzianSusceptibility", "Material", "Object", "Simulation",
     "UniformSource", "run", "run_benchmark", "step", "stop_when_dft_decayed", "Grid", "interpolation_weight", "KhronosError", "build",
     "EX", "EY", "EZ", "HX", "HY", "HZ", "chunking", "grid", "workloads", "PML", "Periodic", "Bloch", "PECBoundary",

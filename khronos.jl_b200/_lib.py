@@ -30,7 +30,7 @@ class GridDesc(C.Structure):
     ]
 
 
-SHAPE_SPHERE, SHAPE_CUBOID = 0, 1
+SHAPE_SPHERE, SHAPE_CUBOID, SHAPE_CYLINDER = 0, 1, 2
 
 
 class KhrObject(C.Structure):

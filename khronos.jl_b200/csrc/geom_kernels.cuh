@@ -9,7 +9,7 @@
 // :795-972 (_apply_subpixel_smoothing!, _smooth_component_yrange!).  The shape predicates
 // (`in`, `bounds`, `surfpt_nearby`, `level`, `volfrac`) live in GeometryPrimitives.jl, which
 // is not vendored and not version-pinned by the reference (Project.toml has no Manifest): they
-// are restated here from that package's published definitions for Sphere and Cuboid.
+// are restated here from that package's published definitions for Sphere, Cuboid and Cylinder.
 //
 // Scheme: per Yee component grid (1) every object paints `atomicMin(owner[voxel], object index)`
 // over its bounding-box voxels — work proportional to the sum of bounding-box volumes, like the
@@ -26,7 +26,7 @@ namespace khr {
 constexpr int GEOM_NONE = 0x7f7f7f7f;   // owner value of a voxel no object covers (memset 0x7f)
 
 struct GeomObj {
-  int kind;              // 0 Sphere, 1 Cuboid
+  int kind;              // 0 Sphere, 1 Cuboid, 2 Cylinder (r[0] = radius, r[1] = half height, ax[0..2] = unit axis)
   int pad_;
   double c[3];           // centre
   double r[3];           // Sphere: r[0] = radius; Cuboid: half sizes along its axes
@@ -54,6 +54,13 @@ __device__ __forceinline__ double geom_coord(double origin, int i, T d) {
 __device__ __forceinline__ bool geom_contains(const GeomObj& o, const double (&x)[3]) {
   const double d0 = x[0] - o.c[0], d1 = x[1] - o.c[1], d2 = x[2] - o.c[2];
   if (o.kind == 0) return ((d0 * d0 + d1 * d1) + d2 * d2) <= o.r[0] * o.r[0];
+  if (o.kind == 2) {
+    // Cylinder: p = (x - c) . a; |p| <= h/2 and sum(abs2, (x - c) - p a) <= r^2
+    const double p = (d0 * o.ax[0] + d1 * o.ax[1]) + d2 * o.ax[2];
+    if (fabs(p) > o.r[1]) return false;
+    const double q0 = d0 - p * o.ax[0], q1 = d1 - p * o.ax[1], q2 = d2 - p * o.ax[2];
+    return ((q0 * q0 + q1 * q1) + q2 * q2) <= o.r[0] * o.r[0];
+  }
   bool in = true;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -113,6 +120,42 @@ __device__ __forceinline__ void geom_surfpt(const GeomObj& o, const double (&x)[
     for (int k = 0; k < 3; ++k) sp[k] = o.c[k] + o.r[0] * nout[k];
     return;
   }
+  if (o.kind == 2) {
+    // Cylinder: axial coordinate p, radial vector q.  Inside: the nearer of side wall and end cap; outside the
+    // radius only: side wall; beyond a cap only: that cap; beyond both: the rim, normal from the rim point to x.
+    const double p = (d[0] * o.ax[0] + d[1] * o.ax[1]) + d[2] * o.ax[2];
+    const double q[3] = {d[0] - p * o.ax[0], d[1] - p * o.ax[1], d[2] - p * o.ax[2]};
+    const double rho = sqrt((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]);
+    const double sgp = copysign(1.0, p);
+    const double dr = o.r[0] - rho, dh = o.r[1] - fabs(p);
+    double qh[3] = {0.0, 0.0, 0.0};        // radial unit vector (any direction perpendicular to the axis on the axis itself)
+    if (rho > 0.0) { qh[0] = q[0] / rho; qh[1] = q[1] / rho; qh[2] = q[2] / rho; }
+    else {
+      const int j = fabs(o.ax[0]) <= fabs(o.ax[1]) ? (fabs(o.ax[0]) <= fabs(o.ax[2]) ? 0 : 2) : (fabs(o.ax[1]) <= fabs(o.ax[2]) ? 1 : 2);
+      double e[3] = {0.0, 0.0, 0.0};
+      e[j] = 1.0;
+      const double pe = o.ax[j];
+      double nr = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { qh[k] = e[k] - pe * o.ax[k]; nr += qh[k] * qh[k]; }
+      nr = sqrt(nr);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) qh[k] /= nr;
+    }
+    const bool side = (dr >= 0.0 && dh >= 0.0) ? (dr < dh) : (dh >= 0.0);   // inside: nearer surface; outside: radial overshoot only
+    const bool cap = (dr >= 0.0 && dh >= 0.0) ? !side : (dr >= 0.0);
+    if (side) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { sp[k] = o.c[k] + p * o.ax[k] + o.r[0] * qh[k]; nout[k] = qh[k]; }
+    } else if (cap) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { sp[k] = x[k] + (o.r[1] * sgp - p) * o.ax[k]; nout[k] = sgp * o.ax[k]; }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { sp[k] = o.c[k] + o.r[1] * sgp * o.ax[k] + o.r[0] * qh[k]; nout[k] = x[k] - sp[k]; }
+    }
+    return;
+  }
   // Cuboid with orthonormal axes (rows of ax): d' = p (x - c); n_k = sign(d'_k) * axis_k
   double dp[3], ad[3], sg[3], dl[3];
   bool isout[3], onbnd[3];
@@ -162,6 +205,12 @@ __device__ __forceinline__ void geom_surfpt(const GeomObj& o, const double (&x)[
 __device__ __forceinline__ bool geom_level_nonneg(const GeomObj& o, const double (&x)[3]) {
   const double d[3] = {x[0] - o.c[0], x[1] - o.c[1], x[2] - o.c[2]};
   if (o.kind == 0) return 1.0 - sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]) / o.r[0] >= 0.0;
+  if (o.kind == 2) {
+    // Cylinder: 1 - max(|p| / (h/2), |q| / r)
+    const double p = (d[0] * o.ax[0] + d[1] * o.ax[1]) + d[2] * o.ax[2];
+    const double q0 = d[0] - p * o.ax[0], q1 = d[1] - p * o.ax[1], q2 = d[2] - p * o.ax[2];
+    return 1.0 - fmax(fabs(p) / o.r[1], sqrt((q0 * q0 + q1 * q1) + q2 * q2) / o.r[0]) >= 0.0;
+  }
   double m = 0.0;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {

@@ -50,6 +50,7 @@ struct NcclApi {
   int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommSplit)(void*, int, int, void**, void*) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
@@ -74,6 +75,7 @@ static void load_nccl() {
   g_nccl.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))sym("ncclSend");
   g_nccl.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))sym("ncclRecv");
   g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclAllReduce");
+  g_nccl.CommSplit = (int (*)(void*, int, int, void**, void*))dlsym(h, "ncclCommSplit");   // NCCL >= 2.18
   g_nccl.GroupStart = (int (*)())sym("ncclGroupStart");
   g_nccl.GroupEnd = (int (*)())sym("ncclGroupEnd");
   g_nccl.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
@@ -108,6 +110,8 @@ struct Base {
   virtual void dft_update(int group, double time) = 0;
   virtual void reset_fields() = 0;
   virtual void comm_init(const void* id, int nranks, int rank) = 0;
+  virtual void comm_split_from(Base* parent) = 0;
+  void* comm_handle = nullptr;
   virtual void halo_exchange(int group) = 0;
   virtual void field_read(int comp, void* out) = 0;
   virtual void field_write(int comp, const void* in) = 0;
@@ -508,8 +512,20 @@ struct Impl : Base {
           for (int j = 0; j < 3; ++j) m += std::fabs(o.ax[3 * j + i]) * o.r[j];
           o.bmin[i] = o.c[i] - m; o.bmax[i] = o.c[i] + m;
         }
+      } else if (in.kind == KHR_SHAPE_CYLINDER) {
+        // Cylinder(c, r, h, a): size = {radius, height}, axes[0..2] = axis (normalised here);
+        // bounds: c -+ (h/2 |a_i| + r sqrt(1 - a_i^2))
+        if (!(in.size[0] > 0) || !(in.size[1] > 0)) throw std::string("khr_geometry_rasterize: cylinder radius and height must be positive");
+        o.r[0] = in.size[0]; o.r[1] = in.size[1] / 2;
+        double nr = std::sqrt((in.axes[0] * in.axes[0] + in.axes[1] * in.axes[1]) + in.axes[2] * in.axes[2]);
+        if (!(nr > 0)) throw std::string("khr_geometry_rasterize: zero cylinder axis");
+        for (int j = 0; j < 3; ++j) o.ax[j] = in.axes[j] / nr;
+        for (int i = 0; i < 3; ++i) {
+          const double m = o.r[1] * std::fabs(o.ax[i]) + o.r[0] * std::sqrt(std::max(0.0, 1.0 - o.ax[i] * o.ax[i]));
+          o.bmin[i] = o.c[i] - m; o.bmax[i] = o.c[i] + m;
+        }
       } else {
-        throw std::string("khr_geometry_rasterize: shape kind must be KHR_SHAPE_SPHERE or KHR_SHAPE_CUBOID");
+        throw std::string("khr_geometry_rasterize: shape kind must be KHR_SHAPE_SPHERE, KHR_SHAPE_CUBOID or KHR_SHAPE_CYLINDER");
       }
       for (int k = 0; k < 3; ++k) {
         o.val[0][k] = (double)(T)in.eps_inv[k]; o.val[1][k] = (double)(T)in.mu_inv[k];
@@ -788,7 +804,6 @@ struct Impl : Base {
     if (nonuniform) axis_spec = false;
     if (!pdl || g.nranks > 1) sweep = false;
     if (sweep) axis_spec = false;
-    if (in_pair && g.nranks > 1) throw std::string("complex fields (Bloch boundaries) are single-GPU for now: nranks must be 1");
     if (in_pair && chi3) throw std::string("chi3 with complex fields is not supported (|E|^2 couples the real and imaginary parts)");
     // per-axis PML cell sets from both groups' profiles
     std::vector<char> pml[3];
@@ -2044,6 +2059,27 @@ struct Impl : Base {
     const long long st[3] = {1, (long long)PX, (long long)PX * PY};
     for (int a = 0; a < 3; ++a) {
       if (!periodic[a]) continue;
+      if (a == 2 && g.nranks > 1) {
+        // z ring over the ranks: the wrapped planes arrived with the halo exchange of both contexts (H: the top
+        // plane of the last rank in the lower ghost of rank 0; E: the bottom plane of rank 0 in the upper ghost of
+        // the last rank); what is left of Chunking.jl:1735-1764 is the phase on those two ghost planes
+        const double kl = bloch_kl[2];
+        const bool lower = gq == 0 && g.rank == 0, upper = gq == 1 && g.rank == g.nranks - 1;
+        if ((lower || upper) && kl != 0.0) {
+          const double pr = std::cos(lower ? -kl : kl), pi_ = std::sin(lower ? -kl : kl);
+          if (!(pr == 1.0 && pi_ == 0.0)) {
+            const long long off = lower ? 0 : (long long)PX * PY * (N[2] + 1);
+            const long long cnt = (long long)PX * PY;
+            for (int d = 0; d < 2; ++d) {    // the two tangential components that travel
+              T* fr = (gq == 0 ? F[3 + d] : F[d]) + off;
+              T* fi = (gq == 0 ? im->F[3 + d] : im->F[d]) + off;
+              bloch_phase_kernel<T><<<(unsigned)((cnt + 255) / 256), 256, 0, stream>>>(fr, fi, cnt, pr, pi_);
+              ++launches;
+            }
+          }
+        }
+        continue;
+      }
       BlochWrapArgs<T> w;
       for (int d = 0; d < 3; ++d) { w.fr[d] = gq == 0 ? F[3 + d] : F[d]; w.fi[d] = gq == 0 ? im->F[3 + d] : im->F[d]; }
       const int t1 = (a + 1) % 3, t2 = (a + 2) % 3;
@@ -2247,6 +2283,7 @@ struct Impl : Base {
     memcpy(u.b, id, 128);
     CUDA_OK(cudaSetDevice(device));
     NCCL_OK(g_nccl.CommInitRank(&comm, nranks, u, rank));
+    comm_handle = comm;
     // which monitor boxes are cut by a slab boundary?  A rank that holds a strict, non-empty part of a box knows
     // it; one max-all-reduce tells everybody.  Surface integrals over uncut boxes then need no array reduction:
     // the owner's accumulators are the whole box, everybody else's are zero (khr_flux: sum of nf doubles).
@@ -2263,6 +2300,15 @@ struct Impl : Base {
       mon_split = h;
       mon_split_known = true;
     }
+  }
+  // complex fields: the imaginary parts exchange their halo planes on a communicator of their own (same ranks,
+  // ncclCommSplit of the real context's), so the two exchanges of a half-step overlap instead of serialising
+  void comm_split_from(Base* parent) override {
+    if (!parent->comm_handle) throw std::string("khr_comm_init: the real context has no communicator");
+    if (!g_nccl.CommSplit) throw std::string("complex fields on several ranks need ncclCommSplit (NCCL >= 2.18)");
+    CUDA_OK(cudaSetDevice(device));
+    NCCL_OK(g_nccl.CommSplit(parent->comm_handle, 0, g.rank, &comm, nullptr));
+    comm_handle = comm;
   }
   std::vector<int> mon_split;
   bool mon_split_known = false;
@@ -2791,7 +2837,7 @@ int32_t khr_comm_unique_id(void* out128) {
 }
 int32_t khr_comm_init(khr_ctx* ctx, const void* unique_id128, int32_t nranks, int32_t rank) {
   NEED_CTX
-  KHR_TRY(ctx->impl->comm_init(unique_id128, nranks, rank))
+  KHR_TRY({ ctx->impl->comm_init(unique_id128, nranks, rank); if (ctx->impl_im) ctx->impl_im->comm_split_from(ctx->impl); })
 }
 int32_t khr_halo_exchange(khr_ctx* ctx, int32_t group) {
   NEED_CTX

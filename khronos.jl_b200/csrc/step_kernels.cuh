@@ -958,6 +958,17 @@ __global__ void __launch_bounds__(256) bloch_wrap_kernel(const __grid_constant__
   }
 }
 
+// phase factor on one received ghost plane of a complex field (z ring over several ranks): (fr + i fi) *= (pr + i pi),
+// the product in ComplexF64 and the result stored as Complex{T} like bloch_wrap_kernel
+template <class T>
+__global__ void __launch_bounds__(256) bloch_phase_kernel(T* __restrict__ fr, T* __restrict__ fi, long long n, double pr, double pi) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const double vr = (double)fr[q], vi = (double)fi[q];
+  fr[q] = (T)(vr * pr - vi * pi);
+  fi[q] = (T)(vr * pi + vi * pr);
+}
+
 // ----------------------------------------------------------------------------
 // Poynting flux through a monitor plane (FluxMonitor.jl:92-156 get_flux), on the device:
 //   S(f) = sum_cells real(E1 conj(H2) - E2 conj(H1)) * dA

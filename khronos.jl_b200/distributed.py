@@ -30,12 +30,13 @@ def broadcast_unique_id(rank, src=0):
     return bytes(t.cpu().tolist())
 
 
-def gather_fields(sim, comp):
-    """Visualization.jl:294-333 _pull_fields_from_device: global field from the per-rank slabs."""
+def gather_fields(sim, comp, part="real"):
+    """Visualization.jl:294-333 _pull_fields_from_device: global field from the per-rank slabs
+    (part = "real" | "imag" | "complex" for complex fields)."""
     import numpy as np
     import torch.distributed as dist
 
-    local = sim.get_field(comp)
+    local = sim.get_field(comp, part) if part != "real" else sim.get_field(comp)
     if sim.nranks == 1:
         return local
     parts = [None] * sim.nranks

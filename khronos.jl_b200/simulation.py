@@ -161,6 +161,22 @@ class Cuboid:
         return ok
 
 
+class Cylinder:
+    """GeometryPrimitives Cylinder(c, r, h, a): radius r, height h along the axis a (normalised here)."""
+
+    def __init__(self, center, radius, height, axis=(0.0, 0.0, 1.0)):
+        self.center, self.radius, self.height = [float(v) for v in center], float(radius), float(height)
+        a = np.asarray(axis, dtype=np.float64)
+        self.axis = a / np.linalg.norm(a)
+
+    def contains(self, X, Y, Z):
+        c, a = self.center, self.axis
+        d = [X - c[0], Y - c[1], Z - c[2]]
+        p = (d[0] * a[0] + d[1] * a[1]) + d[2] * a[2]
+        q = [d[0] - p * a[0], d[1] - p * a[1], d[2] - p * a[2]]
+        return (np.abs(p) <= self.height / 2) & (((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) <= self.radius ** 2)
+
+
 class Object:
     def __init__(self, shape, material):
         self.shape, self.material = shape, material
@@ -670,8 +686,13 @@ class Simulation:
                 if ob.shape.axes is not None:
                     for k in range(9):
                         o.axes[k] = float(ob.shape.axes.reshape(9)[k])
+            elif isinstance(ob.shape, Cylinder):
+                o.kind = _lib.SHAPE_CYLINDER
+                o.size[0], o.size[1] = ob.shape.radius, ob.shape.height
+                for k in range(3):
+                    o.axes[k] = float(ob.shape.axis[k])
             else:
-                raise _lib.KhronosError("the device rasterizer knows Ball and Cuboid shapes")
+                raise _lib.KhronosError("the device rasterizer knows Ball, Cuboid and Cylinder shapes")
             for k in range(3):
                 o.center[k] = ob.shape.center[k]
                 o.eps_inv[k] = float(T(1) / T(m.epsilon))     # one(T) / T(perm)

@@ -16,7 +16,7 @@ import math
 import numpy as np
 
 from .grid import EX, EY, EZ, HX, HY, HZ
-from .simulation import (Ball, ContinuousWaveSource, Cuboid, DFTMonitor, DrudeSusceptibility, FluxMonitor,
+from .simulation import (PML, Ball, Bloch, ContinuousWaveSource, Cuboid, Cylinder, DFTMonitor, DrudeSusceptibility, FluxMonitor,
                          LorentzianSusceptibility, Material, Object, Simulation, UniformSource)
 
 
@@ -138,7 +138,30 @@ def metalens(nx=512, ny=512, nz=128, res=32, pml_cells=15, pillars=8, rotate=Fal
                 courant=0.55, sources=srcs, monitors=mons, geometry=geom)
 
 
-WORKLOADS = {"dipole": dipole, "waveguide_mode": waveguide_mode, "sphere": sphere, "uled": uled, "metalens": metalens}
+def periodic_bloch(res=20, n_cells=3):
+    """benchmark/periodic_bloch.jl:41-110: n x n supercell of air holes (Cylinder) in an eps = 12 slab, Bloch(k) in
+    x (X point) and y (k = 0), PML in z, Hz point dipole; complex fields.  Reference rows: res 20 / n 1 (20x20x90),
+    res 20 / n 3 (60x60x90), res 30 / n 3."""
+    a, r_hole, t_slab = 1.0, 0.2, 0.5
+    pml_z, buffer_z = 1.0, 1.0
+    cell_z = t_slab + 2 * buffer_z + 2 * pml_z
+    cell_xy = n_cells * a
+    geom = []
+    for ix in range(n_cells):
+        for iy in range(n_cells):
+            geom.append(Object(Cylinder([(ix + 0.5) * a - cell_xy / 2, (iy + 0.5) * a - cell_xy / 2, 0.0], r_hole, t_slab, [0, 0, 1]),
+                               Material(epsilon=1.0)))
+    geom.append(Object(Cuboid([0, 0, 0], [cell_xy + 1.0, cell_xy + 1.0, t_slab]), Material(epsilon=12.0)))
+    kx = 0.5 * 2 * math.pi / a
+    srcs = [UniformSource(ContinuousWaveSource(0.3), HZ, [0.13 * a - cell_xy / 2, 0.27 * a - cell_xy / 2, 0.0], [0, 0, 0])]
+    mons = [DFTMonitor(HZ, [0, 0, 0], [cell_xy, cell_xy, 0], [0.3])]
+    return dict(name="periodic_bloch_res%d_n%d" % (res, n_cells), cell_size=[cell_xy, cell_xy, cell_z], resolution=res,
+                pml=[[0.0, 0.0], [0.0, 0.0], [pml_z, pml_z]], courant=0.5, sources=srcs, monitors=mons, geometry=geom,
+                boundary_conditions=[[Bloch(kx), Bloch(kx)], [Bloch(0.0), Bloch(0.0)], [PML(), PML()]])
+
+
+WORKLOADS = {"dipole": dipole, "waveguide_mode": waveguide_mode, "sphere": sphere, "uled": uled, "metalens": metalens,
+             "periodic_bloch": periodic_bloch}
 
 
 def build_simulation(desc, dtype=np.float32, device=0, rank=0, nranks=1, rasterizer="host", subpixel_smoothing=None,
@@ -146,4 +169,5 @@ def build_simulation(desc, dtype=np.float32, device=0, rank=0, nranks=1, rasteri
     return Simulation(desc["cell_size"], [0.0, 0.0, 0.0], desc["resolution"], desc["sources"], boundaries=desc["pml"],
                       geometry=desc["geometry"], monitors=desc["monitors"], Courant=desc["courant"], dtype=dtype,
                       device=device, rank=rank, nranks=nranks, rasterizer=rasterizer,
-                      subpixel_smoothing=subpixel_smoothing, slab_rule=slab_rule)
+                      subpixel_smoothing=subpixel_smoothing, slab_rule=slab_rule,
+                      boundary_conditions=desc.get("boundary_conditions"))

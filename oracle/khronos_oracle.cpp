@@ -1668,7 +1668,7 @@ void ko_mode_amplitudes(void* hv, int normal_axis, const int* ids4, const double
 // ---------------------------------------------------------------------------
 namespace {
 struct GObj {
-  int kind;            // 0 Sphere, 1 Cuboid
+  int kind;            // 0 Sphere, 1 Cuboid, 2 Cylinder (r[0] radius, r[1] half height, ax[0..2] unit axis)
   double c[3], r[3], ax[9], bmin[3], bmax[3];
   double val[4][3];    // eps_inv, mu_inv, sigma_D, sigma_B per component
 };
@@ -1676,6 +1676,13 @@ struct GObj {
 inline bool g_contains(const GObj& o, const double* x) {
   double d0 = x[0] - o.c[0], d1 = x[1] - o.c[1], d2 = x[2] - o.c[2];
   if (o.kind == 0) return ((d0 * d0 + d1 * d1) + d2 * d2) <= o.r[0] * o.r[0];
+  if (o.kind == 2) {
+    // GeometryPrimitives Cylinder: p = (x - c) . a; abs(p) > h2 -> false; sum(abs2, d - p a) <= r^2
+    double p = (d0 * o.ax[0] + d1 * o.ax[1]) + d2 * o.ax[2];
+    if (std::fabs(p) > o.r[1]) return false;
+    double q0 = d0 - p * o.ax[0], q1 = d1 - p * o.ax[1], q2 = d2 - p * o.ax[2];
+    return ((q0 * q0 + q1 * q1) + q2 * q2) <= o.r[0] * o.r[0];
+  }
   for (int k = 0; k < 3; ++k) {
     double p = (o.ax[3 * k] * d0 + o.ax[3 * k + 1] * d1) + o.ax[3 * k + 2] * d2;
     if (!(std::fabs(p) <= o.r[k])) return false;
@@ -1690,6 +1697,33 @@ inline void g_surfpt(const GObj& o, const double* x, double* sp, double* nout) {
     if (nr == 0.0) { nout[0] = 1.0; nout[1] = 0.0; nout[2] = 0.0; }
     else for (int k = 0; k < 3; ++k) nout[k] = d[k] / nr;
     for (int k = 0; k < 3; ++k) sp[k] = o.c[k] + o.r[0] * nout[k];
+    return;
+  }
+  if (o.kind == 2) {
+    // Cylinder (surfpt_nearby): inside -> the nearer of side wall / end cap; radially outside only -> side wall;
+    // beyond a cap only -> that cap; beyond both -> the rim, normal from the rim point towards x
+    double p = (d[0] * o.ax[0] + d[1] * o.ax[1]) + d[2] * o.ax[2];
+    double q[3] = {d[0] - p * o.ax[0], d[1] - p * o.ax[1], d[2] - p * o.ax[2]};
+    double rho = std::sqrt((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]);
+    double sgp = std::copysign(1.0, p);
+    double dr = o.r[0] - rho, dh = o.r[1] - std::fabs(p);
+    double qh[3] = {0, 0, 0};
+    if (rho > 0.0) { for (int k = 0; k < 3; ++k) qh[k] = q[k] / rho; }
+    else {
+      int j = std::fabs(o.ax[0]) <= std::fabs(o.ax[1]) ? (std::fabs(o.ax[0]) <= std::fabs(o.ax[2]) ? 0 : 2) : (std::fabs(o.ax[1]) <= std::fabs(o.ax[2]) ? 1 : 2);
+      double e[3] = {0, 0, 0};
+      e[j] = 1.0;
+      double pe = o.ax[j], nr = 0.0;
+      for (int k = 0; k < 3; ++k) { qh[k] = e[k] - pe * o.ax[k]; nr += qh[k] * qh[k]; }
+      nr = std::sqrt(nr);
+      for (int k = 0; k < 3; ++k) qh[k] /= nr;
+    }
+    bool inside = dr >= 0.0 && dh >= 0.0;
+    bool side = inside ? (dr < dh) : (dh >= 0.0);
+    bool cap = inside ? !side : (dr >= 0.0);
+    if (side) { for (int k = 0; k < 3; ++k) { sp[k] = o.c[k] + p * o.ax[k] + o.r[0] * qh[k]; nout[k] = qh[k]; } }
+    else if (cap) { for (int k = 0; k < 3; ++k) { sp[k] = x[k] + (o.r[1] * sgp - p) * o.ax[k]; nout[k] = sgp * o.ax[k]; } }
+    else { for (int k = 0; k < 3; ++k) { sp[k] = o.c[k] + o.r[1] * sgp * o.ax[k] + o.r[0] * qh[k]; nout[k] = x[k] - sp[k]; } }
     return;
   }
   double dp[3], ad[3], sg[3], dl[3], shift[3] = {0, 0, 0}, nax[3] = {0, 0, 0};
@@ -1725,6 +1759,11 @@ inline void g_surfpt(const GObj& o, const double* x, double* sp, double* nout) {
 inline bool g_level_nonneg(const GObj& o, const double* x) {
   double d[3] = {x[0] - o.c[0], x[1] - o.c[1], x[2] - o.c[2]};
   if (o.kind == 0) return 1.0 - std::sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]) / o.r[0] >= 0.0;
+  if (o.kind == 2) {
+    double p = (d[0] * o.ax[0] + d[1] * o.ax[1]) + d[2] * o.ax[2];
+    double q0 = d[0] - p * o.ax[0], q1 = d[1] - p * o.ax[1], q2 = d[2] - p * o.ax[2];
+    return 1.0 - std::fmax(std::fabs(p) / o.r[1], std::sqrt((q0 * q0 + q1 * q1) + q2 * q2) / o.r[0]) >= 0.0;
+  }
   double m = 0.0;
   for (int k = 0; k < 3; ++k) {
     double p = (o.ax[3 * k] * d[0] + o.ax[3 * k + 1] * d[1]) + o.ax[3 * k + 2] * d[2];
@@ -1772,6 +1811,16 @@ void rasterize_impl(SimT& S, int nobj, const double* flat, int kinds_mask, int s
       o.r[0] = f[4]; o.r[1] = o.r[2] = 0;
       for (int k = 0; k < 3; ++k) { o.bmin[k] = o.c[k] - o.r[0]; o.bmax[k] = o.c[k] + o.r[0]; }
       for (int k = 0; k < 9; ++k) o.ax[k] = 0;
+    } else if (o.kind == 2) {
+      // Cylinder(c, r, h, a): bounds c -+ (h/2 |a_i| + r sqrt(1 - a_i^2))
+      o.r[0] = f[4]; o.r[1] = f[5] / 2; o.r[2] = 0;
+      double nr = std::sqrt((f[7] * f[7] + f[8] * f[8]) + f[9] * f[9]);
+      for (int k = 0; k < 9; ++k) o.ax[k] = 0;
+      for (int k = 0; k < 3; ++k) o.ax[k] = f[7 + k] / nr;
+      for (int i = 0; i < 3; ++i) {
+        double m = o.r[1] * std::fabs(o.ax[i]) + o.r[0] * std::sqrt(std::max(0.0, 1.0 - o.ax[i] * o.ax[i]));
+        o.bmin[i] = o.c[i] - m; o.bmax[i] = o.c[i] + m;
+      }
     } else {
       bool ident = true;
       for (int k = 0; k < 9; ++k) ident = ident && f[7 + k] == 0.0;
@@ -1930,6 +1979,16 @@ inline void parse_objects(const double* flat, int nobj, std::vector<GObj>& objs)
       o.r[0] = f[4]; o.r[1] = o.r[2] = 0;
       for (int k = 0; k < 3; ++k) { o.bmin[k] = o.c[k] - o.r[0]; o.bmax[k] = o.c[k] + o.r[0]; }
       for (int k = 0; k < 9; ++k) o.ax[k] = 0;
+    } else if (o.kind == 2) {
+      // Cylinder(c, r, h, a): bounds c -+ (h/2 |a_i| + r sqrt(1 - a_i^2))
+      o.r[0] = f[4]; o.r[1] = f[5] / 2; o.r[2] = 0;
+      double nr = std::sqrt((f[7] * f[7] + f[8] * f[8]) + f[9] * f[9]);
+      for (int k = 0; k < 9; ++k) o.ax[k] = 0;
+      for (int k = 0; k < 3; ++k) o.ax[k] = f[7 + k] / nr;
+      for (int i = 0; i < 3; ++i) {
+        double m = o.r[1] * std::fabs(o.ax[i]) + o.r[0] * std::sqrt(std::max(0.0, 1.0 - o.ax[i] * o.ax[i]));
+        o.bmin[i] = o.c[i] - m; o.bmax[i] = o.c[i] + m;
+      }
     } else {
       bool ident = true;
       for (int k = 0; k < 9; ++k) ident = ident && f[7 + k] == 0.0;

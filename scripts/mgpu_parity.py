@@ -38,6 +38,14 @@ def run_case(rank, world, local_rank, comm_id, flags=(), nsteps=120):
         # x and z periodic (z closes the halo ring across ranks), PML on y only
         kw["boundaries"] = [[0.0, 0.0], [1.0, 1.0], [0.0, 0.0]]
         kw["boundary_conditions"] = [[kb.Periodic(), kb.Periodic()], [kb.PML(), kb.PML()], [kb.Periodic(), kb.Periodic()]]
+    bloch = "--bloch" in flags or "--blochz" in flags
+    if bloch:
+        # Bloch boundaries (complex fields, two real contexts per rank): x with k = 1.3 always; --blochz adds a
+        # Bloch-periodic z axis, i.e. the halo ring across the ranks with the phase on the seam ghosts
+        zb = "--blochz" in flags
+        kw["boundaries"] = [[0.0, 0.0], [1.0, 1.0], [0.0, 0.0] if zb else [1.0, 1.0]]
+        kw["boundary_conditions"] = [[kb.Bloch(1.3), kb.Bloch(1.3)], [kb.PML(), kb.PML()],
+                                     [kb.Bloch(-0.7), kb.Bloch(-0.7)] if zb else [kb.PML(), kb.PML()]]
     if "--kerr" in flags:
         # a Kerr block that straddles the rank boundary and overlaps the Drude slab partly
         chi3 = np.zeros(N, dtype=np.float32)
@@ -54,6 +62,7 @@ def run_case(rank, world, local_rank, comm_id, flags=(), nsteps=120):
     sim.step(nsteps)
     sim.sync()
     fields = [kd.gather_fields(sim, c) for c in range(6)]
+    fields_im = [kd.gather_fields(sim, c, part="imag") for c in range(6)] if bloch else None
     dfts = [kd.reduce_dft(sim, m) for m in sim.dft_monitors[:2]]
     flux = sim.get_flux(fm)                    # collective: ncclAllReduce of the four accumulators, then the device reduction
     slabs = sim.slabs
@@ -69,6 +78,10 @@ def run_case(rank, world, local_rank, comm_id, flags=(), nsteps=120):
             b = o.get_field(c)
             num += ((fields[c].astype(np.float64) - b) ** 2).sum()
             den += (b ** 2).sum()
+            if bloch:
+                bi = o.get_field(c, "imag")
+                num += ((fields_im[c].astype(np.float64) - bi) ** 2).sum()
+                den += (bi ** 2).sum()
         err = float((num / den) ** 0.5)
         derr = [float(np.linalg.norm(a - o.get_dft(m)) / np.linalg.norm(o.get_dft(m))) for a, m in zip(dfts, mids[:2])]
         fref = o.flux(fm.normal, mids[2:6])

@@ -19,7 +19,8 @@ def _ngpu():
 
 @pytest.mark.parametrize("world,flags,port", [(2, [], 29611), (2, ["--reference-slabs"], 29612), (2, ["--periodic"], 29613),
                                               (2, ["--kerr"], 29614), (2, ["--nonuniform"], 29615), (4, [], 29616),
-                                              (4, ["--periodic"], 29617)])
+                                              (4, ["--periodic"], 29617), (2, ["--bloch"], 29618), (2, ["--blochz"], 29619),
+                                              (4, ["--blochz"], 29620)])
 def test_multirank_parity(world, flags, port):
     if _ngpu() < world:
         pytest.skip("needs %d GPUs on the box" % world)

@@ -80,6 +80,27 @@ def test_metalens_reduced():
     _against_oracle(w.metalens(nx=96, ny=96, nz=64, res=16, pml_cells=10, pillars=3), 120)
 
 
+def test_periodic_bloch_reduced():
+    """benchmark/periodic_bloch.jl at res 12, 2 x 2 holes (24x24x54): Cylinder holes in a slab, Bloch(k) in x and y
+    (complex fields), PML in z, host raster; fields (real and imaginary parts) and the Hz DFT plane against the oracle."""
+    sim = w.build_simulation(w.periodic_bloch(res=12, n_cells=2), np.float32)
+    o, mids = oracle_from_simulation(sim)
+    sim.prepare_simulation()
+    sim.step(150)
+    sim.sync()
+    o.step(150)
+    num = den = 0.0
+    for c in range(6):
+        for part, which in (("real", "EH"), ("imag", "imag")):
+            a, b = sim.get_field(c, part).astype(np.float64), o.get_field(c, which)
+            num += ((a - b) ** 2).sum()
+            den += (b ** 2).sum()
+    assert den > 0 and (num / den) ** 0.5 < 1e-5, (num / den) ** 0.5
+    # (at the X point of an n-cell supercell exp(i k L) = +-1, so the imaginary parts stay zero in this benchmark;
+    # k values that mix the parts are covered by tests/test_periodic.py and the multi-rank --bloch cases)
+    assert rel_l2(sim.get_dft(sim.dft_monitors[0]), o.get_dft(mids[0])) < 1e-5
+
+
 def test_dipole_float64_reduced():
     _against_oracle(w.dipole(40), 60, dtype=np.float64, tol=1e-12)
 
