@@ -376,13 +376,18 @@ def run_workload(name, args, ctx, steps, warmup, dtype=np.float32, e2e=True, sam
                                "note": "sum of the compulsory bytes of every launch of a step / device time of the step on this rank"}}
         tfile = os.path.join(ROOT, "profiles", "traffic_%s.json" % name)
         if world == 1 and os.path.exists(tfile):
-            # DRAM bytes ncu counted for this kernel (one --set full capture, per launch); used only when the capture
-            # is of the same launch: same kernel name AND same number of thread blocks
+            # DRAM bytes ncu counted for this kernel (one --set full capture, per launch, scripts/ncu_summary.py).  Used only
+            # when the capture is of the same launch: same kernel AND same launch shape.  The persistent TMA kernel always
+            # launches one CTA per SM, so its shape is identified by the number of work items of the table instead.
             try:
-                ent = json.load(open(tfile)).get(dom["name"])
-                if isinstance(ent, dict) and int(ent.get("ctas", -1)) == int(dom["ctas"]):
+                tj = json.load(open(tfile))
+                ent = next((v for k, v in tj.items() if dom["name"].startswith(k)), None)
+                persistent = dom["name"].startswith("halfstep_tma_kernel")
+                same = isinstance(ent, dict) and (int(ent.get("items", -1)) == int(dom["ctas"]) if persistent
+                                                  else int(ent.get("grid", -1)) == int(dom["ctas"]))
+                if same:
                     roof["traffic"] = ent["bytes"]
-                    roof["traffic_source"] = "profiles/traffic_%s.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, %d CTAs)" % (name, dom["ctas"])
+                    roof["traffic_source"] = "profiles/traffic_%s.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)" % name
                     roof["traffic_achieved"] = ent["bytes"] / (avg_ms * 1e-3) / 1e9
                     roof["traffic_frac"] = roof["traffic_achieved"] / peak
             except Exception:

@@ -25,6 +25,9 @@ UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 
 
 def bench_name(kname):
+    m = re.search(r"pml_tma_kernel<(float|double), (?:\(int\))?(\d)", kname)
+    if m:   # the persistent TMA half-step kernel: bench.py's name carries a material suffix, matched by prefix there
+        return "halfstep_tma_kernel<%s,%s,interior+pml" % ("f32" if m.group(1) == "float" else "f64", "HE"[int(m.group(2))])
     m = re.search(r"step_kernel<(float|double), (?:\(int\))?(\d), (?:\(int\))?(\d), (?:\(int\)|\(bool\))?(\d), (?:\(int\))?(\d)"
                   r"(?:, (?:\(bool\))?(\d))?>", kname)
     if not m:
@@ -37,12 +40,22 @@ def bench_name(kname):
 def main():
     rep, out_txt = sys.argv[1], sys.argv[2]
     out_json = sys.argv[3] if len(sys.argv) > 3 else None
+    # optional 4th argument: a bench.py JSON line of the same workload; its per-kernel work-item counts identify the launch
+    # shape of the persistent TMA kernel (whose grid is always one CTA per SM)
+    items = {}
+    if len(sys.argv) > 4:
+        try:
+            bj = json.loads(open(sys.argv[4]).read().strip().splitlines()[-1])
+            items = {k["name"]: int(k["ctas"]) for k in bj["details"]["kernels"]}
+        except Exception:
+            items = {}
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     ik = hdr.index("Kernel Name")
     stall = [i for i, h in enumerate(hdr) if "warps_issue_stalled" in h and h.endswith("_per_issue_active.ratio")]
     traffic = {}
+    grids = {}
     with open(out_txt, "w") as f:
         f.write("# %s  (ncu --set full --clock-control none; per-launch, cold cache, serialised)\n" % rep)
         for r in rows[2:]:
@@ -62,9 +75,19 @@ def main():
                     i = hdr.index(w)
                     tot += float(r[i].replace(",", "")) * UNIT.get(units[i], 1.0)
                 traffic.setdefault(bn, []).append(tot)
+                ig = hdr.index("launch__grid_size") if "launch__grid_size" in hdr else -1
+                if ig >= 0:
+                    grids.setdefault(bn, []).append(int(float(r[ig].replace(",", ""))))
     if out_json:
         with open(out_json, "w") as f:
-            json.dump({k: sum(v) / len(v) for k, v in traffic.items()}, f, indent=1)
+            # per kernel: DRAM bytes per launch and the launch's grid size (bench.py uses the entry only for the same launch shape)
+            out = {}
+            for k, v in traffic.items():
+                out[k] = {"bytes": sum(v) / len(v), "grid": max(grids.get(k, [0])), "captures": len(v)}
+                it = [n for name, n in items.items() if name.startswith(k)]
+                if it:
+                    out[k]["items"] = it[0]
+            json.dump(out, f, indent=1)
     print("wrote", out_txt, out_json or "")
 
 
