@@ -468,7 +468,8 @@ def main_ours(args):
             sys.path.insert(0, os.path.join(ROOT, "scripts"))
             try:
                 from mgpu_parity import run_case
-                extra["parity"] = run_case(rank, world, local_rank, fresh_id())
+                # the same kernels the headline uses: the persistent TMA half-step kernel next to the halo exchange
+                extra["parity"] = run_case(rank, world, local_rank, fresh_id(), flags=("--tma",))
             except Exception as e:
                 extra["parity"] = {"error": str(e)[:300], "ok": False}
     if rank == 0:

@@ -1,7 +1,7 @@
 """Multi-GPU parity: N ranks (torchrun, one per GPU, z slabs + NCCL halo exchange) against the
 single-domain CPU oracle on rank 0.
 
-  torchrun --nproc-per-node N scripts/mgpu_parity.py [--periodic] [--kerr] [--nonuniform] [--reference-slabs]
+  torchrun --nproc-per-node N scripts/mgpu_parity.py [--periodic] [--kerr] [--nonuniform] [--reference-slabs] [--bloch] [--blochz] [--tma]
 
 `run_case` is also what `bench.py --gpus N` calls for its `parity` sub-record and what
 tests/test_gpu_multirank.py spawns under torch.distributed.run.
@@ -56,6 +56,8 @@ def run_case(rank, world, local_rank, comm_id, flags=(), nsteps=120):
         ix, iz = np.arange(N[0]), np.arange(N[2])
         kw["grid_spacing"] = [(0.1 * (1 + 0.25 * np.sin(2 * np.pi * ix / N[0]))).astype(np.float32), None,
                               (0.1 * (1 + 0.2 * np.cos(2 * np.pi * iz / N[2] + 0.7))).astype(np.float32)]
+    if "--tma" in flags:
+        os.environ["KHR_TMA"] = "1"      # the persistent TMA half-step kernel next to the halo exchange (automatic only on large slabs)
     rule = "reference" if "--reference-slabs" in flags else "cost"
     sim = kb.Simulation([4.4, 4.0, 9.6], [0, 0, 0], 10, srcs, rank=rank, nranks=world, device=local_rank, slab_rule=rule, **kw)
     sim.prepare_simulation(comm_id=comm_id)

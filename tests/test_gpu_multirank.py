@@ -20,7 +20,8 @@ def _ngpu():
 @pytest.mark.parametrize("world,flags,port", [(2, [], 29611), (2, ["--reference-slabs"], 29612), (2, ["--periodic"], 29613),
                                               (2, ["--kerr"], 29614), (2, ["--nonuniform"], 29615), (4, [], 29616),
                                               (4, ["--periodic"], 29617), (2, ["--bloch"], 29618), (2, ["--blochz"], 29619),
-                                              (4, ["--blochz"], 29620)])
+                                              (4, ["--blochz"], 29620), (2, ["--tma"], 29621), (2, ["--tma", "--periodic"], 29622),
+                                              (4, ["--tma"], 29623)])
 def test_multirank_parity(world, flags, port):
     if _ngpu() < world:
         pytest.skip("needs %d GPUs on the box" % world)

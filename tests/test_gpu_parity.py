@@ -204,7 +204,7 @@ def test_device_flux_all_normals(normal, dtype):
     host = p.k.get_flux(fm, dft=[p.k.get_dft(m) for m in fm.monitors])
     ora = np.asarray(p.o.flux(normal, p.omon))
     assert rel_l2(dev, host) < 1e-12, (dev, host)
-    assert rel_l2(dev, ora) < TOL[dtype] * (10 if dtype is np.float64 else 1), (dev, ora)
+    assert rel_l2(dev, ora) < TOL[dtype], (dev, ora)
 
 
 def test_device_flux_argument_errors():

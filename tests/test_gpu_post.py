@@ -88,7 +88,7 @@ def test_near2far_matches_oracle(normal, dtype):
         assert dev.shape == ora.shape == (obs.shape[0], 6, 3)
         # per observation point: its six components jointly (single components may vanish by symmetry)
         for io in range(obs.shape[0]):
-            assert rel_l2(dev[io], ora[io]) < 10 * TOL[dtype], (io, rel_l2(dev[io], ora[io]))
+            assert rel_l2(dev[io], ora[io]) < TOL[dtype], (io, rel_l2(dev[io], ora[io]))
 
 
 def test_near2far_theta_phi_grid_and_power():
@@ -119,7 +119,7 @@ def test_mode_overlap_matches_oracle(normal, dtype):
     mode = rng.normal(size=(4, n1, n2, 3)) + 1j * rng.normal(size=(4, n1, n2, 3))
     ap, am = p.k.compute_mode_amplitudes(fm, mode)
     oap, oam, _ = p.o.mode_amplitudes(normal, p.omon, mode)
-    assert rel_l2(ap, oap) < 10 * TOL[dtype] and rel_l2(am, oam) < 10 * TOL[dtype], (ap, oap, am, oam)
+    assert rel_l2(ap, oap) < TOL[dtype] and rel_l2(am, oam) < TOL[dtype], (ap, oap, am, oam)
     # a mode equal to the recorded field itself has a+ = 1 exactly (overlap_plus = 4 P_mode)
     def avg(a):
         a = np.asarray(a, dtype=np.complex128)
@@ -148,6 +148,6 @@ def test_diffraction_orders_match_oracle(dtype):
     want = {(m - 3, n - 3): power[:, m, n] for m in range(7) for n in range(7) if prop[:, m, n].any()}
     assert set(got) == set(want) and len(got) == 5
     scale = max(np.abs(v).max() for v in want.values())
-    tol = 2e-5 if dtype is np.float32 else 1e-11
+    tol = 1e-5 if dtype is np.float32 else 1e-12
     for k in want:
         assert np.max(np.abs(got[k] - want[k])) < tol * scale, (k, got[k], want[k])
