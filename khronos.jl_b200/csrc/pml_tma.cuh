@@ -43,6 +43,16 @@ constexpr int TMA_OBOX = 4096;                // owner box: 1024 cells * 4
 constexpr int TMA_HDR = 128;
 constexpr int TMA_ENTRY = 2 * TMA_ABOX;        // per-tile ring entry: the neighbour planes of Ax, Ay the march starts from
 constexpr int TMA_MAXSTAGES = 6;
+// optional register cap of the persistent kernels (-DKHR_TMA_MAXREG=112: 9 warps x 112 registers would leave room on the SM
+// for one 128-thread MODE 2 CTA).  Measured: no gain, 0.3-1 % slower (profiles/r02_tma_ab.txt r2c19) -> off
+#ifndef KHR_TMA_MAXREG
+#define KHR_TMA_MAXREG 0
+#endif
+#if KHR_TMA_MAXREG > 0
+#define KHR_TMA_BOUNDS __maxnreg__(KHR_TMA_MAXREG)
+#else
+#define KHR_TMA_BOUNDS __launch_bounds__(TMA_THREADS, 1)
+#endif
 
 __host__ __device__ constexpr int tma_stage_bytes(int marr) { return TMA_HDR + 3 * TMA_ABOX + 3 * TMA_OBOX + 6 * TMA_OBOX + (marr == 1 ? 3 * TMA_OBOX : 0); }
 __host__ __device__ constexpr int tma_smem_bytes(int marr, int stages) { return 1024 + 2 * TMA_ENTRY + stages * tma_stage_bytes(marr); }
@@ -429,7 +439,7 @@ __device__ __forceinline__ void tma_producer_finish(uint32_t bars, unsigned char
 // One half-step: interior + PML tiles of one field group.   RAGGED: Nx % 4 != 0
 // ----------------------------------------------------------------------------
 template <class T, int GROUP, bool RAGGED>
-__global__ void __launch_bounds__(TMA_THREADS, 1) pml_tma_kernel(const __grid_constant__ TmaParams<T> p) {
+__global__ void KHR_TMA_BOUNDS pml_tma_kernel(const __grid_constant__ TmaParams<T> p) {
   static_assert(sizeof(T) == 4, "Float32 only");
   extern __shared__ __align__(1024) unsigned char smem[];
   const int S = p.nstages;
@@ -497,7 +507,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) pml_tma_kernel(const __grid_co
 // persistent grid cannot deadlock.  H tiles need E of the previous step only: the previous launch.
 // ----------------------------------------------------------------------------
 template <class T, bool RAGGED>
-__global__ void __launch_bounds__(TMA_THREADS, 1) step_tma_kernel(const __grid_constant__ TmaParams<T> ph, const __grid_constant__ TmaParams<T> pe,
+__global__ void KHR_TMA_BOUNDS step_tma_kernel(const __grid_constant__ TmaParams<T> ph, const __grid_constant__ TmaParams<T> pe,
                                                                    const __grid_constant__ TmaFuse fu) {
   static_assert(sizeof(T) == 4, "Float32 only");
   extern __shared__ __align__(1024) unsigned char smem[];
