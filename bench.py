@@ -127,8 +127,10 @@ class ClockSampler:
 WORKLOAD_DEFAULTS = {
     # name: (rasterizer, subpixel smoothing)
     "sphere": ("device", "anisotropic"), "sphere256": ("device", "anisotropic"), "metalens_full": ("device", None),
-    "metalens": ("device", None), "periodic_bloch": ("device", None),
+    "metalens": ("device", None), "periodic_bloch": ("device", None), "metalens_strong": ("device", None),
 }
+# how a workload grows with the number of ranks: "weak" = the cell is stacked N x along z, "strong" = fixed total size
+WORKLOAD_SCALING = {"sphere": "weak", "sphere256": "weak", "waveguide_mode": "weak", "metalens": "weak", "metalens_full": "weak"}
 
 
 def make_desc(name, nranks, sample_scale=1.0):
@@ -158,6 +160,9 @@ def make_desc(name, nranks, sample_scale=1.0):
             n = max(64, int(round(2048 * sample_scale / 32)) * 32)
             return w.metalens(nx=n, ny=n, nz=max(64, n // 4), res=32, pillars=max(2, int(144 * sample_scale)), rotate=True)
         return w.metalens(nx=2048, ny=2048, nz=512 * nranks, res=32, pillars=144, rotate=True)
+    if name == "metalens_strong":
+        # the fixed 2048 x 2048 x 512 metalens split over the ranks (strong scaling)
+        return w.metalens(nx=2048, ny=2048, nz=512, res=32, pillars=144, rotate=True)
     raise SystemExit("unknown workload " + name)
 
 
@@ -433,6 +438,7 @@ def main_ours(args):
         clocks = sampler.summary(*main["window"])
 
     extra = {}
+    name_of = {}
     if not args.no_extra:
         def fresh_id():
             # every workload gets its own communicator (the context owns it)
@@ -449,19 +455,25 @@ def main_ours(args):
                     "config": r["config"], "e2e": (r["e2e"] or {}).get("value"), "gpu_launches": r["gpu_launches"],
                     "roofline": {k: rf.get(k) for k in ("kernel", "frac", "achieved", "share_of_step", "bytes_vs_reference_model", "whole_step")},
                     "dft_updates_in_window": r["details"]["dft_updates_in_window"], "per_rank": r.get("per_rank"),
+                    "scaling": WORKLOAD_SCALING.get(name_of[id(r)], "strong") if world > 1 else None,
                     "slabs": r["details"]["slabs"] if world > 1 else None}
         if world == 1:
             plan = [("waveguide_mode", np.float32, 400), ("uled", np.float32, 400), ("dipole500", np.float32, 60),
                     ("metalens_full", np.float32, 20), ("sphere", np.float64, 70)]
         else:
-            plan = [("metalens_full", np.float32, 20)]
+            # the other named shapes on N ranks: stacked cells (weak) or the fixed domain cut into N slabs (strong)
+            plan = [("metalens_full", np.float32, 20), ("metalens_strong", np.float32, 40), ("waveguide_mode", np.float32, 200),
+                    ("dipole500", np.float32, 60), ("uled", np.float32, 200)]
         for name, dt_, k in plan:
             key = name + ("_f64" if dt_ is np.float64 else "")
             if name == args.workload and dt_ is dtype:
                 continue
             try:
                 ctx["comm_id"] = fresh_id()
-                extra[key] = short(run_workload(name, args, ctx, k, 5, dt_))
+                r = run_workload(name, args, ctx, k, 5, dt_)
+                if r is not None:
+                    name_of[id(r)] = name
+                extra[key] = short(r)
             except Exception as e:          # an extra line must never take the headline down
                 extra[key] = {"error": str(e)[:300]}
         if world > 1:
