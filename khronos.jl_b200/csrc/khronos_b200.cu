@@ -281,7 +281,7 @@ struct Impl : Base {
   // tables MBASE + m hold the tiles of class m (interior / PML) whose per-voxel material arrays are
   // constant over the tile: they run the MARR = 2 kernels (values in the work item, 12 registers
   // fewer, no material loads) next to the remaining tiles of the class
-  static constexpr int MBASE = 9, NTAB = 2 * MBASE, NSIDE = 12;
+  static constexpr int MBASE = 10, NTAB = 2 * MBASE, NSIDE = 14;   // class 9: MODE 2 tiles outside the PML (AXM = 0 variant)
   bool split_uniform = true;
   // CUDA graph of one time step (single GPU): the kernels of both half-steps on their streams are captured once;
   // per step only the MODE 2 kernel nodes get new parameters (source amplitudes, P^n / P^{n-1} pointers) and the
@@ -296,6 +296,7 @@ struct Impl : Base {
   std::vector<DynNode> dyn_nodes;
   int64_t graph_kernels = 0, graph_replays = 0;
   int plain_steps_done = 0;
+  bool full_nopml = false;   // KHR_FULL_NOPML=1: measured no gain (a second latency-bound launch), profiles/r02_mode2_ab.txt
   int full_split = 2;      // MODE 2 tiles: rows per CTA = tile rows / full_split, threads = 256 / full_split
   // sweep mode (KHR_SWEEP=1): one grid per time step with the interior + PML tiles of both half-steps
   // in z-chunk-major order (sweep_kernel, step_kernels.cuh); needs the chain mode's counters
@@ -315,7 +316,7 @@ struct Impl : Base {
   bool axis_spec = false;  // measured slower on B200 (profiles/r01_axis_spec_pdl_ab.txt): more launches, more tails
   static int side_of(int mm) {
     const int m = mm % MBASE;
-    return (m == 1 ? 0 : m == 2 ? 1 : m == 4 ? 2 : m == 7 ? 3 : m == 8 ? 4 : 5) + (mm >= MBASE ? 6 : 0);
+    return (m == 1 ? 0 : m == 2 ? 1 : m == 4 ? 2 : m == 7 ? 3 : m == 8 ? 4 : m == 9 ? 5 : 6) + (mm >= MBASE ? 7 : 0);
   }
   bool main_heaviest = false;
   // chain mode: all kernels of a step on one stream, launched with programmatic dependent launch;
@@ -374,7 +375,7 @@ struct Impl : Base {
     for (int q = 0; q < NSIDE; ++q) {
       // the PML / full kernels are the critical path of a half-step: their CTAs get the SM slots
       // first, the interior kernel (main stream, default priority) fills what is left
-      CUDA_OK(cudaStreamCreateWithPriority(&side[q], cudaStreamNonBlocking, (use_prio && (q % 6) < 5) ? prio_hi : prio_lo));
+      CUDA_OK(cudaStreamCreateWithPriority(&side[q], cudaStreamNonBlocking, (use_prio && (q % 7) < 6) ? prio_hi : prio_lo));
       CUDA_OK(cudaEventCreateWithFlags(&ev_join[q], cudaEventDisableTiming));
     }
     if (const char* e = getenv("KHR_AXIS_SPEC")) axis_spec = atoi(e) != 0;
@@ -1112,7 +1113,7 @@ struct Impl : Base {
       if (t.items.empty()) return;
       if (k == idx && out) {
         memset(out, 0, sizeof(*out));
-        static const char* mn[MBASE] = {"interior", "pml-x", "pml-y", "", "pml-z", "", "", "pml", "full"};
+        static const char* mn[MBASE] = {"interior", "pml-x", "pml-y", "", "pml-z", "", "", "pml", "full", "full-nopml"};
         snprintf(out->name, sizeof(out->name), "step_kernel<%s,%s,%s,%s>%s", sizeof(T) == 4 ? "f32" : "f64",
                  gq == 0 ? "H" : "E", mn[m % MBASE], m >= MBASE ? "muniform" : (m_arr[gq][0] ? "marr" : "mscalar"),
                  ph == 0 ? "[boundary]" : "");
@@ -1253,6 +1254,7 @@ struct Impl : Base {
       if (const char* e = getenv("KHR_ZSEG_FULL")) zseg_full = std::max(1, atoi(e));
       full_split = 2;
       if (const char* e = getenv("KHR_FULL_SPLIT")) full_split = atoi(e) == 1 ? 1 : 2;
+      if (const char* e = getenv("KHR_FULL_NOPML")) full_nopml = atoi(e) != 0;
       bool local_cuts = true;   // x / y cuts only in the z ranges a box reaches (a point source no longer slices every plane)
       if (const char* e = getenv("KHR_LOCAL_CUTS")) local_cuts = atoi(e) != 0;
       for (auto& Z : zr) {
@@ -1295,7 +1297,9 @@ struct Impl : Base {
                     it.flags |= axm << 4;   // axes whose PML the tile touches (pml_tma.cuh loads only their U / W slabs)
                     set_zmask(it);
                     if (!(axm == 1 || axm == 2 || axm == 4) || !axis_spec) axm = axm ? 7 : 0;
-                    int mode = extras ? 8 : axm;
+                    // optional: MODE 2 tiles outside the PML on the AXM = 0 variant of the full kernel (the cascade folds
+                    // away: 144-184 registers instead of 220-250, no U / W traffic)
+                    int mode = extras ? ((axm == 0 && full_nopml && !nonuniform && !pdl) ? 9 : 8) : axm;
                     int phase = 1;
                     if (g.nranks > 1) {
                       if (gq == 0 && rank_up() >= 0 && zs + zc - 1 == N[2]) phase = 0;
@@ -1332,7 +1336,7 @@ struct Impl : Base {
     if (const char* e = getenv("KHR_TAIL_ZN")) tail_zn = atoi(e);
     if (const char* e = getenv("KHR_SORT_ITEMS")) sort_items = atoi(e);
     for_tables([&](Table& t, int, int, int m) {
-      if (t.items.empty() || m % MBASE == 8) return;
+      if (t.items.empty() || m % MBASE >= 8) return;
       const size_t n = t.items.size();
       std::vector<size_t> idx(n);
       for (size_t q = 0; q < n; ++q) idx[q] = q;
@@ -1401,7 +1405,7 @@ struct Impl : Base {
     if (split_uniform && uniform_tiles && !nonuniform && !pdl) {
       for (int gq = 0; gq < 2; ++gq)
         for (int ph = 0; ph < 2; ++ph)
-          for (int m = 0; m < MBASE - 1; ++m) {   // not the "full" class
+          for (int m = 0; m < 8; ++m) {   // not the "full" classes
             // only the general PML class: its MARR = 1 kernel spills at the 128-register cap, the
             // MARR = 2 one does not (E-PML launch 0.145 -> 0.136 ms on the waveguide); the interior
             // kernel gains nothing from a second launch (measured, profiles/r01_s4_ab_split_uniform.txt)
@@ -1732,10 +1736,10 @@ struct Impl : Base {
     auto push_class = [&](int c) { if (MBASE + c != mmain) order[no++] = MBASE + c; if (c != mmain) order[no++] = c; };
     if (launch_order == 1) {        // PML classes, interior, full last
       for (int c = 7; c >= 1; --c) push_class(c);
-      push_class(0); push_class(8);
+      push_class(0); push_class(9); push_class(8);
     } else if (launch_order == 2) { // PML classes, full, interior
       for (int c = 7; c >= 1; --c) push_class(c);
-      push_class(8); push_class(0);
+      push_class(9); push_class(8); push_class(0);
     } else {                        // full, PML classes, interior
       for (int c = MBASE - 1; c >= 0; --c) push_class(c);
     }
@@ -1765,6 +1769,7 @@ struct Impl : Base {
         case 2: launch_mode<GROUP, 1, 2>(p, mk, n, st); break;
         case 4: launch_mode<GROUP, 1, 4>(p, mk, n, st); break;
         case 8: launch_mode<GROUP, 2, 7>(p, mk, n, st); break;
+        case 9: launch_mode<GROUP, 2, 0>(p, mk, n, st); break;
         default: launch_mode<GROUP, 1, 7>(p, mk, n, st); break;
       }
       if (profiling) {
