@@ -303,6 +303,10 @@ struct Impl : Base {
   bool sweep = false;
   Table sweep_tab;
   Table tab[2][2][NTAB];
+  Table fix_tab[2];   // [group]: tiles outside the PML whose source / pole / Kerr voxels are rewritten by fixup_kernel after the marching kernels
+  // off by default (KHR_FIXUP=1 turns it on): bit-identical, but slower on both workloads it was built for
+  // (uled 46.0 -> 43.2, waveguide_mode 50.6 -> 48.5 Gcells/s, profiles/r02_mode2_ab.txt)
+  bool fixup_on = false, fix_ok[2] = {false, false};
   Table tma_tab[2];   // [group]: interior + PML tiles of phase 1 handled by the persistent TMA kernel (pml_tma.cuh)
   // fused step (KHR_FUSE=1): both half-steps' TMA tiles in one launch, E one z chunk behind H (step_tma_kernel)
   bool tma_fuse = false, skip_tma_launch = false;
@@ -312,7 +316,7 @@ struct Impl : Base {
   unsigned int* d_fuse_cnt = nullptr;
   unsigned long long fuse_epoch = 0;
   cudaStream_t side[NSIDE] = {};
-  cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {};
+  cudaEvent_t ev_fork = nullptr, ev_fix = nullptr, ev_join[NSIDE] = {};
   bool axis_spec = false;  // measured slower on B200 (profiles/r01_axis_spec_pdl_ab.txt): more launches, more tails
   static int side_of(int mm) {
     const int m = mm % MBASE;
@@ -388,6 +392,7 @@ struct Impl : Base {
     if (const char* e = getenv("KHR_TMA_STAGES")) tma_stages_req = atoi(e);
     if (const char* e = getenv("KHR_FUSE")) tma_fuse = atoi(e) != 0;
     if (const char* e = getenv("KHR_GRAPH")) graph_on = atoi(e) != 0;
+    if (const char* e = getenv("KHR_FIXUP")) fixup_on = atoi(e) != 0;
     if (const char* e = getenv("KHR_FUSE_LAG")) fuse_lag = std::max(0, atoi(e));
     if (sweep) { pdl = true; multi_stream = false; }
     if (pdl) multi_stream = false;
@@ -395,6 +400,7 @@ struct Impl : Base {
     *h_err = 0;
     CUDA_OK(cudaHostGetDevicePointer((void**)&d_err, h_err, 0));
     CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&ev_fix, cudaEventDisableTiming));
     if (const char* e = getenv("KHR_MULTI_STREAM")) multi_stream = atoi(e) != 0;
     N[0] = gd.n[0]; N[1] = gd.n[1]; N[2] = gd.nz_local;
     PX = round_up(N[0] + 36, 32);
@@ -420,6 +426,7 @@ struct Impl : Base {
     if (step_gexec) cudaGraphExecDestroy(step_gexec);
     if (step_graph) cudaGraphDestroy(step_graph);
     if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_fix) cudaEventDestroy(ev_fix);
     if (ev_pair_a) cudaEventDestroy(ev_pair_a);
     if (ev_pair_b) cudaEventDestroy(ev_pair_b);
     for (int q = 0; q < NSIDE; ++q) {
@@ -431,6 +438,7 @@ struct Impl : Base {
     for (cudaEvent_t e : halo_ev) cudaEventDestroy(e);
     for (int gq = 0; gq < 2; ++gq) for (cudaEvent_t e : tma_tab[gq].ev) cudaEventDestroy(e);
     for (cudaEvent_t e : fuse_tab.ev) cudaEventDestroy(e);
+    for (int gq = 0; gq < 2; ++gq) for (cudaEvent_t e : fix_tab[gq].ev) cudaEventDestroy(e);
     cudaStreamDestroy(stream); cudaStreamDestroy(comm_stream);
   }
 
@@ -1089,7 +1097,7 @@ struct Impl : Base {
     };
     for_tables([&](Table& t, int, int, int) { one(t); });
     one(sweep_tab);
-    one(tma_tab[0]); one(tma_tab[1]); one(fuse_tab);
+    one(tma_tab[0]); one(tma_tab[1]); one(fuse_tab); one(fix_tab[0]); one(fix_tab[1]);
   }
   void set_profiling(int on) override {
     sync_all();
@@ -1102,6 +1110,7 @@ struct Impl : Base {
       sweep_tab.total_ms = 0; sweep_tab.nlaunch = 0;
       for (int gq = 0; gq < 2; ++gq) { tma_tab[gq].total_ms = 0; tma_tab[gq].nlaunch = 0; }
       fuse_tab.total_ms = 0; fuse_tab.nlaunch = 0;
+      for (int gq = 0; gq < 2; ++gq) { fix_tab[gq].total_ms = 0; fix_tab[gq].nlaunch = 0; }
       halo_wait_ms = 0; halo_exchanges = 0;
     }
   }
@@ -1127,6 +1136,18 @@ struct Impl : Base {
       }
       ++k;
     });
+    for (int gq = 0; gq < 2; ++gq) {
+      Table& t = fix_tab[gq];
+      if (t.items.empty()) continue;
+      if (k == idx && out) {
+        memset(out, 0, sizeof(*out));
+        snprintf(out->name, sizeof(out->name), "fixup_kernel<%s,%s,sources+ade>", sizeof(T) == 4 ? "f32" : "f64", gq == 0 ? "H" : "E");
+        out->launches = t.nlaunch; out->total_ms = t.total_ms; out->cells_per_launch = t.cells;
+        out->alg_bytes_per_launch = 0; out->ref_model_bytes_per_launch = 0;
+        out->ctas = (int64_t)t.items.size(); out->uniform_ctas = t.uniform_items;
+      }
+      ++k;
+    }
     if (tma_fuse && !fuse_tab.items.empty()) {
       if (k == idx && out) {
         memset(out, 0, sizeof(*out));
@@ -1238,6 +1259,12 @@ struct Impl : Base {
       if (tma_on) zseg = 4;
       if (const char* e = getenv("KHR_ZSEG")) zseg = std::max(1, atoi(e));
     }
+    // Source / pole / Kerr voxels outside the PML: the tile runs as a plain interior tile and fixup_kernel rewrites those
+    // voxels afterwards (step_kernels.cuh).  Not with conductive media (the sigma_D stage sits inside the cascade), not on
+    // several ranks (the boundary plane would need its own fix-up before the halo send), not in the chain / sweep / fused /
+    // graph modes.
+    for (int gq = 0; gq < 2; ++gq)
+      fix_ok[gq] = fixup_on && !has_sd[gq] && g.nranks == 1 && !pdl && !sweep && !tma_fuse && !graph_on;
     auto set_zmask = [&](WorkItem& it) {
       it.zmask = 0;
       for (int q = 0; q < it.zn && q < 31; ++q)
@@ -1300,6 +1327,7 @@ struct Impl : Base {
                     // optional: MODE 2 tiles outside the PML on the AXM = 0 variant of the full kernel (the cascade folds
                     // away: 144-184 registers instead of 220-250, no U / W traffic)
                     int mode = extras ? ((axm == 0 && full_nopml && !nonuniform && !pdl) ? 9 : 8) : axm;
+                    if (extras && axm == 0 && fix_ok[gq]) { mode = 0; it.flags |= 8; }   // interior tile + fix-up of its special voxels
                     int phase = 1;
                     if (g.nranks > 1) {
                       if (gq == 0 && rank_up() >= 0 && zs + zc - 1 == N[2]) phase = 0;
@@ -1401,6 +1429,16 @@ struct Impl : Base {
       }
     });
     CUDA_OK(cudaStreamSynchronize(stream));
+    for (int gq = 0; gq < 2; ++gq) {
+      fix_tab[gq] = Table();
+      for (auto& it : tab[gq][1][0].items)
+        if (it.flags & 8) fix_tab[gq].items.push_back(it);
+      if (fix_tab[gq].items.empty()) continue;
+      const size_t bytes = fix_tab[gq].items.size() * sizeof(WorkItem);
+      fix_tab[gq].d = (WorkItem*)dalloc((bytes + sizeof(T) - 1) / sizeof(T), false);
+      CUDA_OK(cudaMemcpyAsync(fix_tab[gq].d, fix_tab[gq].items.data(), bytes, cudaMemcpyHostToDevice, stream));
+      for (auto& it : fix_tab[gq].items) { fix_tab[gq].cells += (int64_t)it.xw * it.yh * it.zn; fix_tab[gq].uniform_items += (it.flags & 2) ? 1 : 0; }
+    }
     // move the constant-material tiles of the interior / PML classes into their own tables
     if (split_uniform && uniform_tiles && !nonuniform && !pdl) {
       for (int gq = 0; gq < 2; ++gq)
@@ -1778,13 +1816,37 @@ struct Impl : Base {
       }
       if (st != stream) { CUDA_OK(cudaEventRecord(ev_join[side_of(m)], st)); used[m] = true; }
     }
-    if (phase == 1 && tma_on && !skip_tma_launch && !tma_tab[GROUP].items.empty()) {
+    const bool tma_here = phase == 1 && tma_on && !skip_tma_launch && !tma_tab[GROUP].items.empty();
+    if (phase == 1 && !fix_tab[GROUP].items.empty() && !tma_here) {
+      // the fix-up pass depends only on the two interior tables (its tiles ran there as plain interior tiles): it
+      // follows them on a stream of theirs, next to the PML launches, instead of after the join of the whole group
+      const int m0 = 0, m1 = MBASE;
+      const bool has0 = !tab[GROUP][phase][m0].items.empty(), has1 = !tab[GROUP][phase][m1].items.empty();
+      auto st_of = [&](int m) { return (m == mmain || !multi_stream || serial_prof) ? stream : side[side_of(m)]; };
+      cudaStream_t s0 = st_of(m0), s1 = st_of(m1);
+      const int mf = (has0 && s0 != stream) ? m0 : (has1 && s1 != stream) ? m1 : (has0 ? m0 : m1);
+      cudaStream_t fs = (has0 || has1) ? st_of(mf) : stream;
+      const int mo = mf == m0 ? m1 : m0;
+      if ((mo == m0 ? has0 : has1) && st_of(mo) != fs) {
+        if (st_of(mo) == stream) {
+          CUDA_OK(cudaEventRecord(ev_fix, stream));
+          CUDA_OK(cudaStreamWaitEvent(fs, ev_fix, 0));
+        } else {
+          CUDA_OK(cudaStreamWaitEvent(fs, ev_join[side_of(mo)], 0));
+        }
+      }
+      launch_fixup<GROUP>(p, fs);
+      if (fs != stream) { CUDA_OK(cudaEventRecord(ev_join[side_of(mf)], fs)); used[mf] = true; }
+    }
+    if (tma_here) {
       // the persistent half-step kernel goes last, on the main stream: the small launches above have their
       // CTAs placed first, its 148 CTAs take the SMs as they become free and claim work dynamically
       Table& t = tma_tab[GROUP];
       timed(t, true);
       launch_tma<GROUP>(p, t, stream);
       timed(t, false);
+      // with the TMA kernel the fix-up tiles ran inside it: the pass follows it in stream order
+      if (!fix_tab[GROUP].items.empty()) launch_fixup<GROUP>(p, stream);
     }
     for (int m = 0; m < NTAB; ++m)
       if (used[m]) CUDA_OK(cudaStreamWaitEvent(stream, ev_join[side_of(m)], 0));
@@ -1988,6 +2050,27 @@ struct Impl : Base {
     if (gq == 1) for (auto& pl : poles) pl.cur = 1 - pl.cur;
     epochs[gq] += 1;
   }
+  template <int GROUP>
+  void launch_fixup(StepParams<T>& p, cudaStream_t st) {
+    Table& t = fix_tab[GROUP];
+    if (t.items.empty()) return;
+    p.items = t.d;
+    const int n = (int)t.items.size();
+    const bool marr = m_arr[GROUP][0] != nullptr;
+    int maxc = 1;
+    for (auto& it : t.items) maxc = std::max(maxc, it.xw * it.yh * it.zn);
+    const dim3 grid((unsigned)n, (unsigned)((maxc + 255) / 256));
+    timed(t, true, st);
+    if (nonuniform) {
+      if (marr) fixup_kernel<T, GROUP, 1, true><<<grid, 256, 0, st>>>(p);
+      else fixup_kernel<T, GROUP, 0, true><<<grid, 256, 0, st>>>(p);
+    } else {
+      if (marr) fixup_kernel<T, GROUP, 1, false><<<grid, 256, 0, st>>>(p);
+      else fixup_kernel<T, GROUP, 0, false><<<grid, 256, 0, st>>>(p);
+    }
+    timed(t, false, st);
+    ++launches;
+  }
   void half_step_launch(int gq, StepParams<T>& p) {
     bool marr = m_arr[gq][0] != nullptr;
     if (marr && (!m_arr[gq][1] || !m_arr[gq][2])) throw std::string("per-voxel material needs all three components");
@@ -2117,14 +2200,15 @@ struct Impl : Base {
     CUDA_OK(cudaLaunchKernelEx(&cfg, sweep_kernel<T, MH, ME>, ph, pe, (const WorkItem*)sweep_tab.d));
     ++launches;
   }
-  void timed(Table& t, bool begin) {
+  void timed(Table& t, bool begin, cudaStream_t st = nullptr) {
     if (!profiling) return;
+    if (!st) st = stream;
     if (begin) {
       if (t.ev_used + 2 > t.ev.size())
         for (int q = 0; q < 2; ++q) { cudaEvent_t e; CUDA_OK(cudaEventCreate(&e)); t.ev.push_back(e); }
-      CUDA_OK(cudaEventRecord(t.ev[t.ev_used], stream));
+      CUDA_OK(cudaEventRecord(t.ev[t.ev_used], st));
     } else {
-      CUDA_OK(cudaEventRecord(t.ev[t.ev_used + 1], stream));
+      CUDA_OK(cudaEventRecord(t.ev[t.ev_used + 1], st));
       t.ev_used += 2;
     }
   }

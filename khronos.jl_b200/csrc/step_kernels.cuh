@@ -807,6 +807,125 @@ __global__ void __launch_bounds__(CTA, (min_ctas<T, 1, 7>())) sweep_kernel(const
 }
 
 // ----------------------------------------------------------------------------
+// Fix-up of the source / dispersive / Kerr voxels OUTSIDE the PML (round 2).  The marching kernels run such tiles as
+// plain interior tiles (MODE 0, or the TMA kernel) and this kernel then rewrites the affected voxels with exactly the
+// arithmetic of the MODE 2 path for them, which never used the marched value there anyway: the flux field is kept on
+// those voxels like the reference keeps D / B (Kernels.jl:315,371; Helpers.jl:332-338), so
+//     D <- D + K,   E = eps^-1 ((D + S) - P),   Kerr correction (Dispersive.jl:127-148),   ADE update (Dispersive.jl:25-88)
+// need only the curl operand (untouched during the half-step), D / the source flux slot, S and P — not the marched E.
+// One thread per voxel, high occupancy; the latency-bound 250-register MODE 2 launch then only
+// remains for tiles inside the PML and for conductive media.  Voxels without a source or pole are left alone.
+// ----------------------------------------------------------------------------
+template <class T, int GROUP, int MARR, bool NU>
+__global__ void __launch_bounds__(256) fixup_kernel(const __grid_constant__ StepParams<T> p) {
+  constexpr int IC = (GROUP == 0) ? 1 : -1;
+  const WorkItem it = p.items[blockIdx.x];
+  const int ncell = it.xw * it.yh * it.zn;
+  const T* __restrict__ A0 = p.A[0];
+  const T* __restrict__ A1 = p.A[1];
+  const T* __restrict__ A2 = p.A[2];
+  // one voxel per thread, blockIdx.y walks the tile in slices of 256 voxels: enough independent threads in flight to
+  // hide the dependent loads (a per-thread loop over the tile measured 5x slower, profiles/r02_mode2_ab.txt)
+  for (int q = blockIdx.y * blockDim.x + threadIdx.x; q < ncell; q += gridDim.y * blockDim.x) {
+    const int ix = it.x0 + q % it.xw, iy = it.y0 + (q / it.xw) % it.yh, iz = it.z0 + q / (it.xw * it.yh);
+    const long long fo = p.plane * (long long)iz + (long long)p.px * iy + (ix + XO);
+    const long long mo = p.mplane * (long long)(iz - 1) + (long long)p.mpx * (iy - 1) + (ix - 1);
+    // ---- what lives on this voxel ----
+    T su[3] = {T(0), T(0), T(0)}, pu[3] = {T(0), T(0), T(0)};
+    int sslot[3] = {-1, -1, -1};
+    bool disp = false;
+    if (it.flags & 1) {
+      for (int s_ = 0; s_ < p.nsrc; ++s_) {
+        const SrcDesc<T>& s = p.src_ext ? p.src_ext[s_] : p.src[s_];
+        const int lx = ix - s.s[0], ly = iy - s.s[1], lz = iz - s.s[2];
+        if (lx < 0 || lx >= s.d[0] || ly < 0 || ly >= s.d[1] || lz < 0 || lz >= s.d[2]) continue;
+        const size_t ai = 2 * ((size_t)lx + (size_t)s.d[0] * ((size_t)ly + (size_t)s.d[1] * (size_t)lz));
+        const T are = s.amp[ai], aim = s.amp[ai + 1];
+        su[s.comp] += s.an_re * are - s.an_im * aim;      // S = real(a(t) A[x]) (Sources.jl:355-356)
+        sslot[s.comp] = s.slot[ai >> 1];
+      }
+    }
+    T c3 = T(0);
+    unsigned polmask = 0;
+    if constexpr (GROUP == 1) {
+      if (p.chi3 != nullptr) { c3 = p.chi3[mo]; disp |= (c3 != T(0)); }
+      for (int k = 0; k < p.npole; ++k) {
+        const PoleDesc<T>& pl = p.pole_ext ? p.pole_ext[k] : p.pole[k];
+        if (pl.sigma[mo] != T(0)) {
+          polmask |= 1u << k;
+          disp = true;
+#pragma unroll
+          for (int d = 0; d < 3; ++d) pu[d] += pl.Pc[d][mo];
+        }
+      }
+    }
+    if (!disp && sslot[0] < 0 && sslot[1] < 0 && sslot[2] < 0) continue;
+    // ---- K = dt * curl, the expression and operation order of step_body ----
+    const T dt = p.dt;
+    T idx_ = p.idl[0], idy_ = p.idl[1], idz_ = p.idl[2];
+    if constexpr (NU) { idx_ = p.idv[0][ix - 1]; idy_ = p.idv[1][iy - 1]; idz_ = p.idv[2][iz - 1]; }
+    const T ax0 = A0[fo], ay0 = A1[fo], az0 = A2[fo];
+    const T ay_z = A1[fo + IC * p.plane], ax_z = A0[fo + IC * p.plane];
+    const T az_y = A2[fo + IC * p.px], ax_y = A0[fo + IC * p.px];
+    const T azx = A2[fo + IC], ayx = A1[fo + IC];
+    T ku[3];
+    ku[0] = dt * (idz_ * (ay_z - ay0) - idy_ * (az_y - az0));
+    ku[1] = dt * (idx_ * (azx - az0) - idz_ * (ax_z - ax0));
+    ku[2] = dt * (idy_ * (ax_y - ax0) - idx_ * (ayx - ay0));
+    T f[3];
+    bool touched[3] = {false, false, false};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      T mm;
+      if constexpr (MARR == 1) mm = (it.flags & 2) ? (T)it.mu[d] : p.m_arr[d][mo];
+      else mm = p.m_inv;
+      if constexpr (GROUP == 1) {
+        if (disp) {
+          const T d_new = p.Dst[d][mo] + ku[d];
+          T net = d_new;
+          net += su[d];
+          net -= pu[d];
+          f[d] = mm * net;
+          p.Dst[d][mo] = d_new;
+          touched[d] = true;
+          continue;
+        }
+      }
+      if (sslot[d] >= 0) {
+        const T t_new = p.Tsrc[sslot[d]] + ku[d];
+        T net = t_new;
+        net += su[d];
+        f[d] = mm * net;
+        p.Tsrc[sslot[d]] = t_new;
+        touched[d] = true;
+      }
+    }
+    if constexpr (GROUP == 1) {
+      if (c3 != T(0)) {   // Kerr: the three components at the same array index (Dispersive.jl:127-148); disp => all touched
+        const T e_sq = (f[0] * f[0] + f[1] * f[1]) + f[2] * f[2];
+        const T corr = T(1) / (T(1) + c3 * e_sq);
+        f[0] = f[0] * corr; f[1] = f[1] * corr; f[2] = f[2] * corr;
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      if (touched[d]) p.F[d][fo] = f[d];
+    if constexpr (GROUP == 1) {
+      for (int k = 0; k < p.npole; ++k) {
+        if (!((polmask >> k) & 1u)) continue;
+        const PoleDesc<T>& pl = p.pole_ext ? p.pole_ext[k] : p.pole[k];
+        const T sg = pl.sigma[mo];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const T pc = pl.Pc[d][mo], pp = pl.Pp[d][mo];
+          pl.Pp[d][mo] = pl.g1i * ((pl.cp * pc - pl.g1 * pp) + pl.cd * sg * f[d]);
+        }
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
 // Planner helper (runs once in khr_finalize_plan): marks the work items over which all three
 // per-voxel constitutive arrays are bit-wise constant, and records the values.  Such tiles
 // (most of a piecewise-homogeneous scene) skip the three material loads per plane; the

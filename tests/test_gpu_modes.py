@@ -90,6 +90,8 @@ MODES = [
     dict(KHR_GRAPH=1, KHR_TMA=1),
     dict(KHR_FULL_NOPML=1),
     dict(KHR_FULL_NOPML=1, KHR_FULL_SPLIT=1, KHR_ZSEG_FULL=2),
+    dict(KHR_FIXUP=1),
+    dict(KHR_FIXUP=1, KHR_TMA=1),
     dict(KHR_LOCAL_CUTS=0),
     dict(KHR_LOCAL_CUTS=0, KHR_TMA=1),
 ]
