@@ -1,7 +1,7 @@
 """Multi-GPU parity: N ranks (torchrun, one per GPU, z slabs + NCCL halo exchange) against the
 single-domain CPU oracle on rank 0.
 
-  torchrun --nproc-per-node N scripts/mgpu_parity.py [--periodic] [--kerr] [--nonuniform] [--reference-slabs] [--bloch] [--blochz] [--tma]
+  torchrun --nproc-per-node N scripts/mgpu_parity.py [--periodic] [--kerr] [--nonuniform] [--reference-slabs] [--bloch] [--blochz] [--tma] [--thin]
 
 `run_case` is also what `bench.py --gpus N` calls for its `parity` sub-record and what
 tests/test_gpu_multirank.py spawns under torch.distributed.run.
@@ -25,14 +25,20 @@ def run_case(rank, world, local_rank, comm_id, flags=(), nsteps=120):
     from khronos_b200 import distributed as kd
 
     rng = np.random.default_rng(1234)
-    N = (44, 40, 96)
+    # --thin: 36 z cells, 10 of them PML at either end -> with 4 ranks every slab is 9 planes and the end slabs lie
+    # entirely inside the z PML (what the 280x280x100 uled cell looks like on 8 ranks)
+    thin = "--thin" in flags
+    nz = 36 if thin else 96
+    N = (44, 40, nz)
     eps = [(1.0 / rng.uniform(1.0, 4.0, N)).astype(np.float32) for _ in range(3)]
     sg = np.zeros(N, dtype=np.float32)
-    sg[:, :, 40:56] = 1.5          # a Drude slab that straddles the rank boundary for 2 ranks
+    sg[:, :, nz // 2 - 8:nz // 2 + 8] = 1.5          # a Drude slab that straddles the rank boundary for 2 ranks
     srcs = [kb.UniformSource(kb.ContinuousWaveSource(1.0), kb.EZ, [0, 0, 0.05], [0, 0, 0]),
-            kb.UniformSource(kb.ContinuousWaveSource(1.2), kb.HY, [0.3, 0, -1.0], [1.0, 1.0, 0])]
-    fm = kb.FluxMonitor([0.6, 0, 0], [0, 2.0, 7.0], [1.0, 1.1], 2)     # x-normal plane through every slab
-    mons = [kb.DFTMonitor(kb.EX, [0, 0, 0], [0, 3, 9.6], [1.0, 1.2], 2), kb.DFTMonitor(kb.HZ, [0, 0.2, 1.0], [3, 0, 6.0], [1.0], 1), fm]
+            kb.UniformSource(kb.ContinuousWaveSource(1.2), kb.HY, [0.3, 0, -0.5 if thin else -1.0], [1.0, 1.0, 0])]
+    Lz = nz / 10.0
+    fm = kb.FluxMonitor([0.6, 0, 0], [0, 2.0, 3.0 if thin else 7.0], [1.0, 1.1], 2)     # x-normal plane through every slab
+    mons = [kb.DFTMonitor(kb.EX, [0, 0, 0], [0, 3, Lz], [1.0, 1.2], 2),
+            kb.DFTMonitor(kb.HZ, [0, 0.2, 0.3 if thin else 1.0], [3, 0, 2.4 if thin else 6.0], [1.0], 1), fm]
     kw = dict(boundaries=[[1.0, 1.0]] * 3, monitors=mons, eps_inv=eps, poles=[(0.0, 0.3, sg)])
     if "--periodic" in flags:
         # x and z periodic (z closes the halo ring across ranks), PML on y only
@@ -59,7 +65,7 @@ def run_case(rank, world, local_rank, comm_id, flags=(), nsteps=120):
     if "--tma" in flags:
         os.environ["KHR_TMA"] = "1"      # the persistent TMA half-step kernel next to the halo exchange (automatic only on large slabs)
     rule = "reference" if "--reference-slabs" in flags else "cost"
-    sim = kb.Simulation([4.4, 4.0, 9.6], [0, 0, 0], 10, srcs, rank=rank, nranks=world, device=local_rank, slab_rule=rule, **kw)
+    sim = kb.Simulation([4.4, 4.0, Lz], [0, 0, 0], 10, srcs, rank=rank, nranks=world, device=local_rank, slab_rule=rule, **kw)
     sim.prepare_simulation(comm_id=comm_id)
     sim.step(nsteps)
     sim.sync()
@@ -72,7 +78,7 @@ def run_case(rank, world, local_rank, comm_id, flags=(), nsteps=120):
     out = None
     if rank == 0:
         from bridge import oracle_from_simulation
-        whole = kb.Simulation([4.4, 4.0, 9.6], [0, 0, 0], 10, srcs, **kw)
+        whole = kb.Simulation([4.4, 4.0, Lz], [0, 0, 0], 10, srcs, **kw)
         o, mids = oracle_from_simulation(whole)
         o.step(nsteps)
         num = den = 0.0
@@ -88,8 +94,8 @@ def run_case(rank, world, local_rank, comm_id, flags=(), nsteps=120):
         derr = [float(np.linalg.norm(a - o.get_dft(m)) / np.linalg.norm(o.get_dft(m))) for a, m in zip(dfts, mids[:2])]
         fref = o.flux(fm.normal, mids[2:6])
         ferr = float(np.linalg.norm(flux - fref) / np.linalg.norm(fref))
-        out = dict(case="44x40x96 f32, eps per voxel, Drude slab across the seam, 2 sources, 2 DFT boxes + 1 flux plane, %d steps%s"
-                        % (nsteps, (" " + " ".join(flags)) if flags else ""),
+        out = dict(case="44x40xNZ f32, eps per voxel, Drude slab across the seam, 2 sources, 2 DFT boxes + 1 flux plane, %d steps%s"
+                        .replace("NZ", str(nz)) % (nsteps, (" " + " ".join(flags)) if flags else ""),
                    world=world, slabs=[list(s) for s in slabs], field_rel_l2=err, dft_rel_l2=derr, flux_rel_l2=ferr,
                    tolerance=1e-5, ok=bool(err < 1e-5 and max(derr) < 1e-5 and ferr < 1e-5))
     return out

@@ -21,7 +21,7 @@ def _ngpu():
                                               (2, ["--kerr"], 29614), (2, ["--nonuniform"], 29615), (4, [], 29616),
                                               (4, ["--periodic"], 29617), (2, ["--bloch"], 29618), (2, ["--blochz"], 29619),
                                               (4, ["--blochz"], 29620), (2, ["--tma"], 29621), (2, ["--tma", "--periodic"], 29622),
-                                              (4, ["--tma"], 29623)])
+                                              (4, ["--tma"], 29623), (4, ["--thin"], 29624), (2, ["--thin", "--tma"], 29625)])
 def test_multirank_parity(world, flags, port):
     if _ngpu() < world:
         pytest.skip("needs %d GPUs on the box" % world)
