@@ -805,6 +805,17 @@ struct Impl : Base {
     return b[0] <= x1 && b[3] >= x0 && b[1] <= y1 && b[4] >= y0 && b[2] <= z1 && b[5] >= z0;
   }
   static int lx_index(int w) { return w >= 96 ? 2 : (w >= 48 ? 1 : 0); }
+  // tile shape (0 / 1 / 2 = 32x32 / 64x16 / 128x8) that covers a w x h cell with the fewest tiles; the wider one on a tie
+  static int best_shape(int w, int h) {
+    int best = 2; long long nb = -1;
+    for (int si = 2; si >= 0; --si) {
+      const int tw = 32 << si, th = 32 >> si;
+      const long long n = (long long)((w + tw - 1) / tw) * ((h + th - 1) / th);
+      if (nb < 0 || n < nb) { nb = n; best = si; }
+    }
+    return best;
+  }
+  bool plan_fill = true;
 
   void finalize() override {
     if (finalized) throw std::string("khr_finalize_plan called twice");
@@ -1078,6 +1089,23 @@ struct Impl : Base {
     };
     for_tables([&](Table& t, int gq, int, int) { one(t, gq); });
     one(tma_tab[0], 0); one(tma_tab[1], 1);
+    if (getenv("KHR_PLAN_DUMP")) {
+      // planner statistics: plane iterations (a CTA spends one iteration per plane of an item, whatever the item's
+      // footprint) and how full the 1024-voxel planes are
+      auto dump = [&](const char* what, Table& t, int gq, int m) {
+        if (t.items.empty()) return;
+        long long iters = 0, vox = 0, hist[4] = {0, 0, 0, 0};
+        for (auto& it : t.items) {
+          iters += it.zn; vox += (long long)it.xw * it.yh * it.zn;
+          const double f = (double)it.xw * it.yh / 1024.0;
+          hist[f > 0.95 ? 3 : f > 0.7 ? 2 : f > 0.45 ? 1 : 0] += it.zn;
+        }
+        fprintf(stderr, "[plan] %s group %d class %d: %zu items, %lld plane iterations, fill %.3f (iterations at <=45%% / <=70%% / <=95%% / full: %lld %lld %lld %lld)\n",
+                what, gq, m, t.items.size(), iters, (double)vox / (1024.0 * iters), hist[0], hist[1], hist[2], hist[3]);
+      };
+      for_tables([&](Table& t, int gq, int ph, int m) { if (ph == 1) dump("ldg", t, gq, m); });
+      dump("tma", tma_tab[0], 0, -1); dump("tma", tma_tab[1], 1, -1);
+    }
   }
 
   template <class F>
@@ -1284,6 +1312,7 @@ struct Impl : Base {
       if (const char* e = getenv("KHR_FULL_NOPML")) full_nopml = atoi(e) != 0;
       bool local_cuts = true;   // x / y cuts only in the z ranges a box reaches (a point source no longer slices every plane)
       if (const char* e = getenv("KHR_LOCAL_CUTS")) local_cuts = atoi(e) != 0;
+      if (const char* e = getenv("KHR_PLAN_FILL")) plan_fill = atoi(e) != 0;
       for (auto& Z : zr) {
         // the z ranges are already cut at the z faces of every box, so a box either spans Z or misses it
         std::vector<int> cx, cyv;
@@ -1294,12 +1323,33 @@ struct Impl : Base {
           cyv.push_back(bx.b[1]); cyv.push_back(bx.b[4] + 1);
         }
         const std::vector<Range> xr = split_ranges(xr0, cx), yr = split_ranges(yr0, cyv);
+        // (x range, y range) cells of this z range.  plan_fill (default): the y cuts of a box apply only to the x ranges
+        // the box reaches, and every cell takes the tile shape that covers it with the fewest tiles — a CTA spends the
+        // same time on a plane of a tile whatever part of its 1024 voxels is inside the cell (KHR_PLAN_DUMP=1 prints
+        // the fill; profiles/r02_plan_fill_ab.txt)
+        struct Cell { Range X, Y; int lxi; };
+        std::vector<Cell> cells;
+        if (!plan_fill) {
+          for (auto& Y : yr)
+            for (auto& X : xr) cells.push_back({X, Y, lx_index(X.e - X.s + 1)});
+        } else {
+          for (auto& X : xr) {
+            std::vector<int> cy;
+            for (auto& bx : boxes) {
+              if (local_cuts && (bx.b[2] > Z.e || bx.b[5] < Z.s)) continue;
+              if (bx.b[0] > X.e || bx.b[3] < X.s) continue;
+              cy.push_back(bx.b[1]); cy.push_back(bx.b[4] + 1);
+            }
+            for (auto& Y : split_ranges(yr0, cy)) cells.push_back({X, Y, best_shape(X.e - X.s + 1, Y.e - Y.s + 1)});
+          }
+          std::stable_sort(cells.begin(), cells.end(), [](const Cell& a, const Cell& b) { return a.Y.s != b.Y.s ? a.Y.s < b.Y.s : a.X.s < b.X.s; });
+        }
         for (int z0 = Z.s; z0 <= Z.e; z0 += zseg) {
           int zn = std::min(zseg, Z.e - z0 + 1);
           ++chunk;
-          for (auto& Y : yr)
-            for (auto& X : xr) {
-              int lxi = lx_index(X.e - X.s + 1);
+          for (auto& cl : cells) {
+              const Range &X = cl.X, &Y = cl.Y;
+              int lxi = cl.lxi;
               int lx = 8 << lxi;
               int tw = 4 * lx, th = CTA / lx;
               for (int y0 = Y.s; y0 <= Y.e; y0 += th) {
